@@ -1,0 +1,77 @@
+"""oracle/make_golden.py -- TEST INFRASTRUCTURE ONLY.
+
+Generates tests/golden/*.npz by running the UNMODIFIED reference
+(oracle/_ref/ref_driver, built by `make -C oracle ref` from /root/reference).
+Run in the build container (needs /root/reference to have been compiled):
+
+    python oracle/make_golden.py
+
+The fixtures are the parity anchor for both the C restatement (oracle_pa.c) and the
+CUDA path; the GPU box has no /root/reference, so they are committed.
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import refio  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(refio.HERE), "tests", "golden")
+
+# name -> ref_driver arguments.  Sizes are kept tiny: every array on the path is stored.
+CASES = {
+    # BP3-style diffusion, Gauss-Legendre Q = p+2 (bench_ceed.cpp:121)
+    "diff3d_p1_n3": dict(dim=3, n=3, p=1, kind="diffusion"),
+    "diff3d_p2_n3": dict(dim=3, n=3, p=2, kind="diffusion"),
+    "diff3d_p3_n2": dict(dim=3, n=2, p=3, kind="diffusion"),
+    "diff3d_p4_n3": dict(dim=3, n=3, p=4, kind="diffusion"),
+    "diff3d_p4_n234": dict(dim=3, n=2, ny=3, nz=4, p=4, kind="diffusion"),
+    "diff3d_p5_n2": dict(dim=3, n=2, p=5, kind="diffusion"),
+    "diff3d_p6_n2": dict(dim=3, n=2, p=6, kind="diffusion"),
+    "diff3d_p7_n2": dict(dim=3, n=2, p=7, kind="diffusion"),
+    "diff3d_p8_n2": dict(dim=3, n=2, p=8, kind="diffusion"),
+    "diff3d_p3_n2_curved": dict(dim=3, n=2, p=3, kind="diffusion", curved=1),
+    # ex1 -o 3 default rule (order 2p+dim-1 => Q = p+2 as well) on a lexicographic mesh
+    "diff3d_p3_n3_nosfc": dict(dim=3, n=3, p=3, kind="diffusion", sfc=0),
+    # BP1-style mass
+    "mass3d_p1_n3": dict(dim=3, n=3, p=1, kind="mass"),
+    "mass3d_p2_n2": dict(dim=3, n=2, p=2, kind="mass"),
+    "mass3d_p4_n2": dict(dim=3, n=2, p=4, kind="mass"),
+    "mass3d_p6_n2": dict(dim=3, n=2, p=6, kind="mass"),
+    "mass3d_p8_n2": dict(dim=3, n=2, p=8, kind="mass"),
+    "mass3d_p3_n2_curved": dict(dim=3, n=2, p=3, kind="mass", curved=1),
+    # BP5-style collocated GLL diffusion (Q = p+1, B = I)
+    "bp5_3d_p2_n3": dict(dim=3, n=3, p=2, kind="diffusion", quad="gll"),
+    "bp5_3d_p4_n2": dict(dim=3, n=2, p=4, kind="diffusion", quad="gll"),
+    "bp5_3d_p7_n2": dict(dim=3, n=2, p=7, kind="diffusion", quad="gll"),
+    "bp5_3d_p7_n2_curved": dict(dim=3, n=2, p=7, kind="diffusion", quad="gll", curved=1),
+    # 2D
+    "diff2d_p1_n4": dict(dim=2, n=4, p=1, kind="diffusion"),
+    "diff2d_p3_n3": dict(dim=2, n=3, p=3, kind="diffusion"),
+    "diff2d_p4_n3_curved": dict(dim=2, n=3, p=4, kind="diffusion", curved=1),
+    "diff2d_p8_n2": dict(dim=2, n=2, p=8, kind="diffusion"),
+    "mass2d_p2_n3": dict(dim=2, n=3, p=2, kind="mass"),
+    "mass2d_p5_n2_curved": dict(dim=2, n=2, p=5, kind="mass", curved=1),
+    "bp5_2d_p6_n2": dict(dim=2, n=2, p=6, kind="diffusion", quad="gll"),
+}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    if not refio.have_ref_driver():
+        raise SystemExit("oracle/_ref/ref_driver missing: run `make -C oracle ref` first")
+    total = 0
+    for name, kw in CASES.items():
+        d = refio.run_dump(rtol=1e-8, **kw)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **d)
+        sz = os.path.getsize(path)
+        total += sz
+        print(f"{name:28s} NE={int(d['NE'][0]):4d} ndofs={int(d['ndofs'][0]):6d} "
+              f"pcg_iters={int(d['pcg_iters'][0]):4d} {sz/1024:8.1f} KiB")
+    print(f"total {total/1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,437 @@
+// oracle/ref_driver.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Driver that runs the UNMODIFIED reference (MFEM, compiled by oracle/Makefile into
+// oracle/_ref/libmfem_ref.a) through its own public API on the partial-assembly hot
+// path and (a) dumps every table / vector on that path as a parity fixture, or
+// (b) times the reference's CPU path (cpu_baseline and `bench.py --impl reference`).
+//
+// It is the generator of tests/golden/*.npz (via oracle/make_golden.py) and the
+// "reference" arm of bench.py.  Nothing in mfem_b200/ links or calls it.
+//
+// Reference entry points exercised (file:line under /root/reference):
+//   Mesh::MakeCartesian2D/3D                 mesh/mesh.cpp:4776,4786
+//   H1_FECollection / FiniteElementSpace     fem/fe_coll.hpp, fem/fespace.cpp:356
+//   ElementRestriction (ctor, Mult, MultT)   fem/restriction.cpp:26,116,159
+//   DofToQuad (TENSOR)                       fem/fe/fe_base.cpp:2697
+//   GeometricFactors                         mesh/mesh.cpp:15420
+//   internal::PADiffusionSetup               fem/integ/bilininteg_diffusion_kernels.cpp:107
+//   Diffusion/MassIntegrator::AssemblePA,
+//     AddMultPA, AssembleDiagonalPA          fem/integ/bilininteg_{diffusion,mass}_pa.cpp
+//   BilinearForm (PARTIAL) Mult/AssembleDiagonal/FormLinearSystem
+//                                            fem/bilinearform_ext.cpp:332,370,476,487
+//   OperatorJacobiSmoother, CGSolver         linalg/solvers.cpp:324,869
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+// The PA data of the integrators is private in the reference; the dump needs to read it.
+#define private public
+#define protected public
+#include "mfem.hpp"
+#include "fem/integ/bilininteg_diffusion_kernels.hpp"
+#undef private
+#undef protected
+
+using namespace mfem;
+using std::string;
+
+// ---- tiny binary container: [name:32][dtype:1 ('i','d','l')][count:int64][payload] ----
+struct Dump
+{
+   FILE *f;
+   explicit Dump(const char *path) : f(fopen(path, "wb"))
+   {
+      if (!f) { perror(path); exit(2); }
+   }
+   ~Dump() { fclose(f); }
+   void put(const char *name, char dt, int64_t n, const void *p, size_t esz)
+   {
+      char nm[32]; memset(nm, 0, 32); strncpy(nm, name, 31);
+      fwrite(nm, 1, 32, f); fwrite(&dt, 1, 1, f); fwrite(&n, 8, 1, f);
+      if (n) { fwrite(p, esz, n, f); }
+   }
+   void ints(const char *n, const int *p, int64_t c) { put(n, 'i', c, p, 4); }
+   void dbls(const char *n, const double *p, int64_t c) { put(n, 'd', c, p, 8); }
+   void ints(const char *n, const Array<int> &a) { a.HostRead(); ints(n, a.GetData(), a.Size()); }
+   void dbls(const char *n, const Vector &v) { v.HostRead(); dbls(n, v.GetData(), v.Size()); }
+   void dbls(const char *n, const Array<real_t> &v) { v.HostRead(); dbls(n, v.GetData(), v.Size()); }
+   void scalar(const char *n, int v) { ints(n, &v, 1); }
+   void scalar(const char *n, double v) { dbls(n, &v, 1); }
+};
+
+struct Args
+{
+   std::map<string, string> kv;
+   Args(int argc, char **argv, int first)
+   {
+      for (int i = first; i + 1 < argc; i += 2)
+      {
+         string k = argv[i];
+         if (k.rfind("--", 0) == 0) { k = k.substr(2); }
+         kv[k] = argv[i + 1];
+      }
+   }
+   int geti(const string &k, int d) const
+   { auto it = kv.find(k); return it == kv.end() ? d : atoi(it->second.c_str()); }
+   double getd(const string &k, double d) const
+   { auto it = kv.find(k); return it == kv.end() ? d : atof(it->second.c_str()); }
+   string gets(const string &k, const string &d) const
+   { auto it = kv.find(k); return it == kv.end() ? d : it->second; }
+};
+
+// C5's curved mesh: Q3 nodes displaced by a smooth map.
+static void curve_map(const Vector &x, Vector &y)
+{
+   const double a = 0.05, tp = 2 * M_PI;
+   y = x;
+   if (x.Size() == 3)
+   {
+      y(0) += a * sin(tp * x(1)) * sin(tp * x(2));
+      y(1) += a * sin(tp * x(0)) * sin(tp * x(2));
+      y(2) += a * sin(tp * x(0)) * sin(tp * x(1));
+   }
+   else
+   {
+      y(0) += a * sin(tp * x(1));
+      y(1) += a * sin(tp * x(0));
+   }
+}
+
+struct Problem
+{
+   int dim, n, p, nz;
+   bool mass, gll, curved, sfc;
+   Mesh mesh;
+   H1_FECollection *fec = nullptr;
+   FiniteElementSpace *fes = nullptr;
+   const IntegrationRule *ir = nullptr;
+   IntegrationRules gll_rules{0, Quadrature1D::GaussLobatto};
+   ConstantCoefficient one{1.0};
+   BilinearForm *a = nullptr;
+   BilinearFormIntegrator *bfi = nullptr;
+
+   Problem(const Args &A)
+   {
+      dim = A.geti("dim", 3); n = A.geti("n", 2); p = A.geti("p", 2);
+      nz = A.geti("nz", n);
+      mass = A.gets("kind", "diffusion") == "mass";
+      gll = A.gets("quad", "gl") == "gll";
+      curved = A.geti("curved", 0) != 0;
+      sfc = A.geti("sfc", 1) != 0;
+      const int ny = A.geti("ny", n);
+      string meshfile = A.gets("mesh", "");
+      if (!meshfile.empty())
+      {
+         mesh = Mesh(meshfile.c_str(), 1, 1);
+         int ref = A.geti("refine", 0);
+         for (int l = 0; l < ref; l++) { mesh.UniformRefinement(); }
+         dim = mesh.Dimension();
+      }
+      else if (dim == 3)
+      {
+         mesh = Mesh::MakeCartesian3D(n, ny, nz, Element::HEXAHEDRON, 1.0, 1.0, 1.0, sfc);
+      }
+      else
+      {
+         mesh = Mesh::MakeCartesian2D(n, ny, Element::QUADRILATERAL, false, 1.0, 1.0, sfc);
+      }
+      if (curved) { mesh.SetCurvature(A.geti("node_order", 3)); mesh.Transform(curve_map); }
+      fec = new H1_FECollection(p, dim);
+      fes = new FiniteElementSpace(&mesh, fec);
+      const Geometry::Type g = dim == 3 ? Geometry::CUBE : Geometry::SQUARE;
+      // bench_ceed.cpp:121,133-137 : GL order 2p+3 (Q=p+2) or GLL order 2p-1 (Q=p+1)
+      const int q_extra = A.geti("qorder", -1);
+      if (gll) { ir = &gll_rules.Get(g, q_extra >= 0 ? q_extra : 2 * p - 1); }
+      else { ir = &IntRules.Get(g, q_extra >= 0 ? q_extra : 2 * p + 3); }
+      a = new BilinearForm(fes);
+      a->SetAssemblyLevel(AssemblyLevel::PARTIAL);
+      if (mass) { bfi = new MassIntegrator(one, ir); }
+      else { bfi = new DiffusionIntegrator(one, ir); }
+      a->AddDomainIntegrator(bfi);
+   }
+   ~Problem() { delete a; delete fes; delete fec; }
+};
+
+static double now()
+{
+   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static int do_dump(const Args &A, const char *out)
+{
+   Problem P(A);
+   Dump D(out);
+   P.a->Assemble();
+   FiniteElementSpace &fes = *P.fes;
+   const FiniteElement &fe = *fes.GetTypicalFE();
+   const DofToQuad &maps = fe.GetDofToQuad(*P.ir, DofToQuad::TENSOR);
+   const int D1D = maps.ndof, Q1D = maps.nqpt, NE = fes.GetNE(), ndofs = fes.GetNDofs();
+   const int dim = P.dim;
+   D.scalar("dim", dim); D.scalar("n", P.n); D.scalar("p", P.p);
+   D.scalar("D1D", D1D); D.scalar("Q1D", Q1D); D.scalar("NE", NE); D.scalar("ndofs", ndofs);
+   D.scalar("is_mass", (int)P.mass); D.scalar("is_gll", (int)P.gll); D.scalar("curved", (int)P.curved);
+
+   // --- a1: restriction tables
+   auto R = dynamic_cast<const ElementRestriction *>(
+               fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC));
+   const Table &e2d = fes.GetElementToDofTable();
+   D.ints("elem_dof", e2d.GetJ(), (int64_t)NE * fe.GetDof());
+   auto tfe = dynamic_cast<const TensorBasisElement *>(&fe);
+   D.ints("dof_map", tfe->GetDofMap());
+   D.ints("gather_map", R->GatherMap());
+   D.ints("offsets", R->Offsets());
+   D.ints("indices", R->Indices());
+
+   // --- a12: basis tables
+   D.dbls("B", maps.B); D.dbls("G", maps.G); D.dbls("Bt", maps.Bt); D.dbls("Gt", maps.Gt);
+   D.dbls("W", P.ir->GetWeights());
+   {
+      // 1D points of the dof basis and the quadrature rule (for checking our generators)
+      const IntegrationRule &ir1 = (P.gll ? P.gll_rules : IntRules).Get(Geometry::SEGMENT, P.ir->GetOrder());
+      Vector qp(ir1.GetNPoints()), qw(ir1.GetNPoints());
+      for (int i = 0; i < ir1.GetNPoints(); i++) { qp(i) = ir1.IntPoint(i).x; qw(i) = ir1.IntPoint(i).weight; }
+      D.dbls("qpts1d", qp); D.dbls("qwts1d", qw);
+      const double *gl = poly1d.ClosedPoints(P.p, BasisType::GaussLobatto);
+      D.dbls("dofpts1d", gl, P.p + 1);
+   }
+
+   // --- a21: mesh nodes and geometric factors
+   P.mesh.EnsureNodes();
+   const GridFunction *nodes = P.mesh.GetNodes();
+   const FiniteElementSpace *nfes = nodes->FESpace();
+   const Operator *nR = nfes->GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC);
+   Vector nodesE(nR->Height());
+   nR->Mult(*nodes, nodesE);
+   const int nodeD1D = nfes->GetTypicalFE()->GetOrder() + 1;
+   D.scalar("node_D1D", nodeD1D);
+   D.dbls("nodesE", nodesE); // (nodeD1D^dim, dim, NE)
+   {
+      const DofToQuad &nm = nfes->GetTypicalFE()->GetDofToQuad(*P.ir, DofToQuad::TENSOR);
+      D.dbls("Bn", nm.B); D.dbls("Gn", nm.G);
+   }
+   const GeometricFactors *geom = P.mesh.GetGeometricFactors(
+                                     *P.ir, GeometricFactors::JACOBIANS | GeometricFactors::DETERMINANTS);
+   D.dbls("J", geom->J); D.dbls("detJ", geom->detJ);
+
+   // --- a6/a9: quadrature data
+   Vector pa_data;
+   if (P.mass) { pa_data = static_cast<MassIntegrator *>(P.bfi)->pa_data; }
+   else { pa_data = static_cast<DiffusionIntegrator *>(P.bfi)->pa_data; }
+   D.dbls("pa_data", pa_data);
+   if (!P.mass)
+   {
+      // the seam itself, with a constant and a spatially varying matrix coefficient
+      const int NQ = P.ir->GetNPoints();
+      Vector c1(1); c1 = 1.0;
+      Vector d2(NQ * (dim == 3 ? 6 : 3) * NE);
+      internal::PADiffusionSetup(dim, dim, D1D, Q1D, 1, NE, P.ir->GetWeights(), geom->J, c1, d2);
+      D.dbls("pa_data_seam", d2);
+      const int cd = dim == 3 ? 6 : 3;
+      Vector cm(cd * NQ * NE);
+      srand(7);
+      for (int i = 0; i < NQ * NE; i++)
+      {
+         // SPD-ish symmetric matrix coefficient, storage (11,12,13,22,23,33) / (11,12,22)
+         double r[6]; for (int k = 0; k < 6; k++) { r[k] = rand() / (RAND_MAX + 1.0); }
+         if (dim == 3)
+         {
+            cm(0 + cd * i) = 2 + r[0]; cm(1 + cd * i) = 0.3 * r[1]; cm(2 + cd * i) = 0.3 * r[2];
+            cm(3 + cd * i) = 2 + r[3]; cm(4 + cd * i) = 0.3 * r[4]; cm(5 + cd * i) = 2 + r[5];
+         }
+         else
+         {
+            cm(0 + cd * i) = 2 + r[0]; cm(1 + cd * i) = 0.3 * r[1]; cm(2 + cd * i) = 2 + r[3];
+         }
+      }
+      Vector d3(NQ * cd * NE);
+      internal::PADiffusionSetup(dim, dim, D1D, Q1D, cd, NE, P.ir->GetWeights(), geom->J, cm, d3);
+      D.dbls("coeff_matrix", cm); D.dbls("pa_data_matrix", d3);
+      // vector (diagonal) coefficient
+      Vector cv(dim * NQ * NE);
+      for (int i = 0; i < cv.Size(); i++) { cv(i) = 1 + rand() / (RAND_MAX + 1.0); }
+      Vector d4(NQ * cd * NE);
+      internal::PADiffusionSetup(dim, dim, D1D, Q1D, dim, NE, P.ir->GetWeights(), geom->J, cv, d4);
+      D.dbls("coeff_vector", cv); D.dbls("pa_data_vector", d4);
+   }
+
+   // --- a2/a3/a7/a10: operator action pieces on x = Randomize(1)
+   Vector x(ndofs); x.Randomize(1);
+   D.dbls("x", x);
+   Vector xE(R->Height()), yE(R->Height());
+   R->Mult(x, xE);
+   D.dbls("xE", xE);
+   yE = 0.0;
+   P.bfi->AddMultPA(xE, yE);
+   D.dbls("yE", yE);
+   Vector yRt(ndofs);
+   R->MultTranspose(yE, yRt);
+   D.dbls("y_RtyE", yRt);
+   Vector y(ndofs);
+   P.a->Mult(x, y);
+   D.dbls("y", y);
+   D.scalar("y_norml2", y.Norml2());
+   {
+      Vector t(ndofs);
+      R->AbsMultTranspose(xE, t);
+      D.dbls("absmultT_xE", t);
+      Vector t2(ndofs); t2.Randomize(3);
+      R->AddMultTranspose(xE, t2);
+      D.dbls("addmultT_xE_seed3", t2);
+   }
+
+   // --- a8/a11: diagonal
+   Vector diagE(R->Height()); diagE = 0.0;
+   P.bfi->AssembleDiagonalPA(diagE);
+   D.dbls("diagE", diagE);
+   Vector diag(ndofs);
+   P.a->AssembleDiagonal(diag);
+   D.dbls("diag", diag);
+
+   // --- a14-a17: constrained system + PCG/Jacobi  (ex1.cpp:165-267)
+   Array<int> ess_bdr(P.mesh.bdr_attributes.Max()); ess_bdr = 1;
+   Array<int> ess;
+   fes.GetEssentialTrueDofs(ess_bdr, ess);
+   D.ints("ess_tdof_list", ess);
+   LinearForm b(&fes);
+   b.AddDomainIntegrator(new DomainLFIntegrator(P.one));
+   b.Assemble();
+   D.dbls("b", b);
+   GridFunction u(&fes); u = 0.0;
+   OperatorPtr Aop; Vector B, X;
+   P.a->FormLinearSystem(ess, u, b, Aop, X, B);
+   D.dbls("B_rhs", B);
+   {
+      Vector cy(ndofs);
+      Aop->Mult(x, cy); // ConstrainedOperator::Mult on the random vector
+      D.dbls("y_constrained", cy);
+   }
+   const double rtol = A.getd("rtol", 1e-8);
+   const int maxit = A.geti("maxit", 2000);
+   const int use_prec = A.geti("jacobi", 1);
+   OperatorJacobiSmoother M(*P.a, ess);
+   {
+      Vector t(ndofs), jr(ndofs);
+      t.Randomize(5);
+      M.Mult(t, jr);
+      D.dbls("jacobi_in_seed5", t); D.dbls("jacobi_out", jr);
+   }
+   CGSolver cg;
+   cg.SetRelTol(rtol); cg.SetAbsTol(0.0); cg.SetMaxIter(maxit);
+   cg.SetOperator(*Aop);
+   if (use_prec) { cg.SetPreconditioner(M); }
+   // capture the (B r, r) history through the print stream
+   std::stringstream hist;
+   std::streambuf *old = mfem::out.rdbuf(hist.rdbuf());
+   cg.SetPrintLevel(1);
+   X = 0.0;
+   cg.Mult(B, X);
+   mfem::out.rdbuf(old);
+   std::vector<double> h;
+   {
+      string line;
+      while (std::getline(hist, line))
+      {
+         size_t pos = line.find("(B r, r) =");
+         if (pos != string::npos) { h.push_back(atof(line.c_str() + pos + 10)); }
+      }
+   }
+   D.dbls("pcg_history", h.data(), h.size());
+   D.scalar("pcg_iters", cg.GetNumIterations());
+   D.scalar("pcg_converged", (int)cg.GetConverged());
+   D.scalar("pcg_final_norm", (double)cg.GetFinalNorm());
+   D.scalar("pcg_rtol", rtol);
+   D.scalar("pcg_jacobi", use_prec);
+   D.dbls("X_sol", X);
+   std::printf("dump %s: dim=%d NE=%d p=%d D1D=%d Q1D=%d ndofs=%d |y|=%.17g pcg_iters=%d\n",
+               out, dim, NE, P.p, D1D, Q1D, ndofs, y.Norml2(), cg.GetNumIterations());
+   return 0;
+}
+
+// Timing of the reference CPU path.  Prints one JSON object.
+//   mode=mult : y = A x (BilinearForm::Mult, PA) repeated `reps` times
+//   mode=pcg  : bench_ceed.cpp BP style: CG (optionally Jacobi), fixed `iters` iterations
+static int do_bench(const Args &A)
+{
+   const string mode = A.gets("mode", "pcg");
+   const int reps = A.geti("reps", 3), iters = A.geti("iters", 32);
+   const int use_prec = A.geti("jacobi", 0);
+   double t0 = now();
+   Problem P(A);
+   P.a->Assemble();
+   FiniteElementSpace &fes = *P.fes;
+   const int ndofs = fes.GetNDofs();
+   double t_setup = now() - t0;
+   Vector x(ndofs), y(ndofs);
+   x.UseDevice(true); y.UseDevice(true);
+   x.Randomize(1);
+   double sec = 0, ynorm = 0; int its = 0;
+   if (mode == "mult")
+   {
+      P.a->Mult(x, y); // warm-up
+      double t1 = now();
+      for (int i = 0; i < reps; i++) { P.a->Mult(x, y); }
+      sec = (now() - t1) / reps; its = 1;
+      ynorm = y.Norml2();
+   }
+   else
+   {
+      Array<int> ess_bdr(P.mesh.bdr_attributes.Max()); ess_bdr = 1;
+      Array<int> ess;
+      fes.GetEssentialTrueDofs(ess_bdr, ess);
+      LinearForm b(&fes);
+      b.AddDomainIntegrator(new DomainLFIntegrator(P.one));
+      b.Assemble();
+      GridFunction u(&fes); u = 0.0;
+      OperatorPtr Aop; Vector B, X;
+      P.a->FormLinearSystem(ess, u, b, Aop, X, B);
+      OperatorJacobiSmoother M(*P.a, ess);
+      CGSolver cg;
+      cg.SetRelTol(0.0); cg.SetAbsTol(0.0); cg.SetMaxIter(iters); cg.SetPrintLevel(-1);
+      cg.SetOperator(*Aop);
+      if (use_prec) { cg.SetPreconditioner(M); }
+      double best = 1e300;
+      for (int r = 0; r < reps; r++)
+      {
+         X = 0.0;
+         double t1 = now();
+         cg.Mult(B, X);
+         double t = now() - t1;
+         best = std::min(best, t);
+         sec += t;
+      }
+      sec /= reps; its = cg.GetNumIterations();
+      ynorm = X.Norml2();
+   }
+   const char *dev = getenv("MFEM_DEVICE");
+   std::printf("{\"mode\": \"%s\", \"ndofs\": %d, \"ne\": %d, \"p\": %d, \"iters\": %d, "
+               "\"seconds\": %.6e, \"setup_seconds\": %.3f, \"dofs_iters_per_s\": %.6e, "
+               "\"norm\": %.17g, \"device\": \"%s\"}\n",
+               mode.c_str(), ndofs, fes.GetNE(), P.p, its, sec, t_setup,
+               (double)ndofs * its / sec, ynorm, dev ? dev : "cpu");
+   return 0;
+}
+
+int main(int argc, char **argv)
+{
+   if (argc < 2)
+   {
+      std::fprintf(stderr, "usage: ref_driver dump <out.bin> [--key val ...] | bench [--key val ...]\n");
+      return 1;
+   }
+   const char *dev = getenv("MFEM_DEVICE"); // "omp" uses all host threads (device.cpp:145)
+   Device device(dev ? dev : "cpu");
+   string cmd = argv[1];
+   if (cmd == "dump") { Args A(argc, argv, 3); return do_dump(A, argv[2]); }
+   if (cmd == "bench") { Args A(argc, argv, 2); return do_bench(A); }
+   std::fprintf(stderr, "unknown command %s\n", cmd.c_str());
+   return 1;
+}
