@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- CEED BP GDOF/s (DOFs x CG iterations / s) of the B200 partial-assembly path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--bp 1|3|5] [--p P] [--n ELEMS_PER_SIDE_PER_GPU] [--iters I]
+
+One "step" = one BP solve: Jacobi-preconditioned CG with a FIXED number of iterations
+(rel_tol = 0, the protocol of tests/benchmarks/bench_ceed.cpp:222-243) on a synthetic
+structured hex mesh of the unit cube, all-boundary Dirichlet, RHS (1, phi_i), x0 = 0.
+Default workload (BASELINE.json configs[2], the config the metric is quoted on at one
+GPU): BP3 diffusion, p = 4, Q = 6, 133^3 elements = 151.4 M dofs.  With --gpus N > 1
+(configs[3]) each rank owns a 116^3-element block (100.5 M dofs / GPU, weak scaling) of a
+2x1x1 / 2x2x1 / 2x2x2 Cartesian partition; shared dofs go over NCCL send/recv and the PCG
+dot products over ncclAllReduce.
+
+Prints ONE JSON line (rank 0).  `value`: device-resident solves, CUDA-event timed, max
+over ranks.  `e2e`: the same solves through the public API with HOST buffers -- the RHS
+is copied from pinned host memory and the solution copied back inside the timed region.
+`roofline`: the fused operator kernel alone (CUDA events recorded around each of its
+launches inside the timed region) against MEASURED_PEAKS.json's HBM copy bandwidth.
+`cpu_baseline`: the unmodified reference's CPU PA path (oracle/_ref/ref_driver, OpenMP
+device over all host cores) on a bounded sample of the same workload.
+
+--impl reference times that reference CPU path alone (the oracle side: the only place
+besides tests/ and smoke() that executes anything under oracle/).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "CEED BP GDOF/s (DOFs x CG iterations / s), PA + PCG/Jacobi"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--bp", type=int, default=3, choices=[1, 3, 5])
+    ap.add_argument("--p", type=int, default=None)
+    ap.add_argument("--n", type=int, default=None, help="elements per side per GPU")
+    ap.add_argument("--iters", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-n", type=int, default=None, help="elements per side of the CPU sample")
+    return ap.parse_args()
+
+
+def workload(a):
+    p = a.p or {1: 4, 3: 4, 5: 7}[a.bp]
+    if a.n:
+        n = a.n
+    elif a.gpus == 1:
+        n = {1: round((50e6) ** (1 / 3) / p), 3: 133 if p == 4 else round((150e6) ** (1 / 3) / p),
+             5: round((99e6) ** (1 / 3) / p)}[a.bp]
+    else:
+        n = round((100e6) ** (1 / 3) / p)
+    grid = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[a.gpus]
+    kind = {1: "mass", 3: "diffusion", 5: "diffusion"}[a.bp]
+    q = p + 1 if a.bp == 5 else p + 2
+    return dict(bp=a.bp, p=p, n=n, grid=grid, kind=kind, q1d=q, d1d=p + 1, gll=(a.bp == 5))
+
+
+def alg_bytes_per_apply(w, ne, nd):
+    """fused L->L operator, stored D, int32 gather index."""
+    k = 1 if w["kind"] == "mass" else 6
+    return (k * w["q1d"] ** 3 * 8 + 4 * w["d1d"] ** 3) * ne + 16 * nd
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "", 1).isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names)
+                   if any(len(r) > 4 + k and r[4 + k].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "reasons": reasons}
+
+
+def ref_driver_path():
+    p = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    return p if os.path.isfile(p) and os.access(p, os.X_OK) else None
+
+
+def run_reference(w, n_cpu, iters, reps):
+    """The unmodified reference's CPU PA path on all host cores (MFEM_DEVICE=omp), or the C
+    oracle port on one core when oracle/_ref was not built."""
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        pass
+    drv = ref_driver_path()
+    if drv:
+        env = dict(os.environ, MFEM_DEVICE="omp", OMP_NUM_THREADS=str(cores), OMP_PROC_BIND="true")
+        cmd = [drv, "bench", "--mode", "pcg", "--dim", "3", "--n", str(n_cpu), "--p", str(w["p"]),
+               "--kind", w["kind"], "--quad", "gll" if w["gll"] else "gl", "--iters", str(iters),
+               "--reps", str(reps), "--jacobi", "1"]
+        out = subprocess.run(cmd, check=True, stdout=subprocess.PIPE, env=env).stdout.decode()
+        r = json.loads(out.strip().splitlines()[-1])
+        return dict(value=r["dofs_iters_per_s"] / 1e9, seconds=r["seconds"], ndofs=r["ndofs"],
+                    kind="reference", cores=cores,
+                    sample=f"BP{w['bp']} p={w['p']} {n_cpu}^3 hexes ({r['ndofs']} dofs), {iters} "
+                           f"Jacobi-PCG iterations, MFEM -pa, MFEM_DEVICE=omp, {cores} threads")
+    # port: oracle/oracle_pa.c, scalar, one core
+    import numpy as np
+    from oracle import oracle as orc
+    import mfem_b200 as m
+    fes = m.FiniteElementSpace(m.Mesh.MakeCartesian3D(n_cpu, n_cpu, n_cpu), m.H1_FECollection(w["p"], 3))
+    ir = m.IntegrationRules(w["gll"]).Get(3, 2 * w["p"] - 1 if w["gll"] else 2 * w["p"] + 3)
+    B, G = m.h1_dof_to_quad(w["p"], ir.pts1d)
+    gm, off, ind = orc.restriction_build(fes.ne, fes.dof, fes.ndofs, fes.elem_dof, fes.dof_map)
+    Bn, Gn = m.h1_dof_to_quad(1, ir.pts1d)
+    J, detJ = orc.geometric_factors(3, 2, ir.nq1d, fes.ne, Bn, Gn, fes.elem_vertices)
+    D = (orc.mass_setup(ir.nq1d ** 3, fes.ne, ir.weights, detJ, [1.0]) if w["kind"] == "mass" else
+         orc.diffusion_setup(3, ir.nq1d, 1, fes.ne, ir.weights, J, [1.0]))
+    op = orc.Operator(3, w["d1d"], ir.nq1d, fes.ne, fes.ndofs, gm, off, ind, B, G, D,
+                      is_mass=w["kind"] == "mass", ess=fes.bdr_dofs)
+    b = np.ones(fes.ndofs)
+    b[fes.bdr_dofs] = 0
+    dinv = op.jacobi(op.diag())
+    t0 = time.time()
+    for _ in range(reps):
+        op.pcg(b, dinv, rel_tol=0.0, max_iter=iters)
+    sec = (time.time() - t0) / reps
+    return dict(value=fes.ndofs * iters / sec / 1e9, seconds=sec, ndofs=fes.ndofs, kind="port", cores=1,
+                sample=f"BP{w['bp']} p={w['p']} {n_cpu}^3 hexes ({fes.ndofs} dofs), {iters} "
+                       f"Jacobi-PCG iterations, C oracle port, 1 thread")
+
+
+def main_reference(a, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_cpu = a.cpu_n or {4: 40}.get(w["p"], max(8, round(160 / w["p"])))
+    # warm-up + timed steps: each step is one bounded-sample solve
+    t = []
+    res = None
+    for i in range(a.warmup + a.steps):
+        if i < a.warmup and i > 0:
+            continue  # the sample is seconds long: one warm-up solve is enough to page in
+        res = run_reference(w, n_cpu, a.iters, 1)
+        if i >= a.warmup:
+            t.append(res["seconds"])
+    sec = sum(t) / len(t)
+    val = res["ndofs"] * a.iters / sec / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "GDOF/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"BP{w['bp']} {w['kind']} PA + PCG/Jacobi, p={w['p']}, Q1D={w['q1d']}, "
+                                   f"{a.iters} fixed iterations; CPU sample of the GPU workload",
+                       "sample": res["sample"]},
+            "cpu_baseline": {"value": val, "unit": "GDOF/s", "cores": res["cores"], "kind": res["kind"],
+                             "sample": res["sample"]},
+            "e2e": {"value": val, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    a = parse()
+    w = workload(a)
+    if a.impl == "reference":
+        return main_reference(a, w)
+
+    import numpy as np
+    import torch
+    import mfem_b200 as m
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if a.gpus == 1 and world == 1:
+            pass
+        else:
+            raise SystemExit(f"--gpus {a.gpus} needs torchrun with {a.gpus} ranks (WORLD_SIZE={world})")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = m.Device(f"cuda:{local_rank}")
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- problem ------------------------------------------------------------------------
+    px, py, pz = w["grid"]
+    n, p = w["n"], w["p"]
+    t_setup = time.time()
+    if world > 1:
+        mesh = m.Mesh(3, n * px, n * py, n * pz, True, part=(px, py, pz), rank=rank)
+    else:
+        mesh = m.Mesh.MakeCartesian3D(n, n, n)
+    fes = m.FiniteElementSpace(mesh, m.H1_FECollection(p, 3))
+    rules = m.IntegrationRules(gll=w["gll"])
+    ir = rules.Get(3, 2 * p - 1 if w["gll"] else 2 * p + 3)
+    it = (m.MassIntegrator if w["kind"] == "mass" else m.DiffusionIntegrator)(1.0, ir)
+    form = m.BilinearForm(dev, fes)
+    form.SetAssemblyLevel("PARTIAL")
+    form.AddDomainIntegrator(it)
+    form.Assemble()
+    halo = None
+    if world > 1:
+        ids = [m.Halo.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        halo = m.Halo(dev, rank, world, fes.ndofs, fes.halo_tables, ids[0])
+        form.SetHalo(halo)
+    ess = fes.GetEssentialTrueDofs()
+    b_l = m.LinearForm(dev, fes).Assemble()
+    if halo:
+        b = dev.empty(fes.ntdofs)
+        halo.MultTranspose(b_l, b)
+    else:
+        b = b_l
+    nt = fes.ntdofs
+    A, _, B = form.FormLinearSystem(ess, dev.zeros(nt), b)
+    M = m.OperatorJacobiSmoother(form, ess)
+    cg = m.CGSolver()
+    cg.SetRelTol(0.0); cg.SetAbsTol(0.0); cg.SetMaxIter(a.iters)
+    cg.SetOperator(A); cg.SetPreconditioner(M)
+    cg.check_every = a.iters  # fixed iteration count: the host is consulted once per solve
+    X = dev.zeros(nt)
+    dev.sync()
+    t_setup = time.time() - t_setup
+    nglob = nt
+    if dist:
+        tt = torch.tensor([nt], dtype=torch.int64, device=dev.tdev)
+        dist.all_reduce(tt)
+        nglob = int(tt.item())
+    del fes.elem_dof  # host tables are no longer needed
+    # host buffers of the end-to-end path
+    B_h = torch.empty(nt, dtype=torch.float64).pin_memory()
+    X_h = torch.empty(nt, dtype=torch.float64).pin_memory()
+    B_h.copy_(B)
+
+    def solve_resident():
+        cg.Mult(B, X)
+
+    B_in = dev.empty(nt)
+
+    def solve_e2e():
+        B_in.copy_(B_h, non_blocking=True)
+        cg.Mult(B_in, X)
+        X_h.copy_(X, non_blocking=True)
+
+    def timed(fn, steps, warmup, kernel_timing=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if kernel_timing:
+            capi_call("b2f_ctx_kernel_timing", dev.ctx, 1)
+        dev.reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = dev.launch_count()
+        kt = None
+        if kernel_timing:
+            import ctypes as C
+            tot, cnt = C.c_double(), C.c_int()
+            capi_call("b2f_ctx_kernel_time", dev.ctx, C.byref(tot), C.byref(cnt))
+            capi_call("b2f_ctx_kernel_timing", dev.ctx, 0)
+            kt = (tot.value, cnt.value)
+        barrier()
+        if dist:
+            tm = torch.tensor([ms], dtype=torch.float64, device=dev.tdev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms = float(tm.item())
+        return ms, launches, kt
+
+    from mfem_b200.capi import call as capi_call
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, launches, kt = timed(solve_resident, a.steps, a.warmup, kernel_timing=True)
+    clocks = sampler.stop() if sampler else None
+    assert cg.GetNumIterations() == a.iters, (cg.GetNumIterations(), a.iters)
+    final_norm = cg.GetFinalNorm()
+    ms_e2e, _, _ = timed(solve_e2e, a.steps, min(a.warmup, 1))
+
+    value = nglob * a.iters * a.steps / (ms * 1e-3) / 1e9
+    e2e = nglob * a.iters * a.steps / (ms_e2e * 1e-3) / 1e9
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        peak = peaks.get("hbm_gbs", 6650.0)
+        ab = alg_bytes_per_apply(w, fes.ne, fes.ndofs)
+        k_ms = kt[0] / max(kt[1], 1)
+        achieved = ab / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "GDOF/s", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"BP{w['bp']} {w['kind']} PA + PCG/Jacobi, p={p}, Q1D={w['q1d']}, "
+                                   f"{n}^3 hexes per GPU on a {px}x{py}x{pz} grid, {nglob} dofs, "
+                                   f"{a.iters} fixed CG iterations per step",
+                       "dofs_global": nglob, "dofs_per_gpu": nglob // a.gpus, "elements_per_gpu": fes.ne,
+                       "cg_iterations_per_step": a.iters, "l2": "inputs (quadrature data, "
+                       f"{it_bytes(w, fes.ne) / 1e9:.1f} GB per GPU) far exceed the 126 MB L2",
+                       "final_norm": final_norm, "setup_seconds": round(t_setup, 1)},
+            "e2e": {"value": e2e, "unit": "GDOF/s", "h2d_bytes_per_step": nt * 8 * a.gpus,
+                    "d2h_bytes_per_step": nt * 8 * a.gpus, "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "pa_apply_3d_kernel (fused gather + G^T D G + scatter)",
+                         "kernel_ms": k_ms, "kernel_launches": kt[1],
+                         "kernel_share_of_step": kt[0] / ms,
+                         "algorithmic_bytes_per_launch": ab,
+                         "operator_gdofs": fes.ndofs / (k_ms * 1e-3) / 1e9,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks
+                         else "fallback 6650 GB/s"},
+            "clocks": clocks,
+        }
+        if a.gpus == 1 and not a.no_cpu_baseline:
+            try:
+                n_cpu = a.cpu_n or {4: 40}.get(p, max(8, round(160 / p)))
+                r = run_reference(w, n_cpu, a.iters, 1)
+                line["cpu_baseline"] = {"value": r["value"], "unit": "GDOF/s", "cores": r["cores"],
+                                        "kind": r["kind"], "sample": r["sample"]}
+            except Exception as ex:  # the baseline is reported, never required
+                line["cpu_baseline"] = {"value": None, "unit": "GDOF/s", "cores": 0, "kind": "reference",
+                                        "sample": f"failed: {ex}"}
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        if halo:
+            halo.close()
+        dist.destroy_process_group()
+
+
+def it_bytes(w, ne):
+    return (1 if w["kind"] == "mass" else 6) * w["q1d"] ** 3 * 8 * ne
+
+
+if __name__ == "__main__":
+    main()

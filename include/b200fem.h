@@ -1,0 +1,268 @@
+/* include/b200fem.h -- C ABI of libb200fem.so: the B200-native (sm_100a) partial-assembly
+ * operator path behind MFEM's operator API.
+ *
+ * MFEM has no C ABI of its own: its extension seams are C++ virtual interfaces
+ * (SURVEY.md section 8b).  Each entry point below names the reference interface
+ * (file:line under the MFEM source tree, v4.9.1-dev) it replaces; the MFEM-side adapter
+ * classes that bind them (`B200PAOperator : mfem::Operator`, ...) are in adapter/ and
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns B2F_OK (0) or a B2F_ERR_* code; b2f_last_error() gives the text.
+ *    No exceptions cross the boundary, nothing aborts the process.
+ *  - pointers are DEVICE pointers unless the parameter name ends in `_h` (host memory).
+ *  - tensors use the reference's layout: first index fastest, int32 indices, double values
+ *    (linalg/dtensor.hpp:32; config/config.hpp real_t = double).
+ *  - all work is enqueued on the context's stream (a cudaStream_t passed as void*;
+ *    NULL = the legacy default stream the reference uses, general/forall.hpp:761) and is
+ *    asynchronous unless stated otherwise.
+ *  - the caller owns all vectors; handles own their device tables.
+ *  - there is no CPU fallback: without a CUDA device b2f_ctx_create fails.
+ */
+#ifndef B200FEM_H
+#define B200FEM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2F_VERSION 100
+
+enum
+{
+   B2F_OK = 0,
+   B2F_ERR_ARG = 1,         /* invalid argument                                   */
+   B2F_ERR_CUDA = 2,        /* a CUDA runtime call or kernel launch failed        */
+   B2F_ERR_UNSUPPORTED = 3, /* (dim, D1D, Q1D) or option without a kernel         */
+   B2F_ERR_NCCL = 4,
+   B2F_ERR_NO_DEVICE = 5    /* no usable CUDA device: the library has no CPU path */
+};
+
+typedef struct b2f_ctx b2f_ctx;                 /* device + stream + scratch              */
+typedef struct b2f_restriction b2f_restriction; /* mfem::ElementRestriction               */
+typedef struct b2f_pa b2f_pa;                   /* one BilinearFormIntegrator's PA data   */
+typedef struct b2f_operator b2f_operator;       /* PABilinearFormExtension (+Constrained) */
+typedef struct b2f_halo b2f_halo;               /* (Device)ConformingProlongationOperator */
+
+int b2f_version(void);
+const char *b2f_last_error(void);
+
+/* ---- context: mfem::Device("cuda") (general/device.hpp:128, device.cpp:191,554) ---- */
+int b2f_ctx_create(int device, void *stream, b2f_ctx **out);
+void b2f_ctx_destroy(b2f_ctx *ctx);
+int b2f_ctx_sync(b2f_ctx *ctx);                 /* MFEM_STREAM_SYNC (general/cuda.hpp)    */
+int b2f_ctx_device(const b2f_ctx *ctx);
+int b2f_ctx_sm_count(const b2f_ctx *ctx);
+/* Launch counter: number of kernels of THIS library launched since creation / reset. */
+int64_t b2f_ctx_launch_count(const b2f_ctx *ctx);
+void b2f_ctx_reset_launch_count(b2f_ctx *ctx);
+
+/* CUDA-event timing of the PA operator kernel (pa_apply) launches alone, on the context's
+ * stream: enable, run, then read the summed device time and launch count (synchronises). */
+int b2f_ctx_kernel_timing(b2f_ctx *ctx, int enable);
+int b2f_ctx_kernel_time(b2f_ctx *ctx, double *ms_total_h, int *launches_h);
+
+/* ---- raw device memory for hosts without the CUDA runtime (mem_manager.hpp roles) --- */
+int b2f_malloc(b2f_ctx *ctx, size_t bytes, void **dptr);
+int b2f_free(b2f_ctx *ctx, void *dptr);
+int b2f_malloc_host(b2f_ctx *ctx, size_t bytes, void **hptr); /* pinned */
+int b2f_free_host(b2f_ctx *ctx, void *hptr);
+int b2f_memcpy_h2d(b2f_ctx *ctx, void *dst, const void *src_h, size_t bytes); /* async */
+int b2f_memcpy_d2h(b2f_ctx *ctx, void *dst_h, const void *src, size_t bytes); /* async */
+int b2f_memcpy_d2d(b2f_ctx *ctx, void *dst, const void *src, size_t bytes);
+int b2f_memset(b2f_ctx *ctx, void *dst, int byte, size_t bytes);
+
+/* ---- host-side discretisation tables (C++ host code, no device work) ---------------- */
+/* QuadratureFunctions1D::GaussLegendre / GaussLobatto on [0,1] (fem/intrules.cpp:620,708) */
+int b2f_gauss_legendre_h(int np, double *pts_h, double *wts_h);
+int b2f_gauss_lobatto_h(int np, double *pts_h, double *wts_h);
+/* DofToQuad, TENSOR mode, of the order-p H1 Gauss-Lobatto basis at nq points
+ * (fem/fe/fe_base.cpp:2697-2740, Poly_1D::Basis::Eval :1947): B_h,G_h are (nq, p+1). */
+int b2f_h1_dof_to_quad_h(int p, int nq, const double *qpts_h, double *B_h, double *G_h);
+/* IntegrationRule tensor weights (fem/intrules.cpp:43-96): W_h has nq^dim entries. */
+int b2f_tensor_weights_h(int dim, int nq, const double *w1_h, double *W_h);
+
+/* Structured hex/quad mesh + H1 space with the reference's numbering
+ * (Mesh::MakeCartesian2D/3D mesh/mesh.cpp:3841,4388 incl. the space-filling-curve element
+ * order; edge/face numbering mesh.cpp:8526-8560,8996; H1 dofs fem/fespace.cpp:3428-3536;
+ * lexicographic dof_map fem/fe/fe_base.cpp:2497-2680).  Two-call pattern: pass NULL arrays
+ * to get sizes.  elem_dof_h is the element-to-dof table in the element's NATIVE order
+ * (what FiniteElementSpace::GetElementToDofTable().GetJ() holds); dof_map_h the
+ * lexicographic -> native map; bdr_dofs_h the boundary (essential) dofs, sorted. */
+int b2f_cartesian_h1_space_h(int dim, int nx, int ny, int nz, int p, int sfc_ordering,
+                             int *ne, int *ndofs, int *elem_dof_h, int *dof_map_h,
+                             int *nbdr, int *bdr_dofs_h,
+                             double *elem_vertices_h /* (2^dim, dim, NE) lexicographic, or NULL */);
+
+/* Cartesian block partition of that mesh over a px x py x pz process grid and the rank's
+ * parallel H1 space tables -- what ParMesh + ParFiniteElementSpace + GroupCommunicator
+ * produce in the reference (Mesh::CartesianPartitioning mesh/mesh.cpp:9188; group master =
+ * lowest rank general/communication.cpp:120-124; true dofs fem/pfespace.cpp:2169; neighbour
+ * tables general/communication.cpp:543,579).  No communication: every rank calls it with
+ * its own `rank` (= ix + px*(iy + py*iz)).  All array arguments may be NULL;
+ * sizes_h[10] = {lnx, lny, lnz, ne, n_ldofs, n_tdofs, n_nbr, n_shr, n_ext, n_bdr}.
+ * The local space is numbered as b2f_cartesian_h1_space_h numbers the local block;
+ * elem_vertices_h holds GLOBAL coordinates; bdr_ldofs_h the local dofs on the GLOBAL
+ * boundary; ldof_lattice_h the point gx + LX*(gy + LY*gz) of each local dof on the global
+ * (p*nx+1, p*ny+1, p*nz+1) lattice.  The remaining tables are b2f_halo_create's inputs. */
+int b2f_cartesian_partition_h(int dim, int nx, int ny, int nz, int p, int sfc_ordering,
+                              int px, int py, int pz, int rank, int *sizes_h,
+                              int *elem_dof_h, int *dof_map_h, int *bdr_ldofs_h,
+                              double *elem_vertices_h, int *ltdof_ldof_h, int *nbr_rank_h,
+                              int *shr_offsets_h, int *shr_ltdof_h, int *ext_offsets_h,
+                              int *ext_ldof_h, int64_t *ldof_lattice_h);
+
+/* ---- ElementRestriction (fem/restriction.hpp:40, restriction.cpp:26-228) ------------ */
+/* From the reference's own tables (ElementRestriction::GatherMap/Offsets/Indices,
+ * restriction.hpp:104-106).  Tables are copied to the device. */
+int b2f_restriction_create(b2f_ctx *ctx, int ne, int dof, int ndofs, int vdim, int byvdim,
+                           const int *gather_map_h, const int *offsets_h,
+                           const int *indices_h, b2f_restriction **out);
+/* ElementRestriction::ElementRestriction (restriction.cpp:26-114): builds gather_map,
+ * offsets and indices on the device from the element-to-dof table (signed, native order)
+ * and the lexicographic dof_map (NULL = native ordering). */
+int b2f_restriction_create_from_elem_dof(b2f_ctx *ctx, int ne, int dof, int ndofs, int vdim,
+                                         int byvdim, const int *elem_dof_h,
+                                         const int *dof_map_h, b2f_restriction **out);
+void b2f_restriction_destroy(b2f_restriction *r);
+/* device pointers to the tables (for parity checks and for adapters) */
+int b2f_restriction_tables(const b2f_restriction *r, const int **gather_map,
+                           const int **offsets, const int **indices);
+/* ElementRestriction::Mult (restriction.cpp:116): L -> E, bit-exact */
+int b2f_restriction_mult(b2f_restriction *r, const double *x_l, double *y_e);
+/* ElementRestriction::AbsMult (restriction.cpp:138) */
+int b2f_restriction_abs_mult(b2f_restriction *r, const double *x_l, double *y_e);
+/* ElementRestriction::MultTranspose / AddMultTranspose (restriction.cpp:159-201):
+ * E -> L, per-dof sequential sum in ascending E-index order, bit-exact. */
+int b2f_restriction_mult_transpose(b2f_restriction *r, const double *x_e, double *y_l, int add);
+/* ElementRestriction::AbsMultTranspose (restriction.cpp:203) */
+int b2f_restriction_abs_mult_transpose(b2f_restriction *r, const double *x_e, double *y_l);
+
+/* ---- BilinearFormIntegrator PA seam (fem/bilininteg.hpp:49-95) ---------------------- */
+/* DiffusionIntegrator::AssemblePA (fem/integ/bilininteg_diffusion_pa.cpp:108) ->
+ * PADiffusionSetup (bilininteg_diffusion_kernels.cpp:107-386).  J is the reference's
+ * GeometricFactors::J, (Q^dim, dim, dim, NE).  coeff: coeff_dim = 1 (scalar), dim (vector),
+ * dim(dim+1)/2 (symmetric matrix) or dim*dim; coeff_size == coeff_dim means constant,
+ * otherwise (coeff_dim, Q^dim, NE).  B_h,G_h: (Q1D, D1D); W_h: Q1D^dim weights. */
+int b2f_diffusion_setup(b2f_ctx *ctx, int dim, int d1d, int q1d, int64_t ne,
+                        const double *B_h, const double *G_h, const double *W_h,
+                        const double *J, const double *coeff, int coeff_dim,
+                        int64_t coeff_size, b2f_pa **out);
+/* MassIntegrator::AssemblePA (fem/integ/bilininteg_mass_pa.cpp:25-91): D = W c detJ.
+ * coeff_size == 1 means constant, otherwise (Q^dim, NE). */
+int b2f_mass_setup(b2f_ctx *ctx, int dim, int d1d, int q1d, int64_t ne, const double *B_h,
+                   const double *W_h, const double *detJ, const double *coeff,
+                   int64_t coeff_size, b2f_pa **out);
+/* Same two integrators with the geometric factors (mesh/mesh.cpp:15420-15498,
+ * fem/qinterp/grad.hpp:235, det.hpp) fused in: J is evaluated from the nodal coordinates
+ * E-vector (node_d1d^dim, dim, NE) on the fly and never written to memory.
+ * Bn_h,Gn_h: (Q1D, node_d1d) tables of the nodal basis at the quadrature points.
+ * kind: 0 = diffusion, 1 = mass.  Scalar constant coefficient. */
+int b2f_pa_setup_from_nodes(b2f_ctx *ctx, int kind, int dim, int d1d, int q1d, int64_t ne,
+                            const double *B_h, const double *G_h, const double *W_h,
+                            int node_d1d, const double *Bn_h, const double *Gn_h,
+                            const double *nodes_e, double coeff, b2f_pa **out);
+void b2f_pa_destroy(b2f_pa *pa);
+/* the quadrature-point data ("pa_data", bilininteg.hpp:2287): device pointer and length */
+int b2f_pa_data(const b2f_pa *pa, const double **data, int64_t *size);
+/* BilinearFormIntegrator::AddMultPA (bilininteg.hpp:78): y_e += A_e x_e on E-vectors.
+ * Replaces (Smem)PADiffusionApply2D/3D (bilininteg_diffusion_kernels.hpp:514-1215) and
+ * (Smem)PAMassApply2D/3D (bilininteg_mass_kernels.hpp:440-1165). */
+int b2f_pa_add_mult(b2f_pa *pa, const double *x_e, double *y_e);
+/* BilinearFormIntegrator::AssembleDiagonalPA (bilininteg.hpp:68): diag_e += diag(A_e).
+ * Replaces (Smem)PADiffusionDiagonal2D/3D, (Smem)PAMassAssembleDiagonal2D/3D. */
+int b2f_pa_assemble_diagonal(b2f_pa *pa, double *diag_e);
+
+/* ---- PABilinearFormExtension + ConstrainedOperator ---------------------------------- */
+/* PABilinearFormExtension (fem/bilinearform_ext.cpp:256-564) over one restriction and
+ * n integrators; ess_ldofs_h (may be NULL / 0) is the essential dof list that
+ * FormLinearSystem wraps around it as a ConstrainedOperator (linalg/operator.cpp:526). */
+int b2f_operator_create(b2f_ctx *ctx, b2f_restriction *r, b2f_pa *const *integrators,
+                        int n_integrators, const int *ess_dofs_h, int n_ess,
+                        b2f_operator **out);
+void b2f_operator_destroy(b2f_operator *op);
+/* PABilinearFormExtension::Mult (bilinearform_ext.cpp:487-564): y = R^T (sum_i A_i) R x as
+ * ONE fused kernel per integrator (gather, contraction, D, transpose, scatter): no
+ * E-vector in memory.  1e-12 relative parity (atomic scatter order is not fixed). */
+int b2f_operator_mult(b2f_operator *op, const double *x_l, double *y_l);
+/* The reference's unfused sequence (R, AddMultPA, R^T) with E-vectors in memory; the
+ * scatter is deterministic.  For parity cross-checks. */
+int b2f_operator_mult_unfused(b2f_operator *op, const double *x_l, double *y_l);
+/* ConstrainedOperator::Mult (linalg/operator.cpp:601-660, DIAG_ONE):
+ * z = x; z[ess] = 0; y = A z; y[ess] = x[ess]. */
+int b2f_operator_mult_constrained(b2f_operator *op, const double *x_l, double *y_l);
+/* PABilinearFormExtension::AssembleDiagonal (bilinearform_ext.cpp:370-454) */
+int b2f_operator_assemble_diagonal(b2f_operator *op, double *diag_l);
+/* ConstrainedOperator::EliminateRHS (linalg/operator.cpp:574-599) */
+int b2f_operator_eliminate_rhs(b2f_operator *op, const double *x_l, double *b_l);
+/* Attach the rank-parallel prolongation: the operator becomes
+ * RAPOperator(P, A, P) (linalg/operator.hpp:981-1033) on true-dof vectors. */
+int b2f_operator_set_halo(b2f_operator *op, b2f_halo *halo);
+int b2f_operator_height(const b2f_operator *op); /* true-dof size if a halo is set */
+
+/* ---- OperatorJacobiSmoother (linalg/solvers.cpp:324-450) ----------------------------- */
+/* Setup: dinv = damping / diag; dinv[ess] = damping (solvers.cpp:401-425). */
+int b2f_jacobi_setup(b2f_ctx *ctx, int n, const double *diag, const int *ess_dofs /*device*/,
+                     int n_ess, double damping, double *dinv);
+/* Mult (iterative_mode = false): y = dinv .* x */
+int b2f_jacobi_mult(b2f_ctx *ctx, int n, const double *dinv, const double *x, double *y);
+
+/* ---- Vector BLAS-1 (linalg/vector.cpp:436,570,1079; general/reducers.hpp:536) -------- */
+int b2f_vector_dot(b2f_ctx *ctx, int64_t n, const double *x, const double *y, double *result_h);
+/* z = x + a*y */
+int b2f_vector_add(b2f_ctx *ctx, int64_t n, const double *x, double a, const double *y, double *z);
+
+/* ---- CGSolver (linalg/solvers.cpp:869-1050) ----------------------------------------- */
+/* PCG with the reference's exact control flow (iterative_mode = false: x0 = 0):
+ * r0 = max(nom0 rel_tol^2, abs_tol^2); stop when (B r, r) <= r0 or after max_iter.
+ * dinv == NULL: no preconditioner.  The operator is applied as ConstrainedOperator (and
+ * RAPOperator when a halo is attached); dot products are NCCL all-reduced across ranks
+ * when a halo is attached (IterativeSolver::Dot, solvers.cpp:58).
+ * All scalars live on the device; the host is consulted once per `check_every`
+ * iterations (1 = the reference's behaviour of testing convergence every iteration).
+ * history_h (may be NULL) receives (B r, r) for iterations 0..iters (capacity entries). */
+typedef struct
+{
+   double rel_tol, abs_tol;
+   int max_iter;
+   int check_every;
+} b2f_pcg_options;
+typedef struct
+{
+   int iterations;
+   int converged;
+   double initial_norm, final_norm; /* sqrt((B r, r)) */
+} b2f_pcg_result;
+int b2f_pcg(b2f_operator *op, const double *dinv, const double *b, double *x,
+            const b2f_pcg_options *opt, b2f_pcg_result *result_h, double *history_h,
+            int history_capacity);
+
+/* ---- rank-parallel prolongation: ConformingProlongationOperator ----------------------
+ * (fem/pfespace.hpp:615-697, pfespace.cpp:5479-5927) with the shared-dof exchange as
+ * NCCL send/recv over NVLink instead of MPI_Isend/Irecv. */
+/* rank 0 creates the id and distributes it out of band (e.g. torch.distributed) */
+int b2f_nccl_unique_id_h(void *id128_h);
+int b2f_halo_create(b2f_ctx *ctx, const void *nccl_id128_h, int rank, int nranks,
+                    int n_ldofs, int n_tdofs,
+                    const int *ltdof_ldof_h,         /* [n_tdofs] owned ldofs, ascending   */
+                    int n_nbr, const int *nbr_rank_h,
+                    const int *shr_offsets_h,        /* [n_nbr+1] into shr_ltdof           */
+                    const int *shr_ltdof_h,          /* owned tdofs sent to each neighbour */
+                    const int *ext_offsets_h,        /* [n_nbr+1] into ext_ldof            */
+                    const int *ext_ldof_h,           /* ldofs owned by each neighbour      */
+                    b2f_halo **out);
+void b2f_halo_destroy(b2f_halo *h);
+/* P: true-dof vector -> local-dof vector (pfespace.cpp:5760-5816) */
+int b2f_halo_mult(b2f_halo *h, const double *x_t, double *y_l);
+/* P^T: local-dof vector -> true-dof vector, fixed summation order (pfespace.cpp:5818-5927) */
+int b2f_halo_mult_transpose(b2f_halo *h, const double *x_l, double *y_t);
+/* InnerProduct(comm, x, y) (linalg/vector.hpp:773): local dot + all-reduce */
+int b2f_halo_dot(b2f_halo *h, int64_t n, const double *x, const double *y, double *result_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FEM_H */

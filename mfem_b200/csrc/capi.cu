@@ -1,0 +1,859 @@
+// mfem_b200/csrc/capi.cu -- the extern "C" surface of libb200fem.so (include/b200fem.h).
+//
+// Thin glue: argument checks, handle lifetime, and the host-side orchestration that the
+// reference does in PABilinearFormExtension (fem/bilinearform_ext.cpp:256-564),
+// ConstrainedOperator (linalg/operator.cpp:526-660), OperatorJacobiSmoother
+// (linalg/solvers.cpp:324-450) and CGSolver::Mult (linalg/solvers.cpp:869-1050).
+// No arithmetic happens on the host; without a CUDA device every entry point fails.
+#include <cstdarg>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace b2f
+{
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...)
+{
+   va_list ap;
+   va_start(ap, fmt);
+   vsnprintf(g_err, sizeof(g_err), fmt, ap);
+   va_end(ap);
+}
+
+// restriction.cu
+int restriction_build_device(b2f_restriction *r, const int *elem_dof_d, const int *dof_map_d);
+int restriction_gather(b2f_restriction *r, const double *x, double *y, bool abs);
+int restriction_scatter(b2f_restriction *r, const double *x, double *y, int mode);
+// vector_ops.cu
+int vector_add(b2f_ctx *ctx, int64_t n, const double *x, double a, const double *y, double *z);
+int vector_mul(b2f_ctx *ctx, int64_t n, const double *a, const double *x, double *y);
+int jacobi_setup(b2f_ctx *ctx, int n, const double *diag, const int *ess, int n_ess,
+                 double damping, double *dinv);
+int pcg_state_bytes();
+int pcg_after_nom0(b2f_ctx *ctx, void *state, double rel_tol, double abs_tol, int max_iter,
+                   double *history, int history_cap);
+int pcg_after_den0(b2f_ctx *ctx, void *state);
+int pcg_update(b2f_ctx *ctx, void *state, int64_t n, double *x, const double *d, double *r,
+               const double *q, const double *dinv, double *z);
+int pcg_after_betanom(b2f_ctx *ctx, void *state, double *history, int history_cap);
+int pcg_direction(b2f_ctx *ctx, void *state, int64_t n, const double *z, double *d);
+int pcg_after_den(b2f_ctx *ctx, void *state);
+double *pcg_dot_slot(void *state);
+void pcg_read_state(const void *host_copy, int *iter, int *done, int *converged, int *final_iter,
+                    double *nom0, double *betanom);
+// halo.cu
+int halo_mult(b2f_halo *h, const double *x_t, double *y_l);
+int halo_mult_transpose(b2f_halo *h, const double *x_l, double *y_t);
+int halo_allreduce_sum(b2f_halo *h, double *d_scalar, int count);
+int halo_sizes(const b2f_halo *h, int *n_ldofs, int *n_tdofs);
+const int *halo_ldof_to_tdof_h(const b2f_halo *h); // host array [n_ldofs]: tdof or -1
+
+template <typename T>
+static int upload(const T *h, size_t n, T **d)
+{
+   *d = nullptr;
+   B2F_CUDA(cudaMalloc((void **)d, sizeof(T) * (n ? n : 1)));
+   if (n) { B2F_CUDA(cudaMemcpy(*d, h, sizeof(T) * n, cudaMemcpyHostToDevice)); }
+   return B2F_OK;
+}
+
+} // namespace b2f
+
+using namespace b2f;
+
+#define B2F_TRY(expr)                                                                  \
+   do                                                                                  \
+   {                                                                                   \
+      int rc_ = (expr);                                                                \
+      if (rc_ != B2F_OK) { return rc_; }                                               \
+   } while (0)
+
+extern "C" {
+
+int b2f_version(void) { return B2F_VERSION; }
+const char *b2f_last_error(void) { return g_err; }
+
+// ---- context ----------------------------------------------------------------------------
+int b2f_ctx_create(int device, void *stream, b2f_ctx **out)
+{
+   B2F_REQUIRE(out, "b2f_ctx_create: out is NULL");
+   *out = nullptr;
+   int ndev = 0;
+   cudaError_t e = cudaGetDeviceCount(&ndev);
+   if (e != cudaSuccess || ndev == 0)
+   {
+      cudaGetLastError();
+      set_error("b2f_ctx_create: no CUDA device (%s); libb200fem has no CPU path",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+      return B2F_ERR_NO_DEVICE;
+   }
+   B2F_REQUIRE(device >= 0 && device < ndev, "b2f_ctx_create: device %d out of range [0,%d)",
+               device, ndev);
+   B2F_CUDA(cudaSetDevice(device));
+   b2f_ctx *ctx = new b2f_ctx;
+   ctx->device = device;
+   ctx->stream = (cudaStream_t)stream;
+   B2F_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+   B2F_CUDA(cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin,
+                                   device));
+   ctx->n_partials = ctx->sm_count * 8;
+   B2F_CUDA(cudaMalloc((void **)&ctx->d_partials, sizeof(double) * ctx->n_partials));
+   B2F_CUDA(cudaMalloc((void **)&ctx->d_counter, sizeof(unsigned int)));
+   B2F_CUDA(cudaMemset(ctx->d_counter, 0, sizeof(unsigned int)));
+   B2F_CUDA(cudaMalloc((void **)&ctx->d_scalars, sizeof(double) * 64));
+   B2F_CUDA(cudaMemset(ctx->d_scalars, 0, sizeof(double) * 64));
+   B2F_CUDA(cudaMallocHost((void **)&ctx->h_scalars, sizeof(double) * 64));
+   *out = ctx;
+   return B2F_OK;
+}
+
+void b2f_ctx_destroy(b2f_ctx *ctx)
+{
+   if (!ctx) { return; }
+   cudaSetDevice(ctx->device);
+   cudaStreamSynchronize(ctx->stream);
+   cudaFree(ctx->d_partials);
+   cudaFree(ctx->d_counter);
+   cudaFree(ctx->d_scalars);
+   cudaFreeHost(ctx->h_scalars);
+   for (cudaEvent_t e : ctx->ev) { cudaEventDestroy(e); }
+   delete ctx;
+}
+
+int b2f_ctx_sync(b2f_ctx *ctx)
+{
+   B2F_REQUIRE(ctx, "b2f_ctx_sync: ctx is NULL");
+   B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+   return B2F_OK;
+}
+int b2f_ctx_device(const b2f_ctx *ctx) { return ctx ? ctx->device : -1; }
+int b2f_ctx_sm_count(const b2f_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+int64_t b2f_ctx_launch_count(const b2f_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void b2f_ctx_reset_launch_count(b2f_ctx *ctx) { if (ctx) { ctx->launches = 0; } }
+
+int b2f_ctx_kernel_timing(b2f_ctx *ctx, int enable)
+{
+   B2F_REQUIRE(ctx, "b2f_ctx_kernel_timing: ctx is NULL");
+   B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+   ctx->timing = enable != 0;
+   ctx->ev_used = 0;
+   return B2F_OK;
+}
+
+int b2f_ctx_kernel_time(b2f_ctx *ctx, double *ms_total_h, int *launches_h)
+{
+   B2F_REQUIRE(ctx && ms_total_h && launches_h, "b2f_ctx_kernel_time: NULL argument");
+   B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+   double total = 0.0;
+   const int n = ctx->ev_used / 2;
+   for (int i = 0; i < n; i++)
+   {
+      float ms = 0.f;
+      B2F_CUDA(cudaEventElapsedTime(&ms, ctx->ev[2 * i], ctx->ev[2 * i + 1]));
+      total += ms;
+   }
+   *ms_total_h = total;
+   *launches_h = n;
+   ctx->ev_used = 0;
+   return B2F_OK;
+}
+
+// ---- memory -----------------------------------------------------------------------------
+int b2f_malloc(b2f_ctx *ctx, size_t bytes, void **dptr)
+{
+   B2F_REQUIRE(ctx && dptr, "b2f_malloc: NULL argument");
+   B2F_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+   return B2F_OK;
+}
+int b2f_free(b2f_ctx *ctx, void *dptr)
+{
+   B2F_REQUIRE(ctx, "b2f_free: ctx is NULL");
+   if (dptr) { B2F_CUDA(cudaFree(dptr)); }
+   return B2F_OK;
+}
+int b2f_malloc_host(b2f_ctx *ctx, size_t bytes, void **hptr)
+{
+   B2F_REQUIRE(ctx && hptr, "b2f_malloc_host: NULL argument");
+   B2F_CUDA(cudaMallocHost(hptr, bytes ? bytes : 1));
+   return B2F_OK;
+}
+int b2f_free_host(b2f_ctx *ctx, void *hptr)
+{
+   B2F_REQUIRE(ctx, "b2f_free_host: ctx is NULL");
+   if (hptr) { B2F_CUDA(cudaFreeHost(hptr)); }
+   return B2F_OK;
+}
+int b2f_memcpy_h2d(b2f_ctx *ctx, void *dst, const void *src_h, size_t bytes)
+{
+   B2F_REQUIRE(ctx, "b2f_memcpy_h2d: ctx is NULL");
+   if (bytes) { B2F_CUDA(cudaMemcpyAsync(dst, src_h, bytes, cudaMemcpyHostToDevice, ctx->stream)); }
+   return B2F_OK;
+}
+int b2f_memcpy_d2h(b2f_ctx *ctx, void *dst_h, const void *src, size_t bytes)
+{
+   B2F_REQUIRE(ctx, "b2f_memcpy_d2h: ctx is NULL");
+   if (bytes) { B2F_CUDA(cudaMemcpyAsync(dst_h, src, bytes, cudaMemcpyDeviceToHost, ctx->stream)); }
+   return B2F_OK;
+}
+int b2f_memcpy_d2d(b2f_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+   B2F_REQUIRE(ctx, "b2f_memcpy_d2d: ctx is NULL");
+   if (bytes) { B2F_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream)); }
+   return B2F_OK;
+}
+int b2f_memset(b2f_ctx *ctx, void *dst, int byte, size_t bytes)
+{
+   B2F_REQUIRE(ctx, "b2f_memset: ctx is NULL");
+   if (bytes) { B2F_CUDA(cudaMemsetAsync(dst, byte, bytes, ctx->stream)); }
+   return B2F_OK;
+}
+
+// ---- ElementRestriction -----------------------------------------------------------------
+static int restriction_alloc(b2f_ctx *ctx, int ne, int dof, int ndofs, int vdim, int byvdim,
+                             b2f_restriction **out)
+{
+   B2F_REQUIRE(ctx && out, "b2f_restriction_create: NULL argument");
+   B2F_REQUIRE(ne >= 0 && dof >= 1 && ndofs >= 0 && vdim >= 1,
+               "b2f_restriction_create: bad sizes ne=%d dof=%d ndofs=%d vdim=%d", ne, dof, ndofs, vdim);
+   B2F_REQUIRE((int64_t)ne * dof <= INT32_MAX,
+               "b2f_restriction_create: ne*dof = %lld exceeds the int32 E-index range",
+               (long long)ne * dof);
+   b2f_restriction *r = new b2f_restriction;
+   r->ctx = ctx; r->ne = ne; r->dof = dof; r->ndofs = ndofs; r->vdim = vdim; r->byvdim = byvdim;
+   const size_t n = (size_t)ne * dof;
+   B2F_CUDA(cudaMalloc((void **)&r->gather_map, sizeof(int) * (n ? n : 1)));
+   B2F_CUDA(cudaMalloc((void **)&r->indices, sizeof(int) * (n ? n : 1)));
+   B2F_CUDA(cudaMalloc((void **)&r->offsets, sizeof(int) * ((size_t)ndofs + 1)));
+   *out = r;
+   return B2F_OK;
+}
+
+int b2f_restriction_create(b2f_ctx *ctx, int ne, int dof, int ndofs, int vdim, int byvdim,
+                           const int *gather_map_h, const int *offsets_h, const int *indices_h,
+                           b2f_restriction **out)
+{
+   B2F_REQUIRE(gather_map_h && offsets_h && indices_h, "b2f_restriction_create: NULL table");
+   b2f_restriction *r = nullptr;
+   B2F_TRY(restriction_alloc(ctx, ne, dof, ndofs, vdim, byvdim, &r));
+   const size_t n = (size_t)ne * dof;
+   if (n)
+   {
+      B2F_CUDA(cudaMemcpy(r->gather_map, gather_map_h, sizeof(int) * n, cudaMemcpyHostToDevice));
+      B2F_CUDA(cudaMemcpy(r->indices, indices_h, sizeof(int) * n, cudaMemcpyHostToDevice));
+   }
+   B2F_CUDA(cudaMemcpy(r->offsets, offsets_h, sizeof(int) * ((size_t)ndofs + 1),
+                       cudaMemcpyHostToDevice));
+   *out = r;
+   return B2F_OK;
+}
+
+int b2f_restriction_create_from_elem_dof(b2f_ctx *ctx, int ne, int dof, int ndofs, int vdim,
+                                         int byvdim, const int *elem_dof_h, const int *dof_map_h,
+                                         b2f_restriction **out)
+{
+   B2F_REQUIRE(elem_dof_h || ne == 0, "b2f_restriction_create_from_elem_dof: elem_dof_h is NULL");
+   b2f_restriction *r = nullptr;
+   B2F_TRY(restriction_alloc(ctx, ne, dof, ndofs, vdim, byvdim, &r));
+   int *d_ed = nullptr, *d_dm = nullptr;
+   B2F_TRY(upload(elem_dof_h, (size_t)ne * dof, &d_ed));
+   if (dof_map_h) { B2F_TRY(upload(dof_map_h, (size_t)dof, &d_dm)); }
+   int rc = restriction_build_device(r, d_ed, d_dm);
+   cudaFree(d_ed);
+   cudaFree(d_dm);
+   if (rc) { b2f_restriction_destroy(r); return rc; }
+   *out = r;
+   return B2F_OK;
+}
+
+void b2f_restriction_destroy(b2f_restriction *r)
+{
+   if (!r) { return; }
+   cudaFree(r->gather_map);
+   cudaFree(r->offsets);
+   cudaFree(r->indices);
+   delete r;
+}
+
+int b2f_restriction_tables(const b2f_restriction *r, const int **gather_map, const int **offsets,
+                           const int **indices)
+{
+   B2F_REQUIRE(r, "b2f_restriction_tables: NULL handle");
+   if (gather_map) { *gather_map = r->gather_map; }
+   if (offsets) { *offsets = r->offsets; }
+   if (indices) { *indices = r->indices; }
+   return B2F_OK;
+}
+
+int b2f_restriction_mult(b2f_restriction *r, const double *x_l, double *y_e)
+{
+   B2F_REQUIRE(r && (x_l || !r->ndofs) && (y_e || !r->ne), "b2f_restriction_mult: NULL argument");
+   return restriction_gather(r, x_l, y_e, false);
+}
+int b2f_restriction_abs_mult(b2f_restriction *r, const double *x_l, double *y_e)
+{
+   B2F_REQUIRE(r && (x_l || !r->ndofs) && (y_e || !r->ne), "b2f_restriction_abs_mult: NULL argument");
+   return restriction_gather(r, x_l, y_e, true);
+}
+int b2f_restriction_mult_transpose(b2f_restriction *r, const double *x_e, double *y_l, int add)
+{
+   B2F_REQUIRE(r && (x_e || !r->ne) && (y_l || !r->ndofs),
+               "b2f_restriction_mult_transpose: NULL argument");
+   return restriction_scatter(r, x_e, y_l, add ? 1 : 0);
+}
+int b2f_restriction_abs_mult_transpose(b2f_restriction *r, const double *x_e, double *y_l)
+{
+   B2F_REQUIRE(r && (x_e || !r->ne) && (y_l || !r->ndofs),
+               "b2f_restriction_abs_mult_transpose: NULL argument");
+   return restriction_scatter(r, x_e, y_l, 2);
+}
+
+// ---- integrators ------------------------------------------------------------------------
+static int pa_alloc(b2f_ctx *ctx, int kind, int dim, int d1d, int q1d, int64_t ne, int ncomp,
+                    const double *B_h, const double *G_h, b2f_pa **out)
+{
+   B2F_REQUIRE(ctx && out && B_h, "pa setup: NULL argument");
+   B2F_REQUIRE(dim == 2 || dim == 3, "pa setup: dim = %d (2 or 3 supported)", dim);
+   B2F_REQUIRE(d1d >= 2 && q1d >= 1 && d1d * q1d <= 256, "pa setup: bad D1D=%d Q1D=%d", d1d, q1d);
+   B2F_REQUIRE(ne >= 0, "pa setup: ne < 0");
+   b2f_pa *pa = new b2f_pa;
+   pa->ctx = ctx; pa->kind = kind; pa->dim = dim; pa->d1d = d1d; pa->q1d = q1d; pa->ne = ne;
+   pa->ncomp = ncomp;
+   pa->symmetric = !(kind == B2F_KIND_DIFFUSION && ncomp == dim * dim);
+   memset(pa->B, 0, sizeof(pa->B));
+   memset(pa->G, 0, sizeof(pa->G));
+   memcpy(pa->B, B_h, sizeof(double) * d1d * q1d);
+   if (G_h) { memcpy(pa->G, G_h, sizeof(double) * d1d * q1d); }
+   // collocated (BP5): B is exactly the identity -> the interpolation is skipped.  "Exactly"
+   // up to 2 ulp: the reference's barycentric evaluation at a node gives 1 +- eps.
+   pa->collocated = 0;
+   if (d1d == q1d)
+   {
+      double dev = 0.0;
+      for (int q = 0; q < q1d; q++)
+         for (int d = 0; d < d1d; d++)
+         {
+            const double v = pa->B[q + q1d * d] - (q == d ? 1.0 : 0.0);
+            dev = fabs(v) > dev ? fabs(v) : dev;
+         }
+      pa->collocated = dev == 0.0;
+   }
+   int nq = 1;
+   for (int i = 0; i < dim; i++) { nq *= q1d; }
+   pa->data_size = (int64_t)nq * ncomp * ne;
+   B2F_CUDA(cudaMalloc((void **)&pa->data, sizeof(double) * (pa->data_size ? pa->data_size : 1)));
+   B2F_TRY(upload(pa->B, (size_t)d1d * q1d, &pa->d_B));
+   B2F_TRY(upload(pa->G, (size_t)d1d * q1d, &pa->d_G));
+   *out = pa;
+   return B2F_OK;
+}
+
+int b2f_diffusion_setup(b2f_ctx *ctx, int dim, int d1d, int q1d, int64_t ne, const double *B_h,
+                        const double *G_h, const double *W_h, const double *J,
+                        const double *coeff, int coeff_dim, int64_t coeff_size, b2f_pa **out)
+{
+   B2F_REQUIRE(G_h && W_h && (J || ne == 0) && coeff, "b2f_diffusion_setup: NULL argument");
+   const int sym = dim * (dim + 1) / 2;
+   B2F_REQUIRE(coeff_dim == 1 || coeff_dim == dim || coeff_dim == sym || coeff_dim == dim * dim,
+               "b2f_diffusion_setup: coeff_dim = %d", coeff_dim);
+   int nq = 1;
+   for (int i = 0; i < dim; i++) { nq *= q1d; }
+   const int coeff_const = coeff_size == coeff_dim;
+   B2F_REQUIRE(coeff_const || coeff_size == (int64_t)coeff_dim * nq * ne,
+               "b2f_diffusion_setup: coeff_size = %lld is neither %d (constant) nor %lld",
+               (long long)coeff_size, coeff_dim, (long long)coeff_dim * nq * ne);
+   const int ncomp = coeff_dim == dim * dim ? dim * dim : sym;
+   b2f_pa *pa = nullptr;
+   B2F_TRY(pa_alloc(ctx, B2F_KIND_DIFFUSION, dim, d1d, q1d, ne, ncomp, B_h, G_h, &pa));
+   double *d_W = nullptr;
+   B2F_TRY(upload(W_h, (size_t)nq, &d_W));
+   int rc = diffusion_setup(ctx, dim, q1d, ne, d_W, J, coeff, coeff_dim, coeff_const, pa->data);
+   cudaStreamSynchronize(ctx->stream);
+   cudaFree(d_W);
+   if (rc) { b2f_pa_destroy(pa); return rc; }
+   *out = pa;
+   return B2F_OK;
+}
+
+int b2f_mass_setup(b2f_ctx *ctx, int dim, int d1d, int q1d, int64_t ne, const double *B_h,
+                   const double *W_h, const double *detJ, const double *coeff, int64_t coeff_size,
+                   b2f_pa **out)
+{
+   B2F_REQUIRE(W_h && (detJ || ne == 0) && coeff, "b2f_mass_setup: NULL argument");
+   int nq = 1;
+   for (int i = 0; i < dim; i++) { nq *= q1d; }
+   const int coeff_const = coeff_size == 1;
+   B2F_REQUIRE(coeff_const || coeff_size == (int64_t)nq * ne, "b2f_mass_setup: coeff_size = %lld",
+               (long long)coeff_size);
+   b2f_pa *pa = nullptr;
+   B2F_TRY(pa_alloc(ctx, B2F_KIND_MASS, dim, d1d, q1d, ne, 1, B_h, nullptr, &pa));
+   double *d_W = nullptr;
+   B2F_TRY(upload(W_h, (size_t)nq, &d_W));
+   int rc = mass_setup(ctx, nq, ne, d_W, detJ, coeff, coeff_const, pa->data);
+   cudaStreamSynchronize(ctx->stream);
+   cudaFree(d_W);
+   if (rc) { b2f_pa_destroy(pa); return rc; }
+   *out = pa;
+   return B2F_OK;
+}
+
+int b2f_pa_setup_from_nodes(b2f_ctx *ctx, int kind, int dim, int d1d, int q1d, int64_t ne,
+                            const double *B_h, const double *G_h, const double *W_h, int node_d1d,
+                            const double *Bn_h, const double *Gn_h, const double *nodes_e,
+                            double coeff, b2f_pa **out)
+{
+   B2F_REQUIRE(kind == B2F_KIND_DIFFUSION || kind == B2F_KIND_MASS,
+               "b2f_pa_setup_from_nodes: kind = %d", kind);
+   B2F_REQUIRE(W_h && Bn_h && Gn_h && (nodes_e || ne == 0) && node_d1d >= 2,
+               "b2f_pa_setup_from_nodes: NULL argument");
+   B2F_REQUIRE(kind == B2F_KIND_MASS || G_h, "b2f_pa_setup_from_nodes: G_h is NULL");
+   int nq = 1;
+   for (int i = 0; i < dim; i++) { nq *= q1d; }
+   const int ncomp = kind == B2F_KIND_MASS ? 1 : dim * (dim + 1) / 2;
+   b2f_pa *pa = nullptr;
+   B2F_TRY(pa_alloc(ctx, kind, dim, d1d, q1d, ne, ncomp, B_h, G_h, &pa));
+   double *d_W = nullptr, *d_Bn = nullptr, *d_Gn = nullptr;
+   B2F_TRY(upload(W_h, (size_t)nq, &d_W));
+   B2F_TRY(upload(Bn_h, (size_t)q1d * node_d1d, &d_Bn));
+   B2F_TRY(upload(Gn_h, (size_t)q1d * node_d1d, &d_Gn));
+   int rc = setup_from_nodes(ctx, kind, dim, q1d, ne, d_W, node_d1d, d_Bn, d_Gn, nodes_e, coeff,
+                             pa->data);
+   cudaStreamSynchronize(ctx->stream);
+   cudaFree(d_W); cudaFree(d_Bn); cudaFree(d_Gn);
+   if (rc) { b2f_pa_destroy(pa); return rc; }
+   *out = pa;
+   return B2F_OK;
+}
+
+void b2f_pa_destroy(b2f_pa *pa)
+{
+   if (!pa) { return; }
+   cudaFree(pa->data);
+   cudaFree(pa->d_B);
+   cudaFree(pa->d_G);
+   delete pa;
+}
+
+int b2f_pa_data(const b2f_pa *pa, const double **data, int64_t *size)
+{
+   B2F_REQUIRE(pa, "b2f_pa_data: NULL handle");
+   if (data) { *data = pa->data; }
+   if (size) { *size = pa->data_size; }
+   return B2F_OK;
+}
+
+int b2f_pa_add_mult(b2f_pa *pa, const double *x_e, double *y_e)
+{
+   B2F_REQUIRE(pa && (pa->ne == 0 || (x_e && y_e)), "b2f_pa_add_mult: NULL argument");
+   return pa_apply(pa, x_e, y_e, nullptr);
+}
+
+int b2f_pa_assemble_diagonal(b2f_pa *pa, double *diag_e)
+{
+   B2F_REQUIRE(pa && (pa->ne == 0 || diag_e), "b2f_pa_assemble_diagonal: NULL argument");
+   return pa_diag(pa, diag_e);
+}
+
+// ---- operator ---------------------------------------------------------------------------
+__global__ void mask_gather_map_kernel(int64_t n, const int *__restrict__ gmap,
+                                       const unsigned char *__restrict__ is_ess, int *out)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) { return; }
+   const int g = gmap[i];
+   out[i] = (g >= 0 && is_ess[g]) ? -1 : g;
+}
+__global__ void mark_kernel(int n, const int *__restrict__ idx, unsigned char *flags)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) { flags[idx[i]] = 1; }
+}
+__global__ void any_negative_kernel(int64_t n, const int *__restrict__ v, int *flag)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n && v[i] < 0) { *flag = 1; }
+}
+
+// (re)build the essential-dof tables: ess_l = constrained LOCAL dofs (mask of the fused
+// gather index); op->ess = the list ConstrainedOperator works on (ldofs, or tdofs when a
+// halo is attached).
+static int operator_build_masks(b2f_operator *op, const int *ess_ldofs_h, int n_ess_l)
+{
+   b2f_ctx *ctx = op->ctx;
+   b2f_restriction *r = op->r;
+   const int64_t n = (int64_t)r->ne * r->dof;
+   cudaFree(op->fused_idx); op->fused_idx = nullptr;
+   cudaFree(op->ess); op->ess = nullptr;
+   op->n_ess = 0;
+   std::vector<int> ess_c; // constrained list in the operator's own numbering
+   if (op->halo)
+   {
+      const int *l2t = halo_ldof_to_tdof_h(op->halo);
+      for (int i = 0; i < n_ess_l; i++)
+      {
+         const int t = l2t[ess_ldofs_h[i]];
+         if (t >= 0) { ess_c.push_back(t); }
+      }
+   }
+   else { ess_c.assign(ess_ldofs_h, ess_ldofs_h + n_ess_l); }
+   op->n_ess = (int)ess_c.size();
+   B2F_TRY(upload(ess_c.data(), ess_c.size(), &op->ess));
+   if (n_ess_l > 0 && n > 0)
+   {
+      int *d_ess_l = nullptr;
+      unsigned char *flags = nullptr;
+      B2F_TRY(upload(ess_ldofs_h, (size_t)n_ess_l, &d_ess_l));
+      B2F_CUDA(cudaMalloc((void **)&flags, (size_t)r->ndofs + 1));
+      B2F_CUDA(cudaMemsetAsync(flags, 0, (size_t)r->ndofs + 1, ctx->stream));
+      mark_kernel<<<(unsigned)cdiv(n_ess_l, 256), 256, 0, ctx->stream>>>(n_ess_l, d_ess_l, flags);
+      B2F_LAUNCH_CHECK(ctx);
+      B2F_CUDA(cudaMalloc((void **)&op->fused_idx, sizeof(int) * n));
+      mask_gather_map_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(n, r->gather_map,
+                                                                              flags, op->fused_idx);
+      B2F_LAUNCH_CHECK(ctx);
+      B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaFree(flags);
+      cudaFree(d_ess_l);
+   }
+   return B2F_OK;
+}
+
+int b2f_operator_create(b2f_ctx *ctx, b2f_restriction *r, b2f_pa *const *integrators,
+                        int n_integrators, const int *ess_dofs_h, int n_ess, b2f_operator **out)
+{
+   B2F_REQUIRE(ctx && r && out && integrators && n_integrators >= 1,
+               "b2f_operator_create: NULL argument");
+   B2F_REQUIRE(n_ess == 0 || ess_dofs_h, "b2f_operator_create: ess_dofs_h is NULL");
+   B2F_REQUIRE(r->vdim == 1, "b2f_operator_create: vdim = %d (scalar spaces only)", r->vdim);
+   int dim_dof = 0;
+   for (int i = 0; i < n_integrators; i++)
+   {
+      const b2f_pa *pa = integrators[i];
+      B2F_REQUIRE(pa, "b2f_operator_create: integrator %d is NULL", i);
+      int dof = 1;
+      for (int k = 0; k < pa->dim; k++) { dof *= pa->d1d; }
+      B2F_REQUIRE(dof == r->dof && pa->ne == r->ne,
+                  "b2f_operator_create: integrator %d (D1D=%d dim=%d NE=%lld) does not match the "
+                  "restriction (dof=%d NE=%d)", i, pa->d1d, pa->dim, (long long)pa->ne, r->dof, r->ne);
+      dim_dof = dof;
+   }
+   (void)dim_dof;
+   for (int i = 0; i < n_ess; i++)
+   {
+      B2F_REQUIRE(ess_dofs_h[i] >= 0 && ess_dofs_h[i] < r->ndofs,
+                  "b2f_operator_create: essential dof %d out of range", ess_dofs_h[i]);
+   }
+   b2f_operator *op = new b2f_operator;
+   op->ctx = ctx;
+   op->r = r;
+   op->integ.assign(integrators, integrators + n_integrators);
+   op->ess_l_h.assign(ess_dofs_h, ess_dofs_h + n_ess);
+   // signed gather maps (non-H1 spaces) cannot use the fused kernel's "-1 = skip" encoding
+   {
+      int *flag = nullptr;
+      const int64_t n = (int64_t)r->ne * r->dof;
+      B2F_CUDA(cudaMalloc((void **)&flag, sizeof(int)));
+      B2F_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+      if (n)
+      {
+         any_negative_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(n, r->gather_map, flag);
+         B2F_LAUNCH_CHECK(ctx);
+      }
+      int h = 0;
+      B2F_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaFree(flag);
+      op->signed_map = h;
+   }
+   int rc = operator_build_masks(op, ess_dofs_h, n_ess);
+   if (rc) { b2f_operator_destroy(op); return rc; }
+   *out = op;
+   return B2F_OK;
+}
+
+void b2f_operator_destroy(b2f_operator *op)
+{
+   if (!op) { return; }
+   cudaFree(op->ess); cudaFree(op->fused_idx);
+   cudaFree(op->xe); cudaFree(op->ye);
+   cudaFree(op->z); cudaFree(op->w);
+   cudaFree(op->xl); cudaFree(op->yl);
+   for (double *p : op->pcg_vec) { cudaFree(p); }
+   cudaFree(op->pcg_hist);
+   delete op;
+}
+
+static int ensure(double **p, int64_t n)
+{
+   if (!*p) { B2F_CUDA(cudaMalloc((void **)p, sizeof(double) * (n ? n : 1))); }
+   return B2F_OK;
+}
+
+// y_l = R^T (sum_i A_i) R x_l on LOCAL vectors; idx selects the (masked) gather index
+static int local_mult_fused(b2f_operator *op, const double *x_l, double *y_l, const int *idx)
+{
+   b2f_ctx *ctx = op->ctx;
+   B2F_CUDA(cudaMemsetAsync(y_l, 0, sizeof(double) * (size_t)op->r->ndofs, ctx->stream));
+   for (b2f_pa *pa : op->integ) { B2F_TRY(pa_apply(pa, x_l, y_l, idx)); }
+   return B2F_OK;
+}
+
+static int local_mult_unfused(b2f_operator *op, const double *x_l, double *y_l)
+{
+   b2f_ctx *ctx = op->ctx;
+   b2f_restriction *r = op->r;
+   const int64_t ne_dof = (int64_t)r->ne * r->dof;
+   B2F_TRY(ensure(&op->xe, ne_dof));
+   B2F_TRY(ensure(&op->ye, ne_dof));
+   B2F_TRY(restriction_gather(r, x_l, op->xe, false));                 // bilinearform_ext.cpp:543
+   B2F_CUDA(cudaMemsetAsync(op->ye, 0, sizeof(double) * ne_dof, ctx->stream)); // :545
+   for (b2f_pa *pa : op->integ) { B2F_TRY(pa_apply(pa, op->xe, op->ye, nullptr)); } // :548
+   return restriction_scatter(r, op->ye, y_l, 0);                      // :557
+}
+
+static int local_mult(b2f_operator *op, const double *x_l, double *y_l, bool constrained_mask)
+{
+   if (op->signed_map)
+   {
+      // non-H1 signs: the reference sequence; masking is done by the caller's z = x, z[ess] = 0
+      return local_mult_unfused(op, x_l, y_l);
+   }
+   const int *idx = (constrained_mask && op->fused_idx) ? op->fused_idx : op->r->gather_map;
+   return local_mult_fused(op, x_l, y_l, idx);
+}
+
+// A on the operator's own vectors (true-dof vectors when a halo is attached):
+// RAPOperator::Mult (linalg/operator.hpp:998): P, A, P^T
+static int rap_mult(b2f_operator *op, const double *x, double *y, bool constrained_mask)
+{
+   if (!op->halo) { return local_mult(op, x, y, constrained_mask); }
+   const int nl = op->r->ndofs;
+   B2F_TRY(ensure(&op->xl, nl));
+   B2F_TRY(ensure(&op->yl, nl));
+   B2F_TRY(halo_mult(op->halo, x, op->xl));
+   B2F_TRY(local_mult(op, op->xl, op->yl, constrained_mask));
+   return halo_mult_transpose(op->halo, op->yl, y);
+}
+
+int b2f_operator_height(const b2f_operator *op)
+{
+   if (!op) { return -1; }
+   if (op->halo)
+   {
+      int nl = 0, nt = 0;
+      halo_sizes(op->halo, &nl, &nt);
+      return nt;
+   }
+   return op->r->ndofs;
+}
+
+int b2f_operator_mult(b2f_operator *op, const double *x_l, double *y_l)
+{
+   B2F_REQUIRE(op && x_l && y_l, "b2f_operator_mult: NULL argument");
+   B2F_REQUIRE(x_l != y_l, "b2f_operator_mult: x and y alias");
+   return rap_mult(op, x_l, y_l, false);
+}
+
+int b2f_operator_mult_unfused(b2f_operator *op, const double *x_l, double *y_l)
+{
+   B2F_REQUIRE(op && x_l && y_l, "b2f_operator_mult_unfused: NULL argument");
+   B2F_REQUIRE(!op->halo, "b2f_operator_mult_unfused: local operators only");
+   return local_mult_unfused(op, x_l, y_l);
+}
+
+int b2f_operator_mult_constrained(b2f_operator *op, const double *x, double *y)
+{
+   B2F_REQUIRE(op && x && y, "b2f_operator_mult_constrained: NULL argument");
+   B2F_REQUIRE(x != y, "b2f_operator_mult_constrained: x and y alias");
+   b2f_ctx *ctx = op->ctx;
+   if (op->signed_map && op->n_ess)
+   {
+      // operator.cpp:601-660 literally: z = x; z[ess] = 0; y = A z; y[ess] = x[ess]
+      const int n = b2f_operator_height(op);
+      B2F_TRY(ensure(&op->z, n));
+      B2F_CUDA(cudaMemcpyAsync(op->z, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+      B2F_TRY(set_entries(ctx, op->z, op->ess, op->n_ess, 0.0));
+      B2F_TRY(rap_mult(op, op->z, y, false));
+   }
+   else
+   {
+      // same result without the copy: constrained dofs read as 0 in the gather and are
+      // skipped by the scatter
+      B2F_TRY(rap_mult(op, x, y, true));
+   }
+   return copy_entries(ctx, y, x, op->ess, op->n_ess);
+}
+
+int b2f_operator_assemble_diagonal(b2f_operator *op, double *diag)
+{
+   B2F_REQUIRE(op && diag, "b2f_operator_assemble_diagonal: NULL argument");
+   b2f_ctx *ctx = op->ctx;
+   b2f_restriction *r = op->r;
+   const int64_t ne_dof = (int64_t)r->ne * r->dof;
+   B2F_TRY(ensure(&op->ye, ne_dof));
+   B2F_CUDA(cudaMemsetAsync(op->ye, 0, sizeof(double) * ne_dof, ctx->stream)); // bilinearform_ext.cpp:385
+   for (b2f_pa *pa : op->integ) { B2F_TRY(pa_diag(pa, op->ye)); }
+   if (!op->halo) { return restriction_scatter(r, op->ye, diag, 2); } // AbsMultTranspose :426
+   // ParBilinearForm::AssembleDiagonal (fem/pbilinearform.cpp:293): P^T of the local diagonal
+   B2F_TRY(ensure(&op->yl, r->ndofs));
+   B2F_TRY(restriction_scatter(r, op->ye, op->yl, 2));
+   return halo_mult_transpose(op->halo, op->yl, diag);
+}
+
+int b2f_operator_eliminate_rhs(b2f_operator *op, const double *x, double *b)
+{
+   B2F_REQUIRE(op && x && b, "b2f_operator_eliminate_rhs: NULL argument");
+   b2f_ctx *ctx = op->ctx;
+   const int n = b2f_operator_height(op);
+   if (op->n_ess == 0) { return B2F_OK; }
+   // operator.cpp:574-599: w = 0; w[ess] = x[ess]; z = A w; b -= z; b[ess] = x[ess]
+   B2F_TRY(ensure(&op->w, n));
+   B2F_TRY(ensure(&op->z, n));
+   B2F_CUDA(cudaMemsetAsync(op->w, 0, sizeof(double) * n, ctx->stream));
+   B2F_TRY(copy_entries(ctx, op->w, x, op->ess, op->n_ess));
+   B2F_TRY(rap_mult(op, op->w, op->z, false));
+   B2F_TRY(vector_add(ctx, n, b, -1.0, op->z, b));
+   return copy_entries(ctx, b, x, op->ess, op->n_ess);
+}
+
+int b2f_operator_set_halo(b2f_operator *op, b2f_halo *halo)
+{
+   B2F_REQUIRE(op, "b2f_operator_set_halo: NULL handle");
+   if (halo)
+   {
+      int nl = 0, nt = 0;
+      halo_sizes(halo, &nl, &nt);
+      B2F_REQUIRE(nl == op->r->ndofs, "b2f_operator_set_halo: halo has %d ldofs, the space %d", nl,
+                  op->r->ndofs);
+   }
+   op->halo = halo;
+   cudaFree(op->z); op->z = nullptr;
+   cudaFree(op->w); op->w = nullptr;
+   for (double *&p : op->pcg_vec) { cudaFree(p); p = nullptr; }
+   return operator_build_masks(op, op->ess_l_h.data(), (int)op->ess_l_h.size());
+}
+
+// ---- Jacobi + BLAS-1 --------------------------------------------------------------------
+int b2f_jacobi_setup(b2f_ctx *ctx, int n, const double *diag, const int *ess_dofs, int n_ess,
+                     double damping, double *dinv)
+{
+   B2F_REQUIRE(ctx && (n == 0 || (diag && dinv)) && (n_ess == 0 || ess_dofs),
+               "b2f_jacobi_setup: NULL argument");
+   return jacobi_setup(ctx, n, diag, ess_dofs, n_ess, damping, dinv);
+}
+
+int b2f_jacobi_mult(b2f_ctx *ctx, int n, const double *dinv, const double *x, double *y)
+{
+   B2F_REQUIRE(ctx && (n == 0 || (dinv && x && y)), "b2f_jacobi_mult: NULL argument");
+   return vector_mul(ctx, n, dinv, x, y);
+}
+
+int b2f_vector_dot(b2f_ctx *ctx, int64_t n, const double *x, const double *y, double *result_h)
+{
+   B2F_REQUIRE(ctx && result_h && (n == 0 || (x && y)), "b2f_vector_dot: NULL argument");
+   if (n == 0) { *result_h = 0.0; return B2F_OK; }
+   B2F_TRY(dot_to_device(ctx, n, x, y, ctx->d_scalars + 63));
+   B2F_CUDA(cudaMemcpyAsync(ctx->h_scalars + 63, ctx->d_scalars + 63, sizeof(double),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+   B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+   *result_h = ctx->h_scalars[63];
+   return B2F_OK;
+}
+
+int b2f_vector_add(b2f_ctx *ctx, int64_t n, const double *x, double a, const double *y, double *z)
+{
+   B2F_REQUIRE(ctx && (n == 0 || (x && y && z)), "b2f_vector_add: NULL argument");
+   return vector_add(ctx, n, x, a, y, z);
+}
+
+// ---- PCG --------------------------------------------------------------------------------
+int b2f_pcg(b2f_operator *op, const double *dinv, const double *b, double *x,
+            const b2f_pcg_options *opt, b2f_pcg_result *result_h, double *history_h,
+            int history_capacity)
+{
+   B2F_REQUIRE(op && b && x && opt && result_h, "b2f_pcg: NULL argument");
+   B2F_REQUIRE(opt->max_iter >= 0, "b2f_pcg: max_iter < 0");
+   B2F_REQUIRE(pcg_state_bytes() <= (int)(48 * sizeof(double)), "b2f_pcg: state too large");
+   b2f_ctx *ctx = op->ctx;
+   b2f_halo *halo = op->halo;
+   const int64_t n = b2f_operator_height(op);
+   const int check_every = opt->check_every > 0 ? opt->check_every : 1;
+   void *st = ctx->d_scalars; // PcgState lives in the context's device scalars
+   for (int k = 0; k < 4; k++) { B2F_TRY(ensure(&op->pcg_vec[k], n)); }
+   double *r = op->pcg_vec[0], *d = op->pcg_vec[1], *z = op->pcg_vec[2], *q = op->pcg_vec[3];
+   double *hist = nullptr;
+   if (history_h && history_capacity > 0)
+   {
+      if (op->pcg_hist_cap < history_capacity)
+      {
+         cudaFree(op->pcg_hist);
+         op->pcg_hist = nullptr;
+         B2F_CUDA(cudaMalloc((void **)&op->pcg_hist, sizeof(double) * history_capacity));
+         op->pcg_hist_cap = history_capacity;
+      }
+      hist = op->pcg_hist;
+      B2F_CUDA(cudaMemsetAsync(hist, 0, sizeof(double) * history_capacity, ctx->stream));
+   }
+   auto reduce = [&]() -> int { return halo ? halo_allreduce_sum(halo, pcg_dot_slot(st), 1) : B2F_OK; };
+
+   // r = b; x = 0   (iterative_mode = false, solvers.cpp:881-884)
+   B2F_CUDA(cudaMemcpyAsync(r, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+   B2F_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * n, ctx->stream));
+   const double *zz = r; // "z" of the unpreconditioned iteration is r itself
+   if (dinv)
+   {
+      B2F_TRY(vector_mul(ctx, n, dinv, r, z)); // z = B r
+      zz = z;
+   }
+   B2F_CUDA(cudaMemcpyAsync(d, zz, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+   B2F_TRY(dot_to_device(ctx, n, d, r, pcg_dot_slot(st)));
+   B2F_TRY(reduce());
+   B2F_TRY(pcg_after_nom0(ctx, st, opt->rel_tol, opt->abs_tol, opt->max_iter, hist,
+                          hist ? history_capacity : 0));
+   B2F_TRY(b2f_operator_mult_constrained(op, d, q)); // z = A d
+   B2F_TRY(dot_to_device(ctx, n, q, d, pcg_dot_slot(st)));
+   B2F_TRY(reduce());
+   B2F_TRY(pcg_after_den0(ctx, st));
+
+   unsigned char host_state[48 * sizeof(double)];
+   int iter = 0, done = 0, converged = 0, final_iter = 0;
+   double nom0 = 0, betanom = 0;
+   auto poll = [&]() -> int
+   {
+      B2F_CUDA(cudaMemcpyAsync(ctx->h_scalars, st, pcg_state_bytes(), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+      B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+      memcpy(host_state, ctx->h_scalars, pcg_state_bytes());
+      pcg_read_state(host_state, &iter, &done, &converged, &final_iter, &nom0, &betanom);
+      return B2F_OK;
+   };
+   B2F_TRY(poll());
+   int enq = 0; // iterations enqueued since the last poll
+   while (!done)
+   {
+      B2F_TRY(pcg_update(ctx, st, n, x, d, r, q, dinv, z));
+      B2F_TRY(reduce());
+      B2F_TRY(pcg_after_betanom(ctx, st, hist, hist ? history_capacity : 0));
+      B2F_TRY(pcg_direction(ctx, st, n, zz, d));
+      B2F_TRY(b2f_operator_mult_constrained(op, d, q));
+      B2F_TRY(dot_to_device(ctx, n, d, q, pcg_dot_slot(st)));
+      B2F_TRY(reduce());
+      B2F_TRY(pcg_after_den(ctx, st));
+      if (++enq >= check_every) { B2F_TRY(poll()); enq = 0; }
+   }
+   result_h->iterations = final_iter;
+   result_h->converged = converged;
+   result_h->initial_norm = nom0 >= 0.0 ? sqrt(nom0) : nom0;
+   result_h->final_norm = betanom >= 0.0 ? sqrt(betanom) : betanom;
+   if (hist)
+   {
+      B2F_CUDA(cudaMemcpyAsync(history_h, hist, sizeof(double) * history_capacity,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+      B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+   }
+   return B2F_OK;
+}
+
+} // extern "C"

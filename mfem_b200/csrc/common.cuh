@@ -1,0 +1,154 @@
+// mfem_b200/csrc/common.cuh -- shared declarations of libb200fem.so (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cmath>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/b200fem.h"
+
+namespace b2f
+{
+
+void set_error(const char *fmt, ...);
+
+#define B2F_CUDA(call)                                                                 \
+   do                                                                                  \
+   {                                                                                   \
+      cudaError_t e_ = (call);                                                         \
+      if (e_ != cudaSuccess)                                                           \
+      {                                                                                \
+         b2f::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,             \
+                        cudaGetErrorString(e_));                                       \
+         return B2F_ERR_CUDA;                                                          \
+      }                                                                                \
+   } while (0)
+
+// kernel launch check, the reference does the same after every forall (forall.hpp:762)
+#define B2F_LAUNCH_CHECK(ctx)                                                          \
+   do                                                                                  \
+   {                                                                                   \
+      (ctx)->launches++;                                                               \
+      cudaError_t e_ = cudaGetLastError();                                             \
+      if (e_ != cudaSuccess)                                                           \
+      {                                                                                \
+         b2f::set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__,         \
+                        cudaGetErrorString(e_));                                       \
+         return B2F_ERR_CUDA;                                                          \
+      }                                                                                \
+   } while (0)
+
+#define B2F_REQUIRE(cond, ...)                                                         \
+   do                                                                                  \
+   {                                                                                   \
+      if (!(cond))                                                                     \
+      {                                                                                \
+         b2f::set_error(__VA_ARGS__);                                                  \
+         return B2F_ERR_ARG;                                                           \
+      }                                                                                \
+   } while (0)
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+} // namespace b2f
+
+struct b2f_ctx
+{
+   int device = 0;
+   cudaStream_t stream = nullptr;
+   int sm_count = 0;
+   int max_smem_optin = 0;
+   int64_t launches = 0;
+   // scratch for reductions: device partials + device scalars + pinned host mirror
+   double *d_partials = nullptr;
+   int n_partials = 0;
+   unsigned int *d_counter = nullptr;
+   double *d_scalars = nullptr; // 64 doubles of device-resident scalars
+   double *h_scalars = nullptr; // pinned
+   // optional CUDA-event timing of the PA operator kernel launches (b2f_ctx_kernel_timing)
+   int timing = 0;
+   std::vector<cudaEvent_t> ev; // pairs (start, stop)
+   int ev_used = 0;
+};
+
+namespace b2f
+{
+// record an event on the context's stream when timing is enabled (pairs: before, after)
+inline void timing_mark(b2f_ctx *ctx)
+{
+   if (!ctx->timing) { return; }
+   if (ctx->ev_used == (int)ctx->ev.size())
+   {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) { return; }
+      ctx->ev.push_back(e);
+   }
+   cudaEventRecord(ctx->ev[ctx->ev_used++], ctx->stream);
+}
+} // namespace b2f
+
+struct b2f_restriction
+{
+   b2f_ctx *ctx;
+   int ne, dof, ndofs, vdim, byvdim;
+   int *gather_map = nullptr, *offsets = nullptr, *indices = nullptr;
+};
+
+enum { B2F_KIND_DIFFUSION = 0, B2F_KIND_MASS = 1 };
+
+struct b2f_pa
+{
+   b2f_ctx *ctx;
+   int kind, dim, d1d, q1d;
+   int ncomp;      // quadrature-data components per point: 1 (mass), 3/4 (2D), 6/9 (3D)
+   int symmetric;
+   int64_t ne;
+   double B[256], G[256]; // host copies, (q1d, d1d) column-major
+   double *d_B = nullptr, *d_G = nullptr;
+   double *data = nullptr; // (Q^dim, ncomp, NE)
+   int64_t data_size = 0;
+   int collocated = 0;     // B is the identity (BP5): interpolation is skipped
+};
+
+struct b2f_operator
+{
+   b2f_ctx *ctx;
+   b2f_restriction *r;
+   std::vector<b2f_pa *> integ;
+   int n_ess = 0;
+   int *ess = nullptr;          // device list of essential ldofs / tdofs
+   int *fused_idx = nullptr;    // gather_map with ess dofs marked -1 (constrained fused path)
+   double *xe = nullptr, *ye = nullptr; // E-vectors for the unfused path (lazy)
+   double *z = nullptr, *w = nullptr;   // L-vector scratch
+   b2f_halo *halo = nullptr;
+   double *xl = nullptr, *yl = nullptr; // L-vectors when a halo is attached
+   std::vector<int> ess_l_h;            // essential LOCAL dofs as given at creation
+   int signed_map = 0;                  // gather_map has negative (sign-flipped) entries
+   double *pcg_vec[4] = {nullptr, nullptr, nullptr, nullptr}; // r, d, z, q
+   double *pcg_hist = nullptr;
+   int pcg_hist_cap = 0;
+};
+
+namespace b2f
+{
+// pa_apply_*.cu : E-vector (idx == nullptr) or fused L-vector (idx = gather index, -1 = skip)
+int pa_apply(b2f_pa *pa, const double *x, double *y, const int *idx);
+// pa_diag.cu
+int pa_diag(b2f_pa *pa, double *diag_e);
+// pa_setup.cu
+int diffusion_setup(b2f_ctx *ctx, int dim, int q1d, int64_t ne, const double *W_d,
+                    const double *J, const double *coeff, int coeff_dim, int coeff_const,
+                    double *D);
+int mass_setup(b2f_ctx *ctx, int nq, int64_t ne, const double *W_d, const double *detJ,
+               const double *coeff, int coeff_const, double *D);
+int setup_from_nodes(b2f_ctx *ctx, int kind, int dim, int q1d, int64_t ne, const double *W_d,
+                     int nd, const double *Bn_d, const double *Gn_d, const double *nodes_e,
+                     double coeff, double *D);
+// vector_ops.cu
+int fill(b2f_ctx *ctx, double *x, double v, int64_t n);
+int set_entries(b2f_ctx *ctx, double *x, const int *idx, int n, double v);
+int copy_entries(b2f_ctx *ctx, double *dst, const double *src, const int *idx, int n);
+int dot_to_device(b2f_ctx *ctx, int64_t n, const double *x, const double *y, double *d_out);
+} // namespace b2f

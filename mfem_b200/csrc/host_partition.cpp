@@ -1,0 +1,182 @@
+// mfem_b200/csrc/host_partition.cpp -- Cartesian block partition of the structured mesh and
+// the shared-dof tables of the rank-parallel H1 space (host C++, integer work only).
+//
+// What it stands in for in the reference (which needs MPI + METIS to do the same):
+//   Mesh::CartesianPartitioning                       mesh/mesh.cpp:9188
+//   ParMesh(comm, mesh, partitioning)                 mesh/pmesh.cpp:106
+//   GroupTopology::Create, master = lowest rank       general/communication.cpp:97-124
+//   ParFiniteElementSpace::ConstructTrueDofs          fem/pfespace.cpp:2169
+//     (a true dof is a local dof whose group master is this rank; ltdof order = ldof order)
+//   GroupCommunicator::GetNeighborLTDofTable / GetNeighborLDofTable
+//                                                     general/communication.cpp:543,579
+// Every rank runs this independently (no communication): a dof is identified by its point
+// on the global (p*nx+1) x (p*ny+1) x (p*nz+1) lattice, the ranks that share it follow from
+// the block extents, and both sides of every neighbour pair list their common dofs in
+// ascending lattice order, so send and receive buffers line up.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <map>
+#include <vector>
+
+#include "../../include/b200fem.h"
+
+namespace b2f
+{
+void set_error(const char *fmt, ...);
+}
+
+namespace
+{
+struct Split
+{
+   int n, parts;
+   int lo(int b) const { return (int)((int64_t)b * n / parts); }
+};
+} // namespace
+
+extern "C" int b2f_cartesian_partition_h(int dim, int nx, int ny, int nz, int p, int sfc_ordering,
+                                         int px, int py, int pz, int rank, int *sizes_h,
+                                         int *elem_dof_h, int *dof_map_h, int *bdr_ldofs_h,
+                                         double *elem_vertices_h, int *ltdof_ldof_h,
+                                         int *nbr_rank_h, int *shr_offsets_h, int *shr_ltdof_h,
+                                         int *ext_offsets_h, int *ext_ldof_h,
+                                         int64_t *ldof_lattice_h)
+{
+   using b2f::set_error;
+   if (dim == 2) { nz = 1; pz = 1; }
+   if ((dim != 2 && dim != 3) || !sizes_h || px < 1 || py < 1 || pz < 1 || px > nx || py > ny ||
+       pz > nz || p < 1 || rank < 0 || rank >= px * py * pz)
+   {
+      set_error("b2f_cartesian_partition_h: bad arguments (grid %dx%dx%d over %dx%dx%d elements, "
+                "rank %d)", px, py, pz, nx, ny, nz, rank);
+      return B2F_ERR_ARG;
+   }
+   const Split S[3] = {{nx, px}, {ny, py}, {nz, pz}};
+   const int P[3] = {px, py, pz};
+   const int b[3] = {rank % px, (rank / px) % py, rank / (px * py)};
+   int o[3], ln[3];
+   for (int a = 0; a < 3; a++) { o[a] = S[a].lo(b[a]); ln[a] = S[a].lo(b[a] + 1) - o[a]; }
+
+   int ne = 0, nl = 0, nbdr_local = 0;
+   int rc = b2f_cartesian_h1_space_h(dim, ln[0], ln[1], ln[2], p, sfc_ordering, &ne, &nl, nullptr,
+                                     nullptr, nullptr, nullptr, nullptr);
+   if (rc) { return rc; }
+   const int p1 = p + 1, nv = dim == 2 ? 4 : 8;
+   const int dof = dim == 2 ? p1 * p1 : p1 * p1 * p1;
+   std::vector<int> ed((size_t)ne * dof), dm(dof);
+   std::vector<double> ev((size_t)ne * nv * dim);
+   rc = b2f_cartesian_h1_space_h(dim, ln[0], ln[1], ln[2], p, sfc_ordering, &ne, &nl, ed.data(),
+                                 dm.data(), &nbdr_local, nullptr, ev.data());
+   if (rc) { return rc; }
+
+   // global lattice point of every local dof
+   const int64_t L[3] = {(int64_t)p * nx + 1, (int64_t)p * ny + 1, (int64_t)p * nz + 1};
+   std::vector<int64_t> lat(nl, -1);
+   for (int e = 0; e < ne; e++)
+   {
+      int c[3] = {0, 0, 0};
+      for (int a = 0; a < dim; a++) { c[a] = (int)std::lround(ev[(size_t)e * nv * dim + nv * a] * ln[a]); }
+      for (int k = 0; k < (dim == 3 ? p1 : 1); k++)
+         for (int j = 0; j < p1; j++)
+            for (int i = 0; i < p1; i++)
+            {
+               const int lex = i + p1 * (j + p1 * k);
+               const int l = ed[(size_t)e * dof + dm[lex]];
+               const int64_t g[3] = {(int64_t)p * (o[0] + c[0]) + i, (int64_t)p * (o[1] + c[1]) + j,
+                                     (int64_t)p * (o[2] + c[2]) + k};
+               lat[l] = g[0] + L[0] * (g[1] + L[1] * g[2]);
+            }
+   }
+   // sharing ranks of a lattice point: per axis, the block(s) whose closed extent holds it
+   auto axis_blocks = [&](int a, int64_t g, int out[2]) -> int
+   {
+      if (a >= dim) { out[0] = 0; return 1; }
+      int n = 0;
+      // this rank's block holds g by construction; a neighbour holds it only on an interface
+      if (b[a] > 0 && g == (int64_t)p * o[a]) { out[n++] = b[a] - 1; }
+      out[n++] = b[a];
+      if (b[a] + 1 < P[a] && g == (int64_t)p * (o[a] + ln[a])) { out[n++] = b[a] + 1; }
+      return n; // n <= 2 unless the block is a single lattice layer thick, which p>=1, ln>=1 excludes
+   };
+   std::vector<int> owner(nl);
+   std::map<int, std::vector<std::pair<int64_t, int>>> shr, ext; // neighbour -> (lattice, ldof)
+   std::vector<int> bdr;
+   for (int l = 0; l < nl; l++)
+   {
+      int64_t g[3] = {lat[l] % L[0], (lat[l] / L[0]) % L[1], lat[l] / (L[0] * L[1])};
+      int bl[3][3], nb[3];
+      for (int a = 0; a < 3; a++) { nb[a] = axis_blocks(a, g[a], bl[a]); }
+      int own = rank;
+      std::vector<int> sharers;
+      for (int iz = 0; iz < nb[2]; iz++)
+         for (int iy = 0; iy < nb[1]; iy++)
+            for (int ix = 0; ix < nb[0]; ix++)
+            {
+               const int r = bl[0][ix] + px * (bl[1][iy] + py * bl[2][iz]);
+               if (r != rank) { sharers.push_back(r); }
+               own = std::min(own, r);
+            }
+      owner[l] = own;
+      if (own == rank) { for (int r : sharers) { shr[r].push_back({lat[l], l}); } }
+      else { ext[own].push_back({lat[l], l}); }
+      bool on_bdr = false;
+      for (int a = 0; a < dim; a++) { on_bdr = on_bdr || g[a] == 0 || g[a] == L[a] - 1; }
+      if (on_bdr) { bdr.push_back(l); }
+   }
+   std::vector<int> l2t(nl, -1), ltdof;
+   for (int l = 0; l < nl; l++)
+   {
+      if (owner[l] == rank) { l2t[l] = (int)ltdof.size(); ltdof.push_back(l); }
+   }
+   std::vector<int> nbrs;
+   for (auto &kv : shr) { nbrs.push_back(kv.first); }
+   for (auto &kv : ext) { nbrs.push_back(kv.first); }
+   std::sort(nbrs.begin(), nbrs.end());
+   nbrs.erase(std::unique(nbrs.begin(), nbrs.end()), nbrs.end());
+   int n_shr = 0, n_ext = 0;
+   for (auto &kv : shr) { std::sort(kv.second.begin(), kv.second.end()); n_shr += (int)kv.second.size(); }
+   for (auto &kv : ext) { std::sort(kv.second.begin(), kv.second.end()); n_ext += (int)kv.second.size(); }
+
+   sizes_h[0] = ln[0]; sizes_h[1] = ln[1]; sizes_h[2] = ln[2]; sizes_h[3] = ne; sizes_h[4] = nl;
+   sizes_h[5] = (int)ltdof.size(); sizes_h[6] = (int)nbrs.size(); sizes_h[7] = n_shr;
+   sizes_h[8] = n_ext; sizes_h[9] = (int)bdr.size();
+   if (elem_dof_h) { std::copy(ed.begin(), ed.end(), elem_dof_h); }
+   if (dof_map_h) { std::copy(dm.begin(), dm.end(), dof_map_h); }
+   if (bdr_ldofs_h) { std::copy(bdr.begin(), bdr.end(), bdr_ldofs_h); }
+   if (elem_vertices_h)
+   {
+      // global coordinates the way the reference computes them: ((real_t) i / n) * 1.0
+      const int N[3] = {nx, ny, nz};
+      for (int e = 0; e < ne; e++)
+         for (int a = 0; a < dim; a++)
+            for (int k = 0; k < nv; k++)
+            {
+               const size_t at = (size_t)e * nv * dim + nv * a + k;
+               const int i = o[a] + (int)std::lround(ev[at] * ln[a]);
+               elem_vertices_h[at] = ((double)i / N[a]) * 1.0;
+            }
+   }
+   if (ltdof_ldof_h) { std::copy(ltdof.begin(), ltdof.end(), ltdof_ldof_h); }
+   if (nbr_rank_h) { std::copy(nbrs.begin(), nbrs.end(), nbr_rank_h); }
+   if (ldof_lattice_h) { std::copy(lat.begin(), lat.end(), ldof_lattice_h); }
+   int so = 0, eo = 0;
+   for (size_t k = 0; k < nbrs.size(); k++)
+   {
+      if (shr_offsets_h) { shr_offsets_h[k] = so; }
+      if (ext_offsets_h) { ext_offsets_h[k] = eo; }
+      auto s = shr.find(nbrs[k]);
+      if (s != shr.end())
+      {
+         for (auto &q : s->second) { if (shr_ltdof_h) { shr_ltdof_h[so] = l2t[q.second]; } so++; }
+      }
+      auto x = ext.find(nbrs[k]);
+      if (x != ext.end())
+      {
+         for (auto &q : x->second) { if (ext_ldof_h) { ext_ldof_h[eo] = q.second; } eo++; }
+      }
+   }
+   if (shr_offsets_h) { shr_offsets_h[nbrs.size()] = so; }
+   if (ext_offsets_h) { ext_offsets_h[nbrs.size()] = eo; }
+   return B2F_OK;
+}

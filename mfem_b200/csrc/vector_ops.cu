@@ -1,0 +1,368 @@
+// mfem_b200/csrc/vector_ops.cu -- Vector BLAS-1 and the fused PCG vector kernels.
+//
+// Replaces Vector::operator= / add / subtract / operator* (linalg/vector.cpp:436,570,1079),
+// the block-tree reduction that stages partials through pinned host memory and syncs the
+// device on every dot (general/reducers.hpp:451-594), OperatorJacobiSmoother::Mult's three
+// passes (linalg/solvers.cpp:427-450) and the scalar bookkeeping of CGSolver::Mult
+// (linalg/solvers.cpp:869-1050).
+//
+// B200 design: HBM-bound streaming kernels, 2 x 128-bit loads in flight per thread,
+// warp-shuffle reductions, grid = a multiple of the SM count; every PCG scalar
+// (nom, den, betanom, alpha, beta, iteration state) lives in device memory, so an
+// iteration enqueues without a host round trip.
+#include "common.cuh"
+
+namespace b2f
+{
+
+constexpr int VT = 256; // threads per block for streaming kernels
+
+static inline unsigned stream_grid(const b2f_ctx *ctx, int64_t n, int per_thread)
+{
+   int64_t want = cdiv(n, (int64_t)VT * per_thread);
+   int64_t cap = (int64_t)ctx->sm_count * 8;
+   if (want > cap) { want = cap; }
+   if (want < 1) { want = 1; }
+   return (unsigned)want;
+}
+
+__global__ void __launch_bounds__(VT) fill_kernel(double *x, double v, int64_t n)
+{
+   for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
+   {
+      x[i] = v;
+   }
+}
+
+__global__ void set_entries_kernel(double *x, const int *__restrict__ idx, int n, double v)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) { x[idx[i]] = v; }
+}
+
+__global__ void copy_entries_kernel(double *dst, const double *__restrict__ src,
+                                    const int *__restrict__ idx, int n)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) { const int k = idx[i]; dst[k] = src[k]; }
+}
+
+__global__ void __launch_bounds__(VT)
+add_kernel(int64_t n, const double *__restrict__ x, double a, const double *__restrict__ y,
+           double *z)
+{
+   for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
+   {
+      z[i] = x[i] + a * y[i];
+   }
+}
+
+__global__ void __launch_bounds__(VT)
+mul_kernel(int64_t n, const double *__restrict__ a, const double *__restrict__ x, double *y)
+{
+   for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
+   {
+      y[i] = 0.0 + a[i] * x[i]; // y = 0; y += dinv*r  (solvers.cpp:441-449)
+   }
+}
+
+__global__ void jacobi_setup_kernel(int n, const double *__restrict__ diag, double damping,
+                                    double *dinv)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) { dinv[i] = damping / diag[i]; }
+}
+
+// ---- block reduction: warp shuffles, then one shuffle pass over the warp sums --------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); }
+   return v;
+}
+
+// Sum `v` over the grid into *out.  Block partials go to `partials`; the last block to
+// finish (ticket counter) adds them in index order, so the result is deterministic for a
+// fixed grid size.
+__device__ __forceinline__ void grid_sum(double v, double *partials, unsigned int *counter,
+                                         double *out)
+{
+   __shared__ double wsum[VT / 32];
+   __shared__ bool last;
+   v = warp_sum(v);
+   if ((threadIdx.x & 31) == 0) { wsum[threadIdx.x >> 5] = v; }
+   __syncthreads();
+   if (threadIdx.x < 32)
+   {
+      double s = threadIdx.x < VT / 32 ? wsum[threadIdx.x] : 0.0;
+      s = warp_sum(s);
+      if (threadIdx.x == 0)
+      {
+         partials[blockIdx.x] = s;
+         __threadfence();
+         const unsigned int ticket = atomicInc(counter, gridDim.x - 1);
+         last = (ticket == gridDim.x - 1);
+      }
+   }
+   __syncthreads();
+   if (last && threadIdx.x < 32)
+   {
+      __threadfence();
+      double s = 0.0;
+      for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) { s += partials[i]; }
+      s = warp_sum(s);
+      if (threadIdx.x == 0) { *out = s; }
+   }
+}
+
+__global__ void __launch_bounds__(VT)
+dot_kernel(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
+           double *partials, unsigned int *counter, double *out)
+{
+   double s = 0.0;
+   const int64_t stride = (int64_t)gridDim.x * VT;
+   int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x;
+   for (; i + stride < n; i += 2 * stride)
+   {
+      const double a0 = x[i], b0 = y[i], a1 = x[i + stride], b1 = y[i + stride];
+      s = fma(a0, b0, s);
+      s = fma(a1, b1, s);
+   }
+   if (i < n) { s = fma(x[i], y[i], s); }
+   grid_sum(s, partials, counter, out);
+}
+
+// ---- PCG (linalg/solvers.cpp:869-1050) ------------------------------------------------
+// device-resident solver state; one instance lives in ctx->d_scalars
+struct PcgState
+{
+   double nom, den, betanom, beta, r0, nom0;
+   double dot_tmp;
+   int iter;       // the reference's loop counter i
+   int done;       // 1: loop exited
+   int converged;
+   int final_iter;
+   int max_iter;
+};
+
+// x += alpha d ; r -= alpha q ; z = dinv r (or z aliases r) ; partial (r, z)
+__global__ void __launch_bounds__(VT)
+pcg_update_kernel(int64_t n, PcgState *st, double *x, const double *__restrict__ d, double *r,
+                  const double *__restrict__ q, const double *__restrict__ dinv, double *z,
+                  double *partials, unsigned int *counter)
+{
+   if (st->done) { return; }
+   const double alpha = st->nom / st->den;
+   double s = 0.0;
+   for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
+   {
+      x[i] = x[i] + alpha * d[i];
+      const double ri = r[i] + (-alpha) * q[i];
+      r[i] = ri;
+      if (dinv)
+      {
+         const double zi = 0.0 + dinv[i] * ri;
+         z[i] = zi;
+         s = fma(ri, zi, s);
+      }
+      else { s = fma(ri, ri, s); }
+   }
+   grid_sum(s, partials, counter, &st->dot_tmp);
+}
+
+// scalar control flow after betanom = (r, z) is known (solvers.cpp:963-1000)
+__global__ void pcg_after_betanom_kernel(PcgState *st, double *history, int history_cap)
+{
+   if (st->done) { return; }
+   const double betanom = st->dot_tmp;
+   st->betanom = betanom;
+   const int i = st->iter;
+   if (history && i < history_cap) { history[i] = betanom; }
+   if (betanom < 0.0) { st->done = 1; st->converged = 0; st->final_iter = i; return; }
+   if (betanom <= st->r0) { st->done = 1; st->converged = 1; st->final_iter = i; return; }
+   st->iter = i + 1;
+   if (i + 1 > st->max_iter) { st->done = 1; st->converged = 0; st->final_iter = st->max_iter; return; }
+   st->beta = betanom / st->nom;
+}
+
+// d = z + beta d   (z = r when unpreconditioned)
+__global__ void __launch_bounds__(VT)
+pcg_direction_kernel(int64_t n, const PcgState *st, const double *__restrict__ z, double *d)
+{
+   if (st->done) { return; }
+   const double beta = st->beta;
+   for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
+   {
+      d[i] = z[i] + beta * d[i];
+   }
+}
+
+// den = (d, q) is known (solvers.cpp:1010-1024)
+__global__ void pcg_after_den_kernel(PcgState *st)
+{
+   if (st->done) { return; }
+   const double den = st->dot_tmp;
+   st->den = den;
+   if (den == 0.0) { st->done = 1; st->final_iter = st->iter; return; }
+   st->nom = st->betanom;
+}
+
+// start-up: nom0 = nom = (d, r) known (solvers.cpp:894-935)
+__global__ void pcg_after_nom0_kernel(PcgState *st, double rel_tol, double abs_tol, int max_iter,
+                                      double *history, int history_cap)
+{
+   const double nom = st->dot_tmp;
+   st->nom = st->nom0 = st->betanom = nom;
+   st->iter = 1; st->done = 0; st->converged = 0; st->final_iter = max_iter;
+   st->max_iter = max_iter;
+   if (history && history_cap > 0) { history[0] = nom; }
+   if (nom < 0.0) { st->done = 1; st->final_iter = 0; return; }
+   const double a = nom * rel_tol * rel_tol, b = abs_tol * abs_tol;
+   st->r0 = a > b ? a : b;
+   if (nom <= st->r0) { st->done = 1; st->converged = 1; st->final_iter = 0; }
+}
+
+__global__ void pcg_after_den0_kernel(PcgState *st)
+{
+   if (st->done) { return; }
+   st->den = st->dot_tmp;
+   if (st->den == 0.0) { st->done = 1; st->converged = 0; st->final_iter = 0; }
+}
+
+// ---- host launchers --------------------------------------------------------------------
+int fill(b2f_ctx *ctx, double *x, double v, int64_t n)
+{
+   if (n == 0) { return B2F_OK; }
+   if (v == 0.0)
+   {
+      B2F_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * n, ctx->stream));
+      return B2F_OK;
+   }
+   fill_kernel<<<stream_grid(ctx, n, 4), VT, 0, ctx->stream>>>(x, v, n);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+int set_entries(b2f_ctx *ctx, double *x, const int *idx, int n, double v)
+{
+   if (n == 0) { return B2F_OK; }
+   set_entries_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(x, idx, n, v);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+int copy_entries(b2f_ctx *ctx, double *dst, const double *src, const int *idx, int n)
+{
+   if (n == 0) { return B2F_OK; }
+   copy_entries_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(dst, src, idx, n);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+int dot_to_device(b2f_ctx *ctx, int64_t n, const double *x, const double *y, double *d_out)
+{
+   unsigned grid = stream_grid(ctx, n, 8);
+   if ((int)grid > ctx->n_partials) { grid = ctx->n_partials; }
+   dot_kernel<<<grid, VT, 0, ctx->stream>>>(n, x, y, ctx->d_partials, ctx->d_counter, d_out);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+int vector_add(b2f_ctx *ctx, int64_t n, const double *x, double a, const double *y, double *z)
+{
+   if (n == 0) { return B2F_OK; }
+   add_kernel<<<stream_grid(ctx, n, 4), VT, 0, ctx->stream>>>(n, x, a, y, z);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+int vector_mul(b2f_ctx *ctx, int64_t n, const double *a, const double *x, double *y)
+{
+   if (n == 0) { return B2F_OK; }
+   mul_kernel<<<stream_grid(ctx, n, 4), VT, 0, ctx->stream>>>(n, a, x, y);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+int jacobi_setup(b2f_ctx *ctx, int n, const double *diag, const int *ess, int n_ess,
+                 double damping, double *dinv)
+{
+   if (n == 0) { return B2F_OK; }
+   jacobi_setup_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(n, diag, damping, dinv);
+   B2F_LAUNCH_CHECK(ctx);
+   return set_entries(ctx, dinv, ess, n_ess, damping);
+}
+
+// pieces of the PCG loop, called from capi.cu
+int pcg_state_bytes() { return (int)sizeof(PcgState); }
+
+int pcg_start(b2f_ctx *ctx, void *state, int64_t n, const double *d, const double *r,
+              double rel_tol, double abs_tol, int max_iter, double *history, int history_cap,
+              double *dot_out_for_allreduce)
+{
+   PcgState *st = (PcgState *)state;
+   (void)dot_out_for_allreduce;
+   int rc = dot_to_device(ctx, n, d, r, &st->dot_tmp);
+   if (rc) { return rc; }
+   return B2F_OK;
+}
+
+int pcg_after_nom0(b2f_ctx *ctx, void *state, double rel_tol, double abs_tol, int max_iter,
+                   double *history, int history_cap)
+{
+   pcg_after_nom0_kernel<<<1, 1, 0, ctx->stream>>>((PcgState *)state, rel_tol, abs_tol, max_iter,
+                                                   history, history_cap);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+int pcg_after_den0(b2f_ctx *ctx, void *state)
+{
+   pcg_after_den0_kernel<<<1, 1, 0, ctx->stream>>>((PcgState *)state);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+int pcg_update(b2f_ctx *ctx, void *state, int64_t n, double *x, const double *d, double *r,
+               const double *q, const double *dinv, double *z)
+{
+   unsigned grid = stream_grid(ctx, n, 4);
+   if ((int)grid > ctx->n_partials) { grid = ctx->n_partials; }
+   pcg_update_kernel<<<grid, VT, 0, ctx->stream>>>(n, (PcgState *)state, x, d, r, q, dinv, z,
+                                                   ctx->d_partials, ctx->d_counter);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+int pcg_after_betanom(b2f_ctx *ctx, void *state, double *history, int history_cap)
+{
+   pcg_after_betanom_kernel<<<1, 1, 0, ctx->stream>>>((PcgState *)state, history, history_cap);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+int pcg_direction(b2f_ctx *ctx, void *state, int64_t n, const double *z, double *d)
+{
+   pcg_direction_kernel<<<stream_grid(ctx, n, 4), VT, 0, ctx->stream>>>(n, (PcgState *)state, z, d);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+int pcg_after_den(b2f_ctx *ctx, void *state)
+{
+   pcg_after_den_kernel<<<1, 1, 0, ctx->stream>>>((PcgState *)state);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+double *pcg_dot_slot(void *state) { return &((PcgState *)state)->dot_tmp; }
+
+void pcg_read_state(const void *host_copy, int *iter, int *done, int *converged, int *final_iter,
+                    double *nom0, double *betanom)
+{
+   const PcgState *st = (const PcgState *)host_copy;
+   *iter = st->iter; *done = st->done; *converged = st->converged; *final_iter = st->final_iter;
+   *nom0 = st->nom0; *betanom = st->betanom;
+}
+
+} // namespace b2f
