@@ -27,6 +27,8 @@
 //  * FUSED: x is gathered straight into registers (index -1 = essential dof: reads 0 and
 //    is not scattered), y is scattered with FP64 atomics (RED.ADD.F64 in L2).
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b2f
@@ -113,7 +115,14 @@ __device__ __forceinline__ bool load_qdata(double *dst, const double *src, int n
 // =====================================================================================
 // 3D kernel
 // =====================================================================================
-template <int KIND, int D, int Q, int NEB>
+// DMODE: how the quadrature data reaches the D-apply stage
+//   0  TMA bulk copy of the CTA's slab into shared memory, scalar LDS reads
+//   1  same, rows read back with 128-bit LDS (conflict-free for even Q)
+//   2  no staging: L2 bulk prefetch of the slab at kernel entry, rows loaded straight into
+//      registers with 128-bit LDG right before use (each D value is used exactly once)
+//   3  as 2, loads issued before the y-stage so they overlap it (costs registers)
+//   4  as 2 without the L2 prefetch
+template <int KIND, int D, int Q, int NEB, int DMODE = 0>
 struct Cfg3D
 {
    static constexpr bool DIFF = (KIND == B2F_KIND_DIFFUSION);
@@ -132,18 +141,46 @@ struct Cfg3D
    static constexpr int SE = pad16(T2, 1); // E[field][qy][t2]
    static constexpr int R1 = (NA * D * SA > NA * Q * SF) ? NA * D * SA : NA * Q * SF;
    static constexpr int R2 = (NC * D * SC > NC * Q * SE) ? NC * D * SC : NC * Q * SE;
-   static constexpr int QD = NEB * NQD * Q3; // quadrature data tile
+   static constexpr bool STAGED = DMODE <= 1;                // D goes through shared memory
+   static constexpr int QD = STAGED ? NEB * NQD * Q3 : 0;    // quadrature data tile
    static constexpr size_t SMEM = 16 + sizeof(double) * (size_t)(QD + R1 + R2);
    static_assert(T1 <= NT && T2 <= NT, "one task per thread per stage");
 };
 
-template <int KIND, int D, int Q, int NEB, bool FUSED, bool COLLOC>
-__global__ void __launch_bounds__(Cfg3D<KIND, D, Q, NEB>::NT)
+// one row of Q consecutive quadrature-data values -> registers (128-bit accesses when the
+// row is 16-byte aligned, i.e. Q even; works for shared and global pointers alike)
+template <int Q, bool GLOBAL>
+__device__ __forceinline__ void load_row(const double *__restrict__ p, double (&v)[Q])
+{
+   if constexpr (Q % 2 == 0)
+   {
+      const double2 *p2 = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+      for (int i = 0; i < Q / 2; i++)
+      {
+         const double2 w = GLOBAL ? __ldg(p2 + i) : p2[i];
+         v[2 * i] = w.x; v[2 * i + 1] = w.y;
+      }
+   }
+   else
+   {
+#pragma unroll
+      for (int i = 0; i < Q; i++) { v[i] = GLOBAL ? __ldg(p + i) : p[i]; }
+   }
+}
+
+__device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes)
+{
+   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+template <int KIND, int D, int Q, int NEB, bool FUSED, bool COLLOC, int DMODE, int MINB>
+__global__ void __launch_bounds__(Cfg3D<KIND, D, Q, NEB, DMODE>::NT, MINB)
 pa_apply_3d_kernel(const __grid_constant__ Basis<D, Q> bs, const double *__restrict__ qdata,
                    const double *__restrict__ x, double *__restrict__ y,
-                   const int *__restrict__ idx, const int64_t ne)
+                   const int *__restrict__ idx, const int64_t ne, const int pf)
 {
-   using C = Cfg3D<KIND, D, Q, NEB>;
+   using C = Cfg3D<KIND, D, Q, NEB, DMODE>;
    constexpr bool DIFF = C::DIFF;
    constexpr int D2 = C::D2, D3 = C::D3, Q2 = C::Q2, Q3 = C::Q3;
    extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -156,9 +193,37 @@ pa_apply_3d_kernel(const __grid_constant__ Basis<D, Q> bs, const double *__restr
    const int64_t e0 = (int64_t)blockIdx.x * NEB;
    const int nev = (int)((ne - e0) < NEB ? (ne - e0) : NEB); // valid elements in this tile
 
-   // ---- kick off the quadrature-data stream (TMA) -----------------------------------
-   const bool use_bar =
-      load_qdata<C::NT>(qd, qdata + e0 * (int64_t)(C::NQD * Q3), nev * C::NQD * Q3, bar);
+   // ---- kick off the quadrature-data stream (TMA into smem, or an L2 prefetch) -------
+   bool use_bar = false;
+   const double *qslab = qdata + e0 * (int64_t)(C::NQD * Q3);
+   if constexpr (C::STAGED)
+   {
+      use_bar = load_qdata<C::NT>(qd, qslab, nev * C::NQD * Q3, bar);
+      // keep HBM busy while this CTA computes: pull the slab (and gather indices) of the CTA
+      // that will run `pf` blocks later into L2, so its TMA copy is an L2 hit
+      if (pf > 0 && t == 32)
+      {
+         const int64_t ep = e0 + (int64_t)pf * NEB;
+         if (ep + NEB <= ne)
+         {
+            const uintptr_t q = reinterpret_cast<uintptr_t>(qdata + ep * (int64_t)(C::NQD * Q3)) & ~(uintptr_t)15;
+            l2_prefetch_bulk(reinterpret_cast<const void *>(q), ((uint32_t)(NEB * C::NQD * Q3) * 8u) & ~15u);
+            if (FUSED)
+            {
+               const uintptr_t a = reinterpret_cast<uintptr_t>(idx + ep * D3) & ~(uintptr_t)15;
+               l2_prefetch_bulk(reinterpret_cast<const void *>(a), ((uint32_t)(NEB * D3) * 4u) & ~15u);
+            }
+         }
+      }
+   }
+   else if constexpr (DMODE != 4)
+   {
+      if (t == 0)
+      {
+         const uintptr_t q = reinterpret_cast<uintptr_t>(qslab) & ~(uintptr_t)15;
+         l2_prefetch_bulk(reinterpret_cast<const void *>(q), ((uint32_t)(nev * C::NQD * Q3) * 8u) & ~15u);
+      }
+   }
 
    // ---- stage 1 (z): gather + contraction over dz ; task (dx,dy,e) ------------------
    int gi[D]; // gather indices, reused by the scatter
@@ -206,6 +271,22 @@ pa_apply_3d_kernel(const __grid_constant__ Basis<D, Q> bs, const double *__restr
    }
    __syncthreads();
 
+   // DMODE 3: issue this thread's quadrature-data loads now; they land during the y-stage
+   double dearly[DMODE == 3 ? C::NQD : 1][DMODE == 3 ? Q : 1];
+   if constexpr (DMODE == 3)
+   {
+      const int e = t / Q2, row = t - e * Q2;
+#pragma unroll
+      for (int k = 0; k < C::NQD; k++)
+#pragma unroll
+         for (int qx = 0; qx < Q; qx++) { dearly[k][qx] = 0.0; }
+      if (t < C::T3 && e < nev)
+      {
+         const double *dq = qslab + e * (C::NQD * Q3) + Q * row;
+#pragma unroll
+         for (int k = 0; k < C::NQD; k++) { load_row<Q, true>(dq + k * Q3, dearly[k]); }
+      }
+   }
    // ---- stage 2 (y): contraction over dy ; task t2 = dx + D*(qz + Q*e) --------------
    if (t < C::T2)
    {
@@ -284,17 +365,48 @@ pa_apply_3d_kernel(const __grid_constant__ Basis<D, Q> bs, const double *__restr
          }
          gx[qx] = vx; gy[qx] = vy; gz[qx] = vz;
       }
-      // quadrature data: wait for the TMA slab, then apply D at the Q points of this line
+      // quadrature data of this x-line -> registers (from the TMA slab or straight from HBM/L2)
       if (use_bar) { mbar_wait(bar, 0); }
       const int e = t / Q2, row = t - e * Q2; // row = qy + Q*qz
-      const double *dq = qd + e * (C::NQD * Q3) + Q * row;
+      double dv[C::NQD][Q];
+      if constexpr (DMODE != 3)
+      {
+         const double *dq = (C::STAGED ? qd : qslab) + e * (C::NQD * Q3) + Q * row;
+         if (C::STAGED || e < nev)
+         {
+#pragma unroll
+            for (int k = 0; k < C::NQD; k++)
+            {
+               if (DMODE == 0)
+               {
+#pragma unroll
+                  for (int qx = 0; qx < Q; qx++) { dv[k][qx] = dq[k * Q3 + qx]; }
+               }
+               else { load_row<Q, !C::STAGED>(dq + k * Q3, dv[k]); }
+            }
+         }
+         else
+         {
+#pragma unroll
+            for (int k = 0; k < C::NQD; k++)
+#pragma unroll
+               for (int qx = 0; qx < Q; qx++) { dv[k][qx] = 0.0; }
+         }
+      }
+      else
+      {
+#pragma unroll
+         for (int k = 0; k < C::NQD; k++)
+#pragma unroll
+            for (int qx = 0; qx < Q; qx++) { dv[k][qx] = dearly[k][qx]; }
+      }
       if (DIFF)
       {
 #pragma unroll
          for (int qx = 0; qx < Q; qx++)
          {
-            const double O11 = dq[qx], O12 = dq[Q3 + qx], O13 = dq[2 * Q3 + qx];
-            const double O22 = dq[3 * Q3 + qx], O23 = dq[4 * Q3 + qx], O33 = dq[5 * Q3 + qx];
+            const double O11 = dv[0][qx], O12 = dv[1 % C::NQD][qx], O13 = dv[2 % C::NQD][qx];
+            const double O22 = dv[3 % C::NQD][qx], O23 = dv[4 % C::NQD][qx], O33 = dv[5 % C::NQD][qx];
             const double ux = gx[qx], uy = gy[qx], uz = gz[qx];
             gx[qx] = (O11 * ux) + (O12 * uy) + (O13 * uz);
             gy[qx] = (O12 * ux) + (O22 * uy) + (O23 * uz);
@@ -304,7 +416,7 @@ pa_apply_3d_kernel(const __grid_constant__ Basis<D, Q> bs, const double *__restr
       else
       {
 #pragma unroll
-         for (int qx = 0; qx < Q; qx++) { gx[qx] *= dq[qx]; }
+         for (int qx = 0; qx < Q; qx++) { gx[qx] *= dv[0][qx]; }
       }
       // x^T
 #pragma unroll
@@ -636,10 +748,11 @@ inline void fill_basis(const b2f_pa *pa, Basis<D, Q> &bs)
       }
 }
 
-template <int KIND, int D, int Q, int NEB>
+// FUSEDSEL: 0 = E-vector form only, 1 = fused L-vector form only, 2 = both (runtime idx)
+template <int KIND, int D, int Q, int NEB, int DMODE = 0, int MINB = 1, int FUSEDSEL = 2>
 int launch_3d(b2f_pa *pa, const double *x, double *y, const int *idx)
 {
-   using C = Cfg3D<KIND, D, Q, NEB>;
+   using C = Cfg3D<KIND, D, Q, NEB, DMODE>;
    b2f_ctx *ctx = pa->ctx;
    if ((int)C::SMEM > ctx->max_smem_optin)
    {
@@ -651,22 +764,40 @@ int launch_3d(b2f_pa *pa, const double *x, double *y, const int *idx)
    const int64_t grid = cdiv(pa->ne, NEB);
    auto go = [&](auto kern) -> int
    {
-      B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+      // once per instantiation: opt in to the shared memory size and find how many CTAs are
+      // resident on the device -- that is the L2 prefetch distance (the slab a CTA prefetches
+      // belongs to the CTA that takes over its slot)
+      static int resident = 0;
+      if (resident == 0)
+      {
+         B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+         int occ = 0;
+         B2F_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NT, C::SMEM));
+         resident = (occ < 1 ? 1 : occ) * ctx->sm_count;
+      }
+      const char *pfs = getenv("B2F_PF");
+      const int pf = pfs ? atoi(pfs) : resident;
       timing_mark(ctx);
-      kern<<<(unsigned)grid, C::NT, C::SMEM, ctx->stream>>>(bs, pa->data, x, y, idx, pa->ne);
+      kern<<<(unsigned)grid, C::NT, C::SMEM, ctx->stream>>>(bs, pa->data, x, y, idx, pa->ne, pf);
       timing_mark(ctx);
       B2F_LAUNCH_CHECK(ctx);
       return B2F_OK;
    };
    const bool fused = idx != nullptr;
-   if (pa->collocated && D == Q)
+   if ((fused && FUSEDSEL == 0) || (!fused && FUSEDSEL == 1))
    {
-      constexpr bool CL = (D == Q);
-      return fused ? go(pa_apply_3d_kernel<KIND, D, Q, NEB, true, CL>)
-             : go(pa_apply_3d_kernel<KIND, D, Q, NEB, false, CL>);
+      set_error("pa_apply_3d: kernel form not instantiated");
+      return B2F_ERR_UNSUPPORTED;
    }
-   return fused ? go(pa_apply_3d_kernel<KIND, D, Q, NEB, true, false>)
-          : go(pa_apply_3d_kernel<KIND, D, Q, NEB, false, false>);
+   constexpr bool CL = (D == Q);
+   if (pa->collocated && CL)
+   {
+      if constexpr (FUSEDSEL != 0) { if (fused) { return go(pa_apply_3d_kernel<KIND, D, Q, NEB, true, CL, DMODE, MINB>); } }
+      if constexpr (FUSEDSEL != 1) { if (!fused) { return go(pa_apply_3d_kernel<KIND, D, Q, NEB, false, CL, DMODE, MINB>); } }
+   }
+   if constexpr (FUSEDSEL != 0) { if (fused) { return go(pa_apply_3d_kernel<KIND, D, Q, NEB, true, false, DMODE, MINB>); } }
+   if constexpr (FUSEDSEL != 1) { if (!fused) { return go(pa_apply_3d_kernel<KIND, D, Q, NEB, false, false, DMODE, MINB>); } }
+   return B2F_ERR_UNSUPPORTED;
 }
 
 template <int KIND, int D, int Q, int NEB>

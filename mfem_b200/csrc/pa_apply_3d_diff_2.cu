@@ -1,9 +1,35 @@
 // 3D diffusion PA kernels, D1D = 2..5 (split for parallel compilation)
+#include <cstdlib>
 #include "pa_dispatch.cuh"
+#include "pa_apply_pipe.cuh"
 namespace b2f
 {
+// experiment hook: B2F_VARIANT selects a kernel variant for (D1D,Q1D) = (5,6)
+static int variant()
+{
+   const char *s = getenv("B2F_VARIANT");
+   return s ? atoi(s) : 0;
+}
+
 int pa_apply_3d_diffusion_2(b2f_pa *pa, const double *x, double *y, const int *idx)
 {
+   if (pa->d1d == 5 && pa->q1d == 6 && idx)
+   {
+      constexpr int K = B2F_KIND_DIFFUSION;
+      switch (variant())
+      {
+         case 1: return launch_3d<K, 5, 6, 6, 0, 1, 1>(pa, x, y, idx);
+         case 20: return launch_3d_pipe<K, 5, 6, 6, 1>(pa, x, y, idx);
+         case 21: return launch_3d_pipe<K, 5, 6, 6, 2>(pa, x, y, idx);
+         case 22: return launch_3d_pipe<K, 5, 6, 3, 1>(pa, x, y, idx);
+         case 23: return launch_3d_pipe<K, 5, 6, 3, 4>(pa, x, y, idx);
+         case 24: return launch_3d_pipe<K, 5, 6, 4, 1>(pa, x, y, idx);
+         case 25: return launch_3d_pipe<K, 5, 6, 4, 3>(pa, x, y, idx);
+         case 26: return launch_3d_pipe<K, 5, 6, 8, 1>(pa, x, y, idx);
+         case 27: return launch_3d_pipe<K, 5, 6, 2, 1>(pa, x, y, idx);
+         default: break;
+      }
+   }
    switch (pa->d1d * 100 + pa->q1d)
    {
       B2F_CASE_3D(B2F_KIND_DIFFUSION, 2, 2)

@@ -8,19 +8,52 @@
 namespace b2f
 {
 
-// elements per CTA: fill ~half an SM's shared memory (two CTAs per SM), <= 288 threads
-constexpr int neb_3d(int kind, int D, int Q)
+// shared memory of one CTA of the 3D kernel holding n elements (bytes; mirrors Cfg3D::SMEM)
+constexpr int smem_3d(int kind, int D, int Q, int n)
 {
    const int nqd = kind == B2F_KIND_DIFFUSION ? 6 : 1;
    const int na = kind == B2F_KIND_DIFFUSION ? 2 : 1;
    const int nc = kind == B2F_KIND_DIFFUSION ? 3 : 1;
-   const int per = 8 * (nqd * Q * Q * Q + na * D * D * Q + nc * D * Q * Q);
-   int n = (110 * 1024) / per;
-   const int cap = 288 / (Q * Q);
-   if (n > cap) { n = cap; }
-   if (n > 32) { n = 32; }
-   if (n < 1) { n = 1; }
+   const int t1 = n * D * D, t2 = n * Q * D, t3 = n * Q * Q;
+   const int sa = pad16(t2, D), sf = pad16(t1, D), sc = pad16(t3, 1), se = pad16(t2, 1);
+   const int r1 = na * D * sa > na * Q * sf ? na * D * sa : na * Q * sf;
+   const int r2 = nc * D * sc > nc * Q * se ? nc * D * sc : nc * Q * se;
+   return 16 + 8 * (n * nqd * Q * Q * Q + r1 + r2);
+}
+
+// Elements per CTA.  Candidate i targets a different residency: 0 -> >= 4 CTAs per SM,
+// 1 -> 3 CTAs, 2 -> 2 CTAs (of the 227 KB an SM offers), always <= 512 threads.
+constexpr int neb_3d(int kind, int D, int Q, int cand)
+{
+   const int budget = cand == 0 ? 55 * 1024 : cand == 1 ? 74 * 1024 : 112 * 1024;
+   int n = 1;
+   while (n < 32 && smem_3d(kind, D, Q, n + 1) <= budget && (n + 1) * Q * Q <= 512) { n++; }
    return n;
+}
+
+// CTAs per SM the launch bounds ask for: what shared memory allows, but never fewer than
+// ~80 registers per thread
+constexpr int minb_3d(int kind, int D, int Q, int n)
+{
+   const int nt = ((n * Q * Q + 31) / 32) * 32;
+   int by_smem = (227 * 1024) / (smem_3d(kind, D, Q, n) + 1024);
+   const int by_regs = 65536 / (nt * 80);
+   int b = by_smem < by_regs ? by_smem : by_regs;
+   if (b > 8) { b = 8; }
+   return b < 1 ? 1 : b;
+}
+
+// measured choice of the candidate per (kind, D, Q) (tools/opbench.py sweeps, profiles/)
+constexpr int tuned_cand_3d(int kind, int D, int Q)
+{
+   // BP3-type (Q = D+2) diffusion, sweep of profiles/r01_sweep_*.txt
+   if (kind == B2F_KIND_DIFFUSION)
+   {
+      if (D == 2 || D == 4) { return 1; }
+      if (D == 7) { return 2; }
+      return 0;
+   }
+   return D <= 4 ? 0 : 1;
 }
 
 constexpr int neb_2d(int kind, int D, int Q)
@@ -33,10 +66,32 @@ constexpr int neb_2d(int kind, int D, int Q)
 
 #define B2F_CASE_3D(KIND, D_, Q_)                                                      \
    case (D_) * 100 + (Q_):                                                             \
-      return launch_3d<KIND, D_, Q_, neb_3d(KIND, D_, Q_)>(pa, x, y, idx);
+      return run_3d<KIND, D_, Q_>(pa, x, y, idx);
 #define B2F_CASE_2D(KIND, D_, Q_)                                                      \
    case (D_) * 100 + (Q_):                                                             \
       return launch_2d<KIND, D_, Q_, neb_2d(KIND, D_, Q_)>(pa, x, y, idx);
+
+// One (kind, D, Q): the E-vector form (AddMultPA seam) has one instantiation; the fused
+// L-vector form (the hot path) has three elements-per-CTA candidates, selected by the tuned
+// table or, for experiments, by the environment variable B2F_NEB_CAND = 0|1|2.
+template <int KIND, int D, int Q>
+int run_3d(b2f_pa *pa, const double *x, double *y, const int *idx)
+{
+   constexpr int N0 = neb_3d(KIND, D, Q, 0), N1 = neb_3d(KIND, D, Q, 1), N2 = neb_3d(KIND, D, Q, 2);
+   if (!idx) { return launch_3d<KIND, D, Q, N1, 1, 1, 0>(pa, x, y, idx); }
+   const char *s = getenv("B2F_NEB_CAND");
+   const int cand = s ? atoi(s) : tuned_cand_3d(KIND, D, Q);
+   if (cand == 0 || (cand == 1 && N1 == N0) || (cand == 2 && N2 == N0))
+   {
+      return launch_3d<KIND, D, Q, N0, 1, minb_3d(KIND, D, Q, N0), 1>(pa, x, y, idx);
+   }
+   if (cand == 1 || (cand == 2 && N2 == N1))
+   {
+      if constexpr (N1 != N0) { return launch_3d<KIND, D, Q, N1, 1, minb_3d(KIND, D, Q, N1), 1>(pa, x, y, idx); }
+   }
+   if constexpr (N2 != N1 && N2 != N0) { return launch_3d<KIND, D, Q, N2, 1, minb_3d(KIND, D, Q, N2), 1>(pa, x, y, idx); }
+   return B2F_ERR_UNSUPPORTED;
+}
 
 inline int unsupported(const b2f_pa *pa)
 {
