@@ -150,8 +150,8 @@ def _dp(t):
 
 # ---- mesh + space ------------------------------------------------------------------------
 def curve_map(X):
-    """The smooth displacement of BASELINE config C5 (oracle/ref_driver.cpp
-    curve_map): X is (..., dim)."""
+    """The smooth displacement of BASELINE config C5: x += 0.05 sin(2 pi y)
+    sin(2 pi z), cyclically.  X is (..., dim)."""
     a, tp = 0.05, 2 * np.pi
     Y = X.copy()
     if X.shape[-1] == 3:

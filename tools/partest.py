@@ -1,0 +1,128 @@
+#!/usr/bin/env python
+"""tools/partest.py -- multi-GPU parity of the rank-parallel path (run under torchrun).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29511 tools/partest.py [--p 3] [--n 6] [--kind diffusion]
+
+Every rank owns one block of a Cartesian partition, attaches the NCCL halo and checks, against
+the SERIAL problem on the union mesh solved on its own GPU:  P reproduces the global field,
+y = P^T A P x, the constrained operator, the assembled diagonal, and Jacobi-PCG (iteration
+count within +-1, solution to solver tolerance).  Exit code 0 and "PARTEST OK" on success.
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import mfem_b200 as m  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--p", type=int, default=3)
+ap.add_argument("--n", type=int, default=6, help="elements per side per rank")
+ap.add_argument("--kind", default="diffusion")
+a = ap.parse_args()
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+lr = int(os.environ.get("LOCAL_RANK", rank))
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+dev = m.Device(f"cuda:{lr}")
+grid = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
+N = [a.n * g for g in grid]
+p = a.p
+
+
+def build(mesh):
+    fes = m.FiniteElementSpace(mesh, m.H1_FECollection(p, 3))
+    it = (m.MassIntegrator if a.kind == "mass" else m.DiffusionIntegrator)(1.0, m.IntRules.Get(3, 2 * p + 3))
+    form = m.BilinearForm(dev, fes)
+    form.AddDomainIntegrator(it)
+    form.Assemble()
+    return fes, form
+
+
+# parallel problem
+fes, form = build(m.Mesh(3, N[0], N[1], N[2], True, part=grid, rank=rank))
+ids = [m.Halo.unique_id() if rank == 0 else None]
+dist.broadcast_object_list(ids, src=0)
+halo = m.Halo(dev, rank, world, fes.ndofs, fes.halo_tables, ids[0])
+form.SetHalo(halo)
+# serial problem on the union mesh (every rank solves it on its own GPU as the reference)
+sfes, sform = build(m.Mesh(3, N[0], N[1], N[2], True, part=(1, 1, 1), rank=0))
+slat = sfes.halo_tables["ldof_lattice"]
+lat = fes.halo_tables["ldof_lattice"]
+own = fes.halo_tables["ltdof_ldof"]
+nlat = len(slat)
+s_of_lat = np.empty(nlat, np.int64)
+s_of_lat[slat] = np.arange(nlat)
+t2s = torch.from_numpy(s_of_lat[lat[own]]).to(dev.tdev)   # my true dofs -> serial dof ids
+l2s = torch.from_numpy(s_of_lat[lat]).to(dev.tdev)
+
+
+def rel(u, v):
+    return float(torch.linalg.norm(u - v) / torch.linalg.norm(v))
+
+
+gen = torch.Generator(device="cpu").manual_seed(7)
+xs = torch.rand(nlat, dtype=torch.float64, generator=gen).to(dev.tdev)  # same on every rank
+x_t = xs[t2s].contiguous()
+# P
+x_l = dev.empty(fes.ndofs)
+halo.Mult(x_t, x_l)
+dev.sync()
+assert torch.equal(x_l, xs[l2s]), "P does not reproduce the global field"
+# y = P^T A P x
+y_t, ys = dev.empty(fes.ntdofs), dev.empty(nlat)
+form.Mult(x_t, y_t)
+sform.Mult(xs, ys)
+dev.sync()
+e1 = rel(y_t, ys[t2s])
+assert e1 < 1e-12, f"RAP operator parity {e1}"
+# constrained operator + diagonal
+ess, sess = fes.GetEssentialTrueDofs(), sfes.GetEssentialTrueDofs()
+b_l = m.LinearForm(dev, fes).Assemble()
+b_t = dev.empty(fes.ntdofs)
+halo.MultTranspose(b_l, b_t)
+bs = m.LinearForm(dev, sfes).Assemble()
+dev.sync()
+assert rel(b_t, bs[t2s]) < 1e-12
+A, _, B = form.FormLinearSystem(ess, dev.zeros(fes.ntdofs), b_t)
+As, _, Bs = sform.FormLinearSystem(sess, dev.zeros(nlat), bs)
+A.Mult(x_t, y_t)
+As.Mult(xs, ys)
+dev.sync()
+e2 = rel(y_t, ys[t2s])
+assert e2 < 1e-12, f"constrained operator parity {e2}"
+dg, dgs = dev.empty(fes.ntdofs), dev.empty(nlat)
+form.AssembleDiagonal(dg)
+sform.AssembleDiagonal(dgs)
+dev.sync()
+e3 = rel(dg, dgs[t2s])
+assert e3 < 1e-12, f"diagonal parity {e3}"
+# all-reduced dot
+d_par = halo.Dot(x_t, y_t)
+d_ser = float(torch.dot(xs, ys))
+assert abs(d_par - d_ser) < 1e-12 * abs(d_ser), (d_par, d_ser)
+# PCG
+M, Ms = m.OperatorJacobiSmoother(form, ess), m.OperatorJacobiSmoother(sform, sess)
+res = []
+for (AA, MM, BB, n) in ((A, M, B, fes.ntdofs), (As, Ms, Bs, nlat)):
+    cg = m.CGSolver()
+    cg.SetRelTol(1e-8); cg.SetMaxIter(1000); cg.SetOperator(AA); cg.SetPreconditioner(MM)
+    X = dev.zeros(n)
+    cg.Mult(BB, X)
+    res.append((cg.GetNumIterations(), cg.GetConverged(), X))
+(it_p, conv_p, X_p), (it_s, conv_s, X_s) = res
+assert conv_p and conv_s and abs(it_p - it_s) <= 1, (it_p, it_s)
+e4 = rel(X_p, X_s[t2s])
+assert e4 < 1e-6, f"PCG solution {e4}"
+dist.barrier()
+if rank == 0:
+    print(f"PARTEST OK world={world} grid={grid} p={p} n/rank={a.n} kind={a.kind}: RAP {e1:.1e} constrained {e2:.1e} "
+          f"diag {e3:.1e} pcg its {it_p} vs serial {it_s}, sol {e4:.1e}")
+halo.close()
+dist.destroy_process_group()
