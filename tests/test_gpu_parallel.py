@@ -56,7 +56,7 @@ def test_nccl_halo_matches_serial(world, kind, p):
     port = 29500 + world * 7 + p
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
-           os.path.join(ROOT, "tools", "partest.py"), "--p", str(p), "--n", "5", "--kind", kind]
+           os.path.join(ROOT, "tools", "partest.py"), "--order", str(p), "--elems", "5", "--integrator", kind]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
     out = r.stdout.decode(errors="replace")
     assert r.returncode == 0 and "PARTEST OK" in out, out[-3000:]

@@ -2,7 +2,7 @@
 """tools/partest.py -- multi-GPU parity of the rank-parallel path (run under torchrun).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        --master-port 29511 tools/partest.py [--p 3] [--n 6] [--kind diffusion]
+        --master-port 29511 tools/partest.py [--order 3] [--elems 6] [--integrator diffusion]
 
 Every rank owns one block of a Cartesian partition, attaches the NCCL halo and checks, against
 the SERIAL problem on the union mesh solved on its own GPU:  P reproduces the global field,
@@ -21,9 +21,9 @@ import torch.distributed as dist  # noqa: E402
 import mfem_b200 as m  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--p", type=int, default=3)
-ap.add_argument("--n", type=int, default=6, help="elements per side per rank")
-ap.add_argument("--kind", default="diffusion")
+ap.add_argument("--order", dest="p", type=int, default=3)
+ap.add_argument("--elems", dest="n", type=int, default=6, help="elements per side per rank")
+ap.add_argument("--integrator", dest="kind", default="diffusion")
 a = ap.parse_args()
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
