@@ -104,7 +104,9 @@ int b2f_cartesian_h1_space_h(int dim, int nx, int ny, int nz, int p, int sfc_ord
  * tables general/communication.cpp:543,579).  No communication: every rank calls it with
  * its own `rank` (= ix + px*(iy + py*iz)).  All array arguments may be NULL;
  * sizes_h[10] = {lnx, lny, lnz, ne, n_ldofs, n_tdofs, n_nbr, n_shr, n_ext, n_bdr}.
- * The local space is numbered as b2f_cartesian_h1_space_h numbers the local block;
+ * The local space is numbered as b2f_cartesian_h1_space_h numbers the local block, then
+ * permuted so that the rank's own (true) dofs come first: ltdof_ldof is the identity and a
+ * true-dof vector is the head of a local-dof vector (the halo then works in place);
  * elem_vertices_h holds GLOBAL coordinates; bdr_ldofs_h the local dofs on the GLOBAL
  * boundary; ldof_lattice_h the point gx + LX*(gy + LY*gz) of each local dof on the global
  * (p*nx+1, p*ny+1, p*nz+1) lattice.  The remaining tables are b2f_halo_create's inputs. */

@@ -50,6 +50,9 @@ int halo_mult_transpose(b2f_halo *h, const double *x_l, double *y_t);
 int halo_allreduce_sum(b2f_halo *h, double *d_scalar, int count);
 int halo_sizes(const b2f_halo *h, int *n_ldofs, int *n_tdofs);
 const int *halo_ldof_to_tdof_h(const b2f_halo *h); // host array [n_ldofs]: tdof or -1
+bool halo_is_prefix(const b2f_halo *h);
+int halo_mult_inplace(b2f_halo *h, double *v);
+int halo_mult_transpose_inplace(b2f_halo *h, double *v);
 
 template <typename T>
 static int upload(const T *h, size_t n, T **d)
@@ -625,11 +628,33 @@ static int local_mult(b2f_operator *op, const double *x_l, double *y_l, bool con
 }
 
 // A on the operator's own vectors (true-dof vectors when a halo is attached):
-// RAPOperator::Mult (linalg/operator.hpp:998): P, A, P^T
-static int rap_mult(b2f_operator *op, const double *x, double *y, bool constrained_mask)
+// RAPOperator::Mult (linalg/operator.hpp:998): P, A, P^T.
+// lcap: x and y are caller-owned buffers with room for n_ldofs entries (the PCG work
+// vectors); with the owned-first numbering P and P^T then run in place and no vector is
+// copied.  Otherwise the true-dof vectors go through the L-vector scratch xl / yl.
+static int rap_mult(b2f_operator *op, const double *x, double *y, bool constrained_mask, bool lcap = false)
 {
    if (!op->halo) { return local_mult(op, x, y, constrained_mask); }
+   b2f_ctx *ctx = op->ctx;
    const int nl = op->r->ndofs;
+   if (halo_is_prefix(op->halo))
+   {
+      int nl2 = 0, nt = 0;
+      halo_sizes(op->halo, &nl2, &nt);
+      double *xl = const_cast<double *>(x), *yl = y;
+      if (!lcap)
+      {
+         B2F_TRY(ensure(&op->xl, nl));
+         B2F_TRY(ensure(&op->yl, nl));
+         xl = op->xl; yl = op->yl;
+         B2F_CUDA(cudaMemcpyAsync(xl, x, sizeof(double) * nt, cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+      B2F_TRY(halo_mult_inplace(op->halo, xl));
+      B2F_TRY(local_mult(op, xl, yl, constrained_mask));
+      B2F_TRY(halo_mult_transpose_inplace(op->halo, yl));
+      if (!lcap) { B2F_CUDA(cudaMemcpyAsync(y, yl, sizeof(double) * nt, cudaMemcpyDeviceToDevice, ctx->stream)); }
+      return B2F_OK;
+   }
    B2F_TRY(ensure(&op->xl, nl));
    B2F_TRY(ensure(&op->yl, nl));
    B2F_TRY(halo_mult(op->halo, x, op->xl));
@@ -663,10 +688,8 @@ int b2f_operator_mult_unfused(b2f_operator *op, const double *x_l, double *y_l)
    return local_mult_unfused(op, x_l, y_l);
 }
 
-int b2f_operator_mult_constrained(b2f_operator *op, const double *x, double *y)
+static int mult_constrained(b2f_operator *op, const double *x, double *y, bool lcap)
 {
-   B2F_REQUIRE(op && x && y, "b2f_operator_mult_constrained: NULL argument");
-   B2F_REQUIRE(x != y, "b2f_operator_mult_constrained: x and y alias");
    b2f_ctx *ctx = op->ctx;
    if (op->signed_map && op->n_ess)
    {
@@ -681,9 +704,16 @@ int b2f_operator_mult_constrained(b2f_operator *op, const double *x, double *y)
    {
       // same result without the copy: constrained dofs read as 0 in the gather and are
       // skipped by the scatter
-      B2F_TRY(rap_mult(op, x, y, true));
+      B2F_TRY(rap_mult(op, x, y, true, lcap));
    }
    return copy_entries(ctx, y, x, op->ess, op->n_ess);
+}
+
+int b2f_operator_mult_constrained(b2f_operator *op, const double *x, double *y)
+{
+   B2F_REQUIRE(op && x && y, "b2f_operator_mult_constrained: NULL argument");
+   B2F_REQUIRE(x != y, "b2f_operator_mult_constrained: x and y alias");
+   return mult_constrained(op, x, y, false);
 }
 
 int b2f_operator_assemble_diagonal(b2f_operator *op, double *diag)
@@ -781,7 +811,10 @@ int b2f_pcg(b2f_operator *op, const double *dinv, const double *b, double *x,
    const int64_t n = b2f_operator_height(op);
    const int check_every = opt->check_every > 0 ? opt->check_every : 1;
    void *st = ctx->d_scalars; // PcgState lives in the context's device scalars
-   for (int k = 0; k < 4; k++) { B2F_TRY(ensure(&op->pcg_vec[k], n)); }
+   // d and q (the operator's input and output) get room for a local-dof vector so that the
+   // halo can run in place on them
+   const int64_t ncap = halo ? (int64_t)op->r->ndofs : n;
+   for (int k = 0; k < 4; k++) { B2F_TRY(ensure(&op->pcg_vec[k], ncap)); }
    double *r = op->pcg_vec[0], *d = op->pcg_vec[1], *z = op->pcg_vec[2], *q = op->pcg_vec[3];
    double *hist = nullptr;
    if (history_h && history_capacity > 0)
@@ -812,7 +845,7 @@ int b2f_pcg(b2f_operator *op, const double *dinv, const double *b, double *x,
    B2F_TRY(reduce());
    B2F_TRY(pcg_after_nom0(ctx, st, opt->rel_tol, opt->abs_tol, opt->max_iter, hist,
                           hist ? history_capacity : 0));
-   B2F_TRY(b2f_operator_mult_constrained(op, d, q)); // z = A d
+   B2F_TRY(mult_constrained(op, d, q, true)); // z = A d
    B2F_TRY(dot_to_device(ctx, n, q, d, pcg_dot_slot(st)));
    B2F_TRY(reduce());
    B2F_TRY(pcg_after_den0(ctx, st));
@@ -837,7 +870,7 @@ int b2f_pcg(b2f_operator *op, const double *dinv, const double *b, double *x,
       B2F_TRY(reduce());
       B2F_TRY(pcg_after_betanom(ctx, st, hist, hist ? history_capacity : 0));
       B2F_TRY(pcg_direction(ctx, st, n, zz, d));
-      B2F_TRY(b2f_operator_mult_constrained(op, d, q));
+      B2F_TRY(mult_constrained(op, d, q, true));
       B2F_TRY(dot_to_device(ctx, n, d, q, pcg_dot_slot(st)));
       B2F_TRY(reduce());
       B2F_TRY(pcg_after_den(ctx, st));

@@ -104,6 +104,7 @@ struct b2f_halo
    int *unq_i = nullptr;          // [n_unq+1] CSR into unq_j
    int *unq_j = nullptr;          // [n_shr] positions in shr_buf, ascending per row
    double *shr_buf = nullptr, *ext_buf = nullptr;
+   bool prefix = false;           // ltdof_ldof is the identity: a T-vector is the head of an L-vector
 };
 
 namespace b2f
@@ -206,6 +207,49 @@ int halo_mult_transpose(b2f_halo *h, const double *x_l, double *y_t)
    return B2F_OK;
 }
 
+// In-place forms for the owned-first numbering (ltdof_ldof = identity): v has n_ldofs entries
+// whose head is the true-dof vector.  P only fills the tail, P^T only adds into the head.
+bool halo_is_prefix(const b2f_halo *h) { return h->prefix; }
+
+int halo_mult_inplace(b2f_halo *h, double *v)
+{
+   b2f_ctx *ctx = h->ctx;
+   cudaStream_t s = ctx->stream;
+   if (h->n_shr)
+   {
+      gather_from_kernel<<<(unsigned)cdiv(h->n_shr, 256), 256, 0, s>>>(h->n_shr, h->shr_ltdof, v, h->shr_buf);
+      B2F_LAUNCH_CHECK(ctx);
+   }
+   int rc = exchange(h, h->shr_buf, h->shr_off, h->ext_buf, h->ext_off);
+   if (rc) { return rc; }
+   if (h->n_ext)
+   {
+      scatter_to_kernel<<<(unsigned)cdiv(h->n_ext, 256), 256, 0, s>>>(h->n_ext, h->ext_ldof, h->ext_buf, v);
+      B2F_LAUNCH_CHECK(ctx);
+   }
+   return B2F_OK;
+}
+
+int halo_mult_transpose_inplace(b2f_halo *h, double *v)
+{
+   b2f_ctx *ctx = h->ctx;
+   cudaStream_t s = ctx->stream;
+   if (h->n_ext)
+   {
+      gather_from_kernel<<<(unsigned)cdiv(h->n_ext, 256), 256, 0, s>>>(h->n_ext, h->ext_ldof, v, h->ext_buf);
+      B2F_LAUNCH_CHECK(ctx);
+   }
+   int rc = exchange(h, h->ext_buf, h->ext_off, h->shr_buf, h->shr_off);
+   if (rc) { return rc; }
+   if (h->n_unq)
+   {
+      assemble_shared_kernel<<<(unsigned)cdiv(h->n_unq, 256), 256, 0, s>>>(
+         h->n_unq, h->unq_ltdof, h->unq_i, h->unq_j, h->shr_buf, v);
+      B2F_LAUNCH_CHECK(ctx);
+   }
+   return B2F_OK;
+}
+
 int halo_allreduce_sum(b2f_halo *h, double *d_scalar, int count)
 {
    if (h->nranks == 1) { return B2F_OK; }
@@ -281,8 +325,10 @@ int b2f_halo_create(b2f_ctx *ctx, const void *nccl_id128_h, int rank, int nranks
       { return fail("b2f_halo_create: bad neighbour rank %d", nbr_rank_h[k]); }
    }
    h->l2t_h.assign(n_ldofs, -1);
+   h->prefix = true;
    for (int i = 0; i < n_tdofs; i++)
    {
+      h->prefix = h->prefix && ltdof_ldof_h[i] == i;
       const int l = ltdof_ldof_h[i];
       if (l < 0 || l >= n_ldofs || h->l2t_h[l] != -1) { return fail("b2f_halo_create: bad ltdof_ldof entry %d", l); }
       h->l2t_h[l] = i;

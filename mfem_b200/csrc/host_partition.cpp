@@ -6,7 +6,8 @@
 //   ParMesh(comm, mesh, partitioning)                 mesh/pmesh.cpp:106
 //   GroupTopology::Create, master = lowest rank       general/communication.cpp:97-124
 //   ParFiniteElementSpace::ConstructTrueDofs          fem/pfespace.cpp:2169
-//     (a true dof is a local dof whose group master is this rank; ltdof order = ldof order)
+//     (a true dof is a local dof whose group master is this rank; ltdof order = ldof order;
+//      here the local dofs are additionally renumbered owned-first, see below)
 //   GroupCommunicator::GetNeighborLTDofTable / GetNeighborLDofTable
 //                                                     general/communication.cpp:543,579
 // Every rank runs this independently (no communication): a dof is identified by its point
@@ -123,6 +124,27 @@ extern "C" int b2f_cartesian_partition_h(int dim, int nx, int ny, int nz, int p,
       bool on_bdr = false;
       for (int a = 0; a < dim; a++) { on_bdr = on_bdr || g[a] == 0 || g[a] == L[a] - 1; }
       if (on_bdr) { bdr.push_back(l); }
+   }
+   // Local renumbering: owned (true) dofs first, in their original relative order, then the
+   // dofs owned by neighbours.  With it ltdof_ldof is the identity, a true-dof vector is the
+   // head of a local vector, and P / P^T only touch the tail (halo.cu works in place).
+   {
+      std::vector<int> perm(nl);
+      int nown = 0, next = 0;
+      for (int l = 0; l < nl; l++) { nown += owner[l] == rank; }
+      next = nown;
+      nown = 0;
+      for (int l = 0; l < nl; l++) { perm[l] = owner[l] == rank ? nown++ : next++; }
+      for (auto &v : ed) { v = perm[v]; }
+      std::vector<int64_t> lat2(nl);
+      std::vector<int> own2(nl);
+      for (int l = 0; l < nl; l++) { lat2[perm[l]] = lat[l]; own2[perm[l]] = owner[l]; }
+      lat.swap(lat2);
+      owner.swap(own2);
+      for (auto &v : bdr) { v = perm[v]; }
+      std::sort(bdr.begin(), bdr.end());
+      for (auto &kv : shr) { for (auto &q : kv.second) { q.second = perm[q.second]; } }
+      for (auto &kv : ext) { for (auto &q : kv.second) { q.second = perm[q.second]; } }
    }
    std::vector<int> l2t(nl, -1), ltdof;
    for (int l = 0; l < nl; l++)
