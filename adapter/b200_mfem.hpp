@@ -1,0 +1,331 @@
+// adapter/b200_mfem.hpp -- MFEM-side binding of libb200fem.so (include/b200fem.h).
+//
+// Compiled against MFEM's own headers (v4.9.1-dev); this is the code a maintainer adds to an
+// MFEM application to route the partial-assembly hot path to the B200 library.  It honours
+// MFEM's three nested seams:
+//
+//   seam 3  b200::DiffusionIntegrator / b200::MassIntegrator : mfem::{Diffusion,Mass}Integrator
+//           override AssemblePA / AddMultPA / AssembleDiagonalPA (fem/bilininteg.hpp:49-95), so
+//           an unchanged `BilinearForm a; a.SetAssemblyLevel(PARTIAL); a.AddDomainIntegrator(
+//           new b200::DiffusionIntegrator(one))` runs MFEM's own PABilinearFormExtension with the
+//           B200 element kernels (E-vector in, E-vector out).
+//   seam 1  b200::PAOperator : mfem::Operator (linalg/operator.hpp:25-313) -- the FUSED operator
+//           y = R^T A_E R x on L-vectors (one kernel, no E-vector in memory), with
+//           AssembleDiagonal; b200::ConstrainedOperator wraps it the way
+//           Operator::FormLinearSystem does (linalg/operator.cpp:130-146, 526-660).
+//           b200::CGSolver : mfem::IterativeSolver runs the whole PCG (linalg/solvers.cpp:
+//           869-1050) on the device with device-resident scalars.
+//
+// Memory: "host-MFEM" mode: MFEM is built CPU-only, Vectors live
+// on the host, the adapter owns the device copies and moves x / y across the boundary of each
+// call (the CG adapter moves b in and x out once per solve).  With an MFEM built with
+// MFEM_USE_CUDA the same calls take x.Read() / y.Write() device pointers and the copies vanish.
+// Errors: a failing library call becomes mfem::mfem_error (MFEM_ABORT), the reference's policy.
+#ifndef B200_MFEM_HPP
+#define B200_MFEM_HPP
+
+#include <memory>
+#include <vector>
+
+#include "mfem.hpp"
+#include "../include/b200fem.h"
+
+namespace b200
+{
+
+#define B200_CHECK(call)                                                               \
+   do                                                                                  \
+   {                                                                                   \
+      if ((call) != B2F_OK) { MFEM_ABORT("libb200fem: " << b2f_last_error()); }        \
+   } while (0)
+
+/// The process-wide library context: the role of mfem::Device("cuda") (general/device.hpp:128).
+class Context
+{
+   b2f_ctx *ctx = nullptr;
+   Context(int dev) { B200_CHECK(b2f_ctx_create(dev, nullptr, &ctx)); }
+public:
+   ~Context() { b2f_ctx_destroy(ctx); }
+   static Context &Get(int dev = 0)
+   {
+      static Context c(dev);
+      return c;
+   }
+   b2f_ctx *get() const { return ctx; }
+};
+
+/// A device buffer of doubles (what mfem::Vector's device pointer would be).
+class DeviceVector
+{
+   double *p = nullptr;
+   size_t n = 0;
+public:
+   DeviceVector() = default;
+   explicit DeviceVector(size_t n_) { Resize(n_); }
+   DeviceVector(const DeviceVector &) = delete;
+   ~DeviceVector() { if (p) { b2f_free(Context::Get().get(), p); } }
+   void Resize(size_t n_)
+   {
+      if (n_ == n) { return; }
+      if (p) { b2f_free(Context::Get().get(), p); p = nullptr; }
+      n = n_;
+      B200_CHECK(b2f_malloc(Context::Get().get(), sizeof(double) * (n ? n : 1), (void **)&p));
+   }
+   double *Ptr() const { return p; }
+   size_t Size() const { return n; }
+   void Upload(const mfem::Vector &v)
+   {
+      Resize(v.Size());
+      B200_CHECK(b2f_memcpy_h2d(Context::Get().get(), p, v.HostRead(), sizeof(double) * n));
+   }
+   void Download(mfem::Vector &v) const
+   {
+      MFEM_VERIFY((size_t)v.Size() == n, "size mismatch");
+      B200_CHECK(b2f_memcpy_d2h(Context::Get().get(), v.HostWrite(), p, sizeof(double) * n));
+      B200_CHECK(b2f_ctx_sync(Context::Get().get()));
+   }
+};
+
+/// Shared implementation of the two integrators: builds b2f_pa from MFEM's own tables.
+class PAData
+{
+public:
+   b2f_pa *pa = nullptr;
+   int ne = 0, dof = 0;
+   mutable DeviceVector xe, ye;
+   ~PAData() { b2f_pa_destroy(pa); }
+
+   /** AssemblePA: B, G from MFEM's DofToQuad (fem/fe/fe_base.cpp:2697), weights from the
+       IntegrationRule, geometry from the mesh nodes E-vector (mesh/mesh.cpp:15445); the
+       Jacobians are evaluated inside the setup kernel and never stored. */
+   void Assemble(int kind, const mfem::FiniteElementSpace &fes, const mfem::IntegrationRule &ir,
+                 double coeff)
+   {
+      using namespace mfem;
+      Mesh &mesh = *fes.GetMesh();
+      const FiniteElement &fe = *fes.GetTypicalFE();
+      const DofToQuad &maps = fe.GetDofToQuad(ir, DofToQuad::TENSOR);
+      mesh.EnsureNodes();
+      const GridFunction *nodes = mesh.GetNodes();
+      const FiniteElementSpace *nfes = nodes->FESpace();
+      const Operator *nR = nfes->GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC);
+      Vector nodesE(nR->Height());
+      nR->Mult(*nodes, nodesE);
+      const FiniteElement &nfe = *nfes->GetTypicalFE();
+      const DofToQuad &nmaps = nfe.GetDofToQuad(ir, DofToQuad::TENSOR);
+      DeviceVector d_nodes;
+      d_nodes.Upload(nodesE);
+      ne = fes.GetNE();
+      dof = fe.GetDof();
+      b2f_pa_destroy(pa);
+      pa = nullptr;
+      B200_CHECK(b2f_pa_setup_from_nodes(Context::Get().get(), kind, mesh.Dimension(), maps.ndof,
+                                         maps.nqpt, ne, maps.B.HostRead(), maps.G.HostRead(),
+                                         ir.GetWeights().HostRead(), nmaps.ndof, nmaps.B.HostRead(),
+                                         nmaps.G.HostRead(), d_nodes.Ptr(), coeff, &pa));
+   }
+   void AddMult(const mfem::Vector &x, mfem::Vector &y) const
+   {
+      xe.Upload(x);
+      ye.Upload(y); // AddMultPA accumulates into y (fem/bilininteg.hpp:78)
+      B200_CHECK(b2f_pa_add_mult(pa, xe.Ptr(), ye.Ptr()));
+      ye.Download(y);
+   }
+   void AddDiagonal(mfem::Vector &diag) const
+   {
+      ye.Upload(diag);
+      B200_CHECK(b2f_pa_assemble_diagonal(pa, ye.Ptr()));
+      ye.Download(diag);
+   }
+};
+
+inline double ConstantOf(mfem::Coefficient *Q)
+{
+   if (!Q) { return 1.0; }
+   auto c = dynamic_cast<mfem::ConstantCoefficient *>(Q);
+   MFEM_VERIFY(c, "b200 integrators take a ConstantCoefficient (or none)");
+   return c->constant;
+}
+
+/// seam 3: drop-in for mfem::DiffusionIntegrator on the PA path.
+class DiffusionIntegrator : public mfem::DiffusionIntegrator
+{
+   PAData data;
+public:
+   using mfem::DiffusionIntegrator::DiffusionIntegrator;
+   using mfem::BilinearFormIntegrator::AssemblePA;
+   void AssemblePA(const mfem::FiniteElementSpace &fes) override
+   {
+      const mfem::FiniteElement &fe = *fes.GetTypicalFE();
+      const mfem::IntegrationRule *ir = GetIntegrationRule();
+      if (!ir) { ir = &GetRule(fe, fe); }
+      data.Assemble(0, fes, *ir, ConstantOf(Q));
+   }
+   void AddMultPA(const mfem::Vector &x, mfem::Vector &y) const override { data.AddMult(x, y); }
+   void AssembleDiagonalPA(mfem::Vector &diag) override { data.AddDiagonal(diag); }
+   b2f_pa *Handle() const { return data.pa; }
+};
+
+/// seam 3: drop-in for mfem::MassIntegrator on the PA path.
+class MassIntegrator : public mfem::MassIntegrator
+{
+   PAData data;
+public:
+   using mfem::MassIntegrator::MassIntegrator;
+   using mfem::BilinearFormIntegrator::AssemblePA;
+   void AssemblePA(const mfem::FiniteElementSpace &fes) override
+   {
+      const mfem::FiniteElement &fe = *fes.GetTypicalFE();
+      const mfem::IntegrationRule *ir = GetIntegrationRule();
+      if (!ir) { ir = &GetRule(fe, fe, *fes.GetMesh()->GetTypicalElementTransformation()); }
+      data.Assemble(1, fes, *ir, ConstantOf(Q));
+   }
+   void AddMultPA(const mfem::Vector &x, mfem::Vector &y) const override { data.AddMult(x, y); }
+   void AssembleDiagonalPA(mfem::Vector &diag) override { data.AddDiagonal(diag); }
+   b2f_pa *Handle() const { return data.pa; }
+};
+
+/// seam 1: the fused PA operator of a BilinearForm whose domain integrators are b200 ones.
+class PAOperator : public mfem::Operator
+{
+protected:
+   b2f_restriction *restr = nullptr;
+   b2f_operator *op = nullptr;
+   std::vector<b2f_pa *> integ;
+   mutable DeviceVector dx, dy;
+   friend class CGSolver;
+public:
+   /** @param a  a BilinearForm with AssemblyLevel::PARTIAL, already Assemble()d, whose domain
+                  integrators are b200::DiffusionIntegrator / b200::MassIntegrator.
+       @param ess_tdof_list  essential dofs (FormLinearSystem semantics), may be empty. */
+   PAOperator(mfem::BilinearForm &a, const mfem::Array<int> &ess_tdof_list)
+      : mfem::Operator(a.FESpace()->GetVSize())
+   {
+      using namespace mfem;
+      const FiniteElementSpace &fes = *a.FESpace();
+      auto R = dynamic_cast<const ElementRestriction *>(
+                  fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC));
+      MFEM_VERIFY(R, "tensor-product H1 space expected");
+      const int dof = fes.GetTypicalFE()->GetDof();
+      // MFEM's own tables (fem/restriction.hpp:104-106) are handed over unchanged
+      B200_CHECK(b2f_restriction_create(Context::Get().get(), fes.GetNE(), dof, fes.GetNDofs(), 1, 0,
+                                        R->GatherMap().HostRead(), R->Offsets().HostRead(),
+                                        R->Indices().HostRead(), &restr));
+      for (BilinearFormIntegrator *bfi : *a.GetDBFI())
+      {
+         if (auto d = dynamic_cast<b200::DiffusionIntegrator *>(bfi)) { integ.push_back(d->Handle()); }
+         else if (auto m = dynamic_cast<b200::MassIntegrator *>(bfi)) { integ.push_back(m->Handle()); }
+         else { MFEM_ABORT("PAOperator: only b200::DiffusionIntegrator / MassIntegrator are supported"); }
+      }
+      B200_CHECK(b2f_operator_create(Context::Get().get(), restr, integ.data(), (int)integ.size(),
+                                     ess_tdof_list.HostRead(), ess_tdof_list.Size(), &op));
+   }
+   ~PAOperator() override
+   {
+      b2f_operator_destroy(op);
+      b2f_restriction_destroy(restr);
+   }
+   /// PABilinearFormExtension::Mult (fem/bilinearform_ext.cpp:487): y = R^T A_E R x, fused.
+   void Mult(const mfem::Vector &x, mfem::Vector &y) const override
+   {
+      dx.Upload(x);
+      dy.Resize(height);
+      B200_CHECK(b2f_operator_mult(op, dx.Ptr(), dy.Ptr()));
+      dy.Download(y);
+   }
+   void MultTranspose(const mfem::Vector &x, mfem::Vector &y) const override { Mult(x, y); } // symmetric
+   void AssembleDiagonal(mfem::Vector &diag) const override
+   {
+      dy.Resize(height);
+      B200_CHECK(b2f_operator_assemble_diagonal(op, dy.Ptr()));
+      diag.SetSize(height);
+      dy.Download(diag);
+   }
+   b2f_operator *Handle() const { return op; }
+};
+
+/// ConstrainedOperator (linalg/operator.cpp:526-660, DIAG_ONE) over the fused operator.
+class ConstrainedOperator : public PAOperator
+{
+public:
+   using PAOperator::PAOperator;
+   void Mult(const mfem::Vector &x, mfem::Vector &y) const override
+   {
+      dx.Upload(x);
+      dy.Resize(height);
+      B200_CHECK(b2f_operator_mult_constrained(op, dx.Ptr(), dy.Ptr()));
+      dy.Download(y);
+   }
+   /// EliminateRHS (linalg/operator.cpp:574): b -= A w (w = x on ess); b[ess] = x[ess].
+   void EliminateRHS(const mfem::Vector &x, mfem::Vector &b) const
+   {
+      dx.Upload(x);
+      dy.Upload(b);
+      B200_CHECK(b2f_operator_eliminate_rhs(op, dx.Ptr(), dy.Ptr()));
+      dy.Download(b);
+   }
+};
+
+/// CGSolver (linalg/solvers.cpp:869-1050) with an optional Jacobi preconditioner
+/// (OperatorJacobiSmoother, solvers.cpp:324-450), entirely on the device.
+class CGSolver : public mfem::IterativeSolver
+{
+   const ConstrainedOperator *A = nullptr;
+   bool jacobi = false;
+   DeviceVector dinv;
+   mutable DeviceVector db, dxs;
+public:
+   void SetOperator(const mfem::Operator &op_) override
+   {
+      A = dynamic_cast<const ConstrainedOperator *>(&op_);
+      MFEM_VERIFY(A, "b200::CGSolver needs a b200::ConstrainedOperator");
+      height = width = A->Height();
+      oper = A;
+   }
+   /// OperatorJacobiSmoother(a, ess): dinv = 1/diag, dinv[ess] = 1.
+   void UseJacobi(const mfem::Array<int> &ess_tdof_list)
+   {
+      MFEM_VERIFY(A, "SetOperator first");
+      DeviceVector diag(height);
+      B200_CHECK(b2f_operator_assemble_diagonal(A->Handle(), diag.Ptr()));
+      dinv.Resize(height);
+      int *d_ess = nullptr;
+      b2f_ctx *ctx = Context::Get().get();
+      B200_CHECK(b2f_malloc(ctx, sizeof(int) * (ess_tdof_list.Size() + 1), (void **)&d_ess));
+      B200_CHECK(b2f_memcpy_h2d(ctx, d_ess, ess_tdof_list.HostRead(), sizeof(int) * ess_tdof_list.Size()));
+      B200_CHECK(b2f_jacobi_setup(ctx, height, diag.Ptr(), d_ess, ess_tdof_list.Size(), 1.0, dinv.Ptr()));
+      B200_CHECK(b2f_ctx_sync(ctx));
+      b2f_free(ctx, d_ess);
+      jacobi = true;
+   }
+   void Mult(const mfem::Vector &b, mfem::Vector &x) const override
+   {
+      MFEM_VERIFY(A, "operator not set");
+      b2f_ctx *ctx = Context::Get().get();
+      db.Upload(b);
+      dxs.Resize(height);
+      DeviceVector x0, ax0;
+      if (iterative_mode)
+      {
+         // r = b - A x0; the library iterates on the correction from a zero start, which
+         // generates the same Krylov iterates as CGSolver::Mult does from x0
+         x0.Upload(x);
+         ax0.Resize(height);
+         B200_CHECK(b2f_operator_mult_constrained(A->Handle(), x0.Ptr(), ax0.Ptr()));
+         B200_CHECK(b2f_vector_add(ctx, height, db.Ptr(), -1.0, ax0.Ptr(), db.Ptr()));
+      }
+      b2f_pcg_options opt = {rel_tol, abs_tol, max_iter, 1};
+      b2f_pcg_result res;
+      B200_CHECK(b2f_pcg(A->Handle(), jacobi ? dinv.Ptr() : nullptr, db.Ptr(), dxs.Ptr(), &opt, &res,
+                         nullptr, 0));
+      if (iterative_mode) { B200_CHECK(b2f_vector_add(ctx, height, x0.Ptr(), 1.0, dxs.Ptr(), dxs.Ptr())); }
+      dxs.Download(x);
+      final_iter = res.iterations;
+      converged = res.converged != 0;
+      initial_norm = res.initial_norm;
+      final_norm = res.final_norm;
+   }
+};
+
+} // namespace b200
+#endif

@@ -1,0 +1,130 @@
+// adapter/ex1_b200.cpp -- examples/ex1.cpp (-pa) with the PA hot path routed to libb200fem.so.
+//
+// Same driver flow as the reference's ex1 (examples/ex1.cpp:122-267): mesh, H1 space, essential
+// boundary, RHS (1, phi_i), BilinearForm with AssemblyLevel::PARTIAL and a DiffusionIntegrator,
+// FormLinearSystem, Jacobi-PCG.  It runs the problem TWICE in one process -- MFEM's own CPU PA
+// path and the B200 path behind the same interfaces (adapter/b200_mfem.hpp) -- and checks
+//   seam 3: MFEM's PABilinearFormExtension::Mult with the b200 integrator == MFEM's   (1e-12)
+//   seam 1: fused b200::PAOperator::Mult == MFEM's a.Mult, AssembleDiagonal          (1e-12)
+//   solve : b200::CGSolver iteration count within +-1 of mfem::CGSolver, same solution.
+// usage: ex1_b200 [-o order] [-n elems_per_side | -m mesh -r refinements] [-k mass|diffusion]
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+
+#include "b200_mfem.hpp"
+
+using namespace mfem;
+
+static double relerr(const Vector &a, const Vector &b)
+{
+   Vector d(a);
+   d -= b;
+   return d.Norml2() / b.Norml2();
+}
+
+int main(int argc, char *argv[])
+{
+   int order = 3, n = 6, ref = 0;
+   const char *mesh_file = "";
+   const char *kind = "diffusion";
+   OptionsParser args(argc, argv);
+   args.AddOption(&order, "-o", "--order", "H1 order");
+   args.AddOption(&n, "-n", "--elems", "elements per side of the Cartesian hex mesh");
+   args.AddOption(&mesh_file, "-m", "--mesh", "mesh file (instead of the Cartesian mesh)");
+   args.AddOption(&ref, "-r", "--refine", "uniform refinements of the mesh file");
+   args.AddOption(&kind, "-k", "--kind", "diffusion | mass");
+   args.Parse();
+   if (!args.Good()) { args.PrintUsage(std::cout); return 1; }
+   Device device("cpu"); // MFEM itself stays on the host ("host-MFEM" mode)
+
+   Mesh mesh = strlen(mesh_file) ? Mesh(mesh_file, 1, 1)
+               : Mesh::MakeCartesian3D(n, n, n, Element::HEXAHEDRON);
+   for (int l = 0; l < ref; l++) { mesh.UniformRefinement(); }
+   const int dim = mesh.Dimension();
+   H1_FECollection fec(order, dim);
+   FiniteElementSpace fes(&mesh, &fec);
+   Array<int> ess_bdr(mesh.bdr_attributes.Max()), ess;
+   ess_bdr = 1;
+   fes.GetEssentialTrueDofs(ess_bdr, ess);
+   ConstantCoefficient one(1.0);
+   const bool mass = !strcmp(kind, "mass");
+   std::printf("ex1_b200: %s, order %d, %d elements, %d unknowns\n", kind, order, mesh.GetNE(),
+               fes.GetTrueVSize());
+
+   auto make_form = [&](bool b200) -> BilinearForm *
+   {
+      BilinearForm *a = new BilinearForm(&fes);
+      a->SetAssemblyLevel(AssemblyLevel::PARTIAL);
+      if (mass) { a->AddDomainIntegrator(b200 ? (BilinearFormIntegrator *)new b200::MassIntegrator(one) : new MassIntegrator(one)); }
+      else { a->AddDomainIntegrator(b200 ? (BilinearFormIntegrator *)new b200::DiffusionIntegrator(one) : new DiffusionIntegrator(one)); }
+      a->Assemble();
+      return a;
+   };
+   std::unique_ptr<BilinearForm> a_ref(make_form(false)), a_b2(make_form(true));
+
+   int fails = 0;
+   auto check = [&](const char *what, double err, double tol)
+   {
+      std::printf("  %-58s %.3e  %s\n", what, err, err <= tol ? "ok" : "FAIL");
+      fails += !(err <= tol);
+   };
+   const int N = fes.GetVSize();
+   Vector x(N), y_ref(N), y(N);
+   x.Randomize(1);
+   a_ref->Mult(x, y_ref);
+   a_b2->Mult(x, y); // MFEM's extension + restriction, b200 element kernel (seam 3)
+   check("seam 3: PABilinearFormExtension::Mult with b200 integrator", relerr(y, y_ref), 1e-12);
+   Vector d_ref(N), d(N);
+   a_ref->AssembleDiagonal(d_ref);
+   a_b2->AssembleDiagonal(d);
+   check("seam 3: AssembleDiagonal with b200 integrator", relerr(d, d_ref), 1e-12);
+
+   Array<int> none;
+   b200::PAOperator A_fused(*a_b2, none);
+   A_fused.Mult(x, y);
+   check("seam 1: fused b200::PAOperator::Mult", relerr(y, y_ref), 1e-12);
+   A_fused.AssembleDiagonal(d);
+   check("seam 1: b200::PAOperator::AssembleDiagonal", relerr(d, d_ref), 1e-12);
+
+   // the linear system of ex1: b = (1, phi_i), x = 0 on the boundary
+   LinearForm b(&fes);
+   b.AddDomainIntegrator(new DomainLFIntegrator(one));
+   b.Assemble();
+   GridFunction u(&fes);
+   u = 0.0;
+   OperatorPtr A;
+   Vector B, X;
+   a_ref->FormLinearSystem(ess, u, b, A, X, B);
+   Vector yc_ref(N), yc(N);
+   A->Mult(x, yc_ref);
+   b200::ConstrainedOperator A_b2(*a_b2, ess);
+   A_b2.Mult(x, yc);
+   check("seam 1: b200::ConstrainedOperator::Mult", relerr(yc, yc_ref), 1e-12);
+   Vector B2(b);
+   Vector zero(N);
+   zero = 0.0;
+   A_b2.EliminateRHS(zero, B2);
+   check("EliminateRHS", relerr(B2, B), 1e-12);
+
+   OperatorJacobiSmoother M(*a_ref, ess);
+   CGSolver cg;
+   cg.SetRelTol(1e-6); cg.SetAbsTol(0.0); cg.SetMaxIter(2000); cg.SetPrintLevel(-1);
+   cg.SetOperator(*A);
+   cg.SetPreconditioner(M);
+   X = 0.0;
+   cg.Mult(B, X);
+
+   b200::CGSolver cg2;
+   cg2.SetRelTol(1e-6); cg2.SetAbsTol(0.0); cg2.SetMaxIter(2000);
+   cg2.SetOperator(A_b2);
+   cg2.UseJacobi(ess);
+   Vector X2(N);
+   cg2.Mult(B2, X2);
+   std::printf("  PCG iterations: MFEM %d, b200 %d\n", cg.GetNumIterations(), cg2.GetNumIterations());
+   check("PCG iteration count |difference|", std::abs(cg.GetNumIterations() - cg2.GetNumIterations()), 1.0);
+   check("PCG solution", relerr(X2, X), 1e-5);
+   std::printf(fails ? "ex1_b200: %d check(s) FAILED\n" : "ex1_b200: all checks passed\n", fails);
+   return fails ? 1 : 0;
+}

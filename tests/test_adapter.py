@@ -1,0 +1,34 @@
+"""The MFEM-side adapter (adapter/b200_mfem.hpp, compiled against the reference's own headers
+and linked with the unmodified reference library): on a GPU it must reproduce MFEM's own CPU
+PA path at all three seams; without a GPU it must fail loudly (there is no CPU fallback)."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+EXE = os.path.join(ROOT, "adapter", "_build", "ex1_b200")
+needs_exe = pytest.mark.skipif(not os.path.isfile(EXE), reason="adapter/_build/ex1_b200 not built "
+                               "(needs /root/reference: make -C adapter)")
+
+
+@needs_exe
+def test_adapter_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([EXE, "-n", "2", "-o", "2"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=120)
+    out = r.stdout.decode(errors="replace")
+    assert r.returncode != 0
+    assert "no CPU path" in out
+
+
+@needs_exe
+@pytest.mark.gpu
+@pytest.mark.parametrize("args", [["-n", "6", "-o", "3"], ["-n", "4", "-o", "4"], ["-n", "3", "-o", "8"],
+                                  ["-n", "5", "-o", "2", "-k", "mass"], ["-n", "8", "-o", "1"]])
+def test_adapter_matches_mfem_at_all_seams(args):
+    r = subprocess.run([EXE] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    out = r.stdout.decode(errors="replace")
+    assert r.returncode == 0 and "all checks passed" in out, out[-3000:]
