@@ -1,7 +1,7 @@
 // 3D diffusion PA kernels, D1D = 2..5 (split for parallel compilation)
 #include <cstdlib>
 #include "pa_dispatch.cuh"
-#include "pa_apply_pipe.cuh"
+#include "pa_apply_eo.cuh"
 namespace b2f
 {
 // experiment hook: B2F_VARIANT selects a kernel variant for (D1D,Q1D) = (5,6)
@@ -19,6 +19,17 @@ int pa_apply_3d_diffusion_2(b2f_pa *pa, const double *x, double *y, const int *i
       switch (variant())
       {
          case 1: return launch_3d<K, 5, 6, 6, 0, 1, 1>(pa, x, y, idx);
+         case 2: return launch_3d<K, 5, 6, 2, 1, 6, 1>(pa, x, y, idx);
+         case 3: return launch_3d<K, 5, 6, 2, 1, 5, 1>(pa, x, y, idx);
+         case 4: return launch_3d<K, 5, 6, 3, 1, 3, 1>(pa, x, y, idx);
+         case 5: return launch_3d<K, 5, 6, 4, 1, 3, 1>(pa, x, y, idx);
+         case 6: return launch_3d<K, 5, 6, 1, 1, 8, 1>(pa, x, y, idx);
+         case 30: return launch_3d_eo<K, 5, 6, 3, 4>(pa, x, y, idx);
+         case 31: return launch_3d_eo<K, 5, 6, 3, 3>(pa, x, y, idx);
+         case 32: return launch_3d_eo<K, 5, 6, 4, 3>(pa, x, y, idx);
+         case 33: return launch_3d_eo<K, 5, 6, 6, 2>(pa, x, y, idx);
+         case 34: return launch_3d_eo<K, 5, 6, 2, 5>(pa, x, y, idx);
+         case 35: return launch_3d_eo<K, 5, 6, 3, 5>(pa, x, y, idx);
          case 20: return launch_3d_pipe<K, 5, 6, 6, 1>(pa, x, y, idx);
          case 21: return launch_3d_pipe<K, 5, 6, 6, 2>(pa, x, y, idx);
          case 22: return launch_3d_pipe<K, 5, 6, 3, 1>(pa, x, y, idx);

@@ -1,0 +1,622 @@
+// mfem_b200/csrc/pa_apply_eo.cuh -- 3D PA operator kernel, even-odd sum factorisation.
+//
+// Same operator as pa_apply.cuh (MFEM's SmemPADiffusionApply3D / SmemPAMassApply3D,
+// fem/integ/bilininteg_diffusion_kernels.hpp:989-1215, bilininteg_mass_kernels.hpp:815-1165,
+// fused with ElementRestriction::Mult / MultTranspose, fem/restriction.cpp:116,159), with two
+// changes that cut what actually limits the kernel on B200 (profiles/: the LSU / shared-memory
+// pipe and instruction issue at the 1 kW power cap, not HBM):
+//
+//  * EVEN-ODD decomposition of every 1D contraction.  The H1 basis on symmetric nodes and a
+//    symmetric quadrature rule satisfies B[Q-1-q][D-1-d] = B[q][d], G[Q-1-q][D-1-d] =
+//    -G[q][d].  Splitting a line into its symmetric and antisymmetric halves
+//    (s_i = u_i + u_{D-1-i}, a_i = u_i - u_{D-1-i}) halves the multiply-adds and -- as every
+//    DFMA needs its own basis entry from the constant bank -- halves the constant loads:
+//    per 1D transform D*Q FMAs + D*Q constant loads become D*Q/2 FMAs + D*Q/2 loads + (D+Q)
+//    adds.  Results differ from the plain contraction by rounding only (~1e-16).
+//  * the shared-memory layout of pa_apply_pipe.cuh: stage order y -> z -> x with
+//    yq = qy + Q*e the fastest lane AND address index of stages 2-4 (consecutive lanes touch
+//    consecutive words: no bank conflicts, no transposition), the x-stage overwrites its
+//    own input column in place (no staging registers, one barrier fewer), quadrature-data
+//    rows are read with 128-bit LDS from per-element TMA slabs padded so that lanes of
+//    neighbouring elements hit different bank groups.
+//
+// Streams: one TMA bulk copy per element (cp.async.bulk + mbarrier complete_tx) at kernel
+// entry; an L2 bulk prefetch of the slab and gather indices of the CTA that will take over
+// this SM slot (`pf` blocks ahead).  Requires the symmetry above (checked on the host when
+// the integrator is set up; otherwise pa_apply.cuh's general kernel runs).
+#pragma once
+#include "pa_apply_pipe.cuh"
+
+namespace b2f
+{
+
+template <int D, int Q>
+struct EOBasis
+{
+   static constexpr int DH = (D + 1) / 2, QH = (Q + 1) / 2;
+   // M[q][i] = S[q][i] (s-part) and A[q][i] (a-part) for q < QH, i < DH; the middle column
+   // (D odd) is stored in S, its A entry is 0
+   double Bs[QH][DH], Ba[QH][DH], Gs[QH][DH], Ga[QH][DH];
+};
+
+// s_i = u_i + sg*u_{N-1-i}, a_i = u_i - sg*u_{N-1-i}; middle (N odd): s = a = u
+template <int N, bool NEG>
+__device__ __forceinline__ void eo_split(const double (&u)[N], double (&s)[(N + 1) / 2],
+                                         double (&a)[(N + 1) / 2])
+{
+#pragma unroll
+   for (int i = 0; i < N / 2; i++)
+   {
+      s[i] = NEG ? u[i] - u[N - 1 - i] : u[i] + u[N - 1 - i];
+      a[i] = NEG ? u[i] + u[N - 1 - i] : u[i] - u[N - 1 - i];
+   }
+   if (N % 2) { s[N / 2] = u[N / 2]; a[N / 2] = u[N / 2]; }
+}
+
+// forward D -> Q:  es[q] += sum_i S[q][i] s_i ; ea[q] += sum_{i<D/2} A[q][i] a_i
+// out[q] = es + ea ; out[Q-1-q] = sg (es - ea).  ANTI: the matrix is antisymmetric (G).
+template <int D, int Q, bool ANTI>
+__device__ __forceinline__ void eo_fwd(const double (&S)[(Q + 1) / 2][(D + 1) / 2],
+                                       const double (&A)[(Q + 1) / 2][(D + 1) / 2],
+                                       const double (&s)[(D + 1) / 2], const double (&a)[(D + 1) / 2],
+                                       double (&out)[Q])
+{
+   constexpr int DH = (D + 1) / 2, QH = (Q + 1) / 2, dh = D / 2, qh = Q / 2;
+#pragma unroll
+   for (int q = 0; q < QH; q++)
+   {
+      double es = 0.0, ea = 0.0;
+      const bool mid = (Q % 2) && q == qh; // middle row: sym -> A row is 0, anti -> S row is 0
+      if (!(mid && ANTI))
+      {
+#pragma unroll
+         for (int i = 0; i < DH; i++) { es = fma(S[q][i], s[i], es); }
+      }
+      if (!(mid && !ANTI))
+      {
+#pragma unroll
+         for (int i = 0; i < dh; i++) { ea = fma(A[q][i], a[i], ea); }
+      }
+      out[q] = es + ea;
+      if (!mid) { out[Q - 1 - q] = ANTI ? ea - es : es - ea; }
+   }
+}
+
+// backward Q -> D, accumulating in the split space:
+// es[i] += sum_q S[q][i] s_q ; ea[i] += sum_q A[q][i] a_q   (s,a split with sign sg)
+template <int D, int Q, bool ANTI>
+__device__ __forceinline__ void eo_bwd_acc(const double (&S)[(Q + 1) / 2][(D + 1) / 2],
+                                           const double (&A)[(Q + 1) / 2][(D + 1) / 2],
+                                           const double (&s)[(Q + 1) / 2], const double (&a)[(Q + 1) / 2],
+                                           double (&es)[(D + 1) / 2], double (&ea)[(D + 1) / 2])
+{
+   constexpr int DH = (D + 1) / 2, QH = (Q + 1) / 2, dh = D / 2, qh = Q / 2;
+   // middle row (Q odd): sym -> contributes to es only, anti -> to ea only
+   constexpr int QS = ANTI ? qh : QH, QA = ANTI ? QH : qh;
+#pragma unroll
+   for (int i = 0; i < DH; i++)
+   {
+#pragma unroll
+      for (int q = 0; q < QS; q++) { es[i] = fma(S[q][i], s[q], es[i]); }
+      if (i < dh)
+      {
+#pragma unroll
+         for (int q = 0; q < QA; q++) { ea[i] = fma(A[q][i], a[q], ea[i]); }
+      }
+   }
+}
+
+template <int D>
+__device__ __forceinline__ void eo_bwd_out(const double (&es)[(D + 1) / 2],
+                                           const double (&ea)[(D + 1) / 2], double (&out)[D])
+{
+#pragma unroll
+   for (int i = 0; i < D / 2; i++)
+   {
+      out[i] = es[i] + ea[i];
+      out[D - 1 - i] = es[i] - ea[i];
+   }
+   if (D % 2) { out[D / 2] = es[D / 2]; }
+}
+
+template <int N>
+__device__ __forceinline__ void zero(double (&v)[N])
+{
+#pragma unroll
+   for (int i = 0; i < N; i++) { v[i] = 0.0; }
+}
+
+template <int KIND, int D, int Q, int NEB, bool FUSED, bool COLLOC, int MINB>
+__global__ void __launch_bounds__(PipeCfg<KIND, D, Q, NEB>::NT, MINB)
+pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__restrict__ qdata,
+                      const double *__restrict__ x, double *__restrict__ y,
+                      const int *__restrict__ idx, const int64_t ne, const int pf)
+{
+   using C = PipeCfg<KIND, D, Q, NEB>;
+   constexpr bool DIFF = C::DIFF;
+   constexpr int D2 = C::D2, D3 = C::D3, Q3 = C::Q3, YQ = C::YQ;
+   constexpr int DH = (D + 1) / 2, QH = (Q + 1) / 2;
+   extern __shared__ __align__(16) unsigned char smem_raw[];
+   uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+   double *qd = reinterpret_cast<double *>(smem_raw + 16);
+   double *r1 = qd + C::QD;
+   double *r2 = r1 + C::R1;
+
+   const int t = threadIdx.x;
+   const int64_t e0 = (int64_t)blockIdx.x * NEB;
+   const int nev = (int)((ne - e0) < NEB ? (ne - e0) : NEB);
+
+   // ---- quadrature-data stream: TMA per element + L2 prefetch for the CTA `pf` blocks on ----
+   const double *qslab = qdata + e0 * (int64_t)(C::NQD * Q3);
+   if constexpr (C::TMA_OK)
+   {
+      if (t == 0)
+      {
+         mbar_init(bar, 1);
+         mbar_expect_tx(bar, (uint32_t)(nev * C::NQD * Q3) * 8u);
+         for (int e = 0; e < nev; e++)
+         {
+            bulk_g2s(qd + e * C::DS, qslab + (int64_t)e * (C::NQD * Q3), (uint32_t)(C::NQD * Q3) * 8u, bar);
+         }
+      }
+   }
+   else
+   {
+      for (int i = t; i < nev * C::NQD * Q3; i += C::NT) { cp_async8(qd + i, qslab + i); }
+   }
+   if (pf > 0 && t == 32 % C::NT)
+   {
+      const int64_t ep = e0 + (int64_t)pf * NEB;
+      if (ep + NEB <= ne)
+      {
+         const uintptr_t q = reinterpret_cast<uintptr_t>(qdata + ep * (int64_t)(C::NQD * Q3)) & ~(uintptr_t)15;
+         l2_prefetch_bulk(reinterpret_cast<const void *>(q), ((uint32_t)(NEB * C::NQD * Q3) * 8u) & ~15u);
+         if (FUSED)
+         {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(idx + ep * D3) & ~(uintptr_t)15;
+            l2_prefetch_bulk(reinterpret_cast<const void *>(a), ((uint32_t)(NEB * D3) * 4u) & ~15u);
+         }
+      }
+   }
+
+   // ---- task coordinates of stages 1 and 5: line (dx, dz, e) --------------------------------
+   int e1, dx1, dz1;
+   if (C::L.order == 0) { e1 = t % NEB; dx1 = (t / NEB) % D; dz1 = t / (NEB * D); }
+   else if (C::L.order == 1) { dx1 = t % D; dz1 = (t / D) % D; e1 = t / D2; }
+   else if (C::L.order == 2) { e1 = t % NEB; dz1 = (t / NEB) % D; dx1 = t / (NEB * D); }
+   else { dz1 = t % D; e1 = (t / D) % NEB; dx1 = t / (NEB * D); }
+   const bool has1 = t < C::T1;
+   const bool act1 = has1 && e1 < nev;
+   const int loc1 = dx1 + D2 * dz1;                // + D*dy : position inside the element
+   const int a1 = Q * e1 + YQ * dx1 + C::SA * dz1; // + qy   : A/F address of this line
+
+   // ---- stage 1 (y): gather, u[dy] -> B u, G u at qy ---------------------------------------
+   int gi[D];
+   {
+      double u[D];
+#pragma unroll
+      for (int dy = 0; dy < D; dy++) { gi[dy] = -1; u[dy] = 0.0; }
+      if (act1)
+      {
+         if constexpr (FUSED)
+         {
+            const int *ip = idx + (e0 + e1) * D3 + loc1;
+#pragma unroll
+            for (int dy = 0; dy < D; dy++) { gi[dy] = __ldg(ip + D * dy); }
+#pragma unroll
+            for (int dy = 0; dy < D; dy++) { u[dy] = gi[dy] >= 0 ? __ldg(x + gi[dy]) : 0.0; }
+         }
+         else
+         {
+            const double *xe = x + (e0 + e1) * D3 + loc1;
+#pragma unroll
+            for (int dy = 0; dy < D; dy++) { u[dy] = __ldg(xe + D * dy); }
+         }
+      }
+      if (has1)
+      {
+         double s[DH], a[DH], vb[Q], vg[Q];
+         eo_split<D, false>(u, s, a);
+         if (COLLOC)
+         {
+#pragma unroll
+            for (int q = 0; q < Q; q++) { vb[q] = u[q < D ? q : 0]; }
+         }
+         else { eo_fwd<D, Q, false>(bs.Bs, bs.Ba, s, a, vb); }
+         if (DIFF) { eo_fwd<D, Q, true>(bs.Gs, bs.Ga, s, a, vg); }
+         double *A0 = r1 + a1;
+#pragma unroll
+         for (int qy = 0; qy < Q; qy++)
+         {
+            A0[qy] = vb[qy];
+            if (DIFF) { A0[D * C::SA + qy] = vg[qy]; }
+         }
+      }
+   }
+   __syncthreads();
+
+   // ---- stage 2 (z): line t2 = (yq, dx), contraction over dz -------------------------------
+   if (t < C::T2)
+   {
+      double a0[D], a1v[D];
+#pragma unroll
+      for (int dz = 0; dz < D; dz++)
+      {
+         a0[dz] = r1[t + C::SA * dz];
+         if (DIFF) { a1v[dz] = r1[t + C::SA * (D + dz)]; }
+      }
+      double s0[DH], d0[DH], bb[Q], gyv[Q], gzv[Q];
+      eo_split<D, false>(a0, s0, d0);
+      if (COLLOC)
+      {
+#pragma unroll
+         for (int q = 0; q < Q; q++) { bb[q] = a0[q < D ? q : 0]; if (DIFF) { gyv[q] = a1v[q < D ? q : 0]; } }
+      }
+      else { eo_fwd<D, Q, false>(bs.Bs, bs.Ba, s0, d0, bb); }
+      if (DIFF)
+      {
+         eo_fwd<D, Q, true>(bs.Gs, bs.Ga, s0, d0, gzv);
+         if (!COLLOC)
+         {
+            double s1[DH], d1[DH];
+            eo_split<D, false>(a1v, s1, d1);
+            eo_fwd<D, Q, false>(bs.Bs, bs.Ba, s1, d1, gyv);
+         }
+      }
+      const int yq = t % YQ, dx = t / YQ;
+      double *C0 = r2 + yq + C::SC * dx;
+#pragma unroll
+      for (int qz = 0; qz < Q; qz++)
+      {
+         C0[YQ * qz] = bb[qz];
+         if (DIFF)
+         {
+            C0[D * C::SC + YQ * qz] = gyv[qz];     // d/dy
+            C0[2 * D * C::SC + YQ * qz] = gzv[qz]; // d/dz
+         }
+      }
+   }
+   if constexpr (!C::TMA_OK) { cp_async_wait_all(); }
+   __syncthreads();
+
+   // ---- stage 3 (x, D, x^T) in place: line t3 = (yq, qz) ------------------------------------
+   if (t < C::T3)
+   {
+      const int yq = t % YQ, qz = t / YQ;
+      const int e = yq / Q, qy = yq - e * Q;
+      double *C0 = r2 + yq + YQ * qz;
+      double gx[Q], gy[Q], gz[Q];
+      {
+         double c0[D], s[DH], a[DH];
+#pragma unroll
+         for (int dx = 0; dx < D; dx++) { c0[dx] = C0[C::SC * dx]; }
+         eo_split<D, false>(c0, s, a);
+         if (DIFF) { eo_fwd<D, Q, true>(bs.Gs, bs.Ga, s, a, gx); }
+         else if (COLLOC)
+         {
+#pragma unroll
+            for (int q = 0; q < Q; q++) { gx[q] = c0[q < D ? q : 0]; }
+         }
+         else { eo_fwd<D, Q, false>(bs.Bs, bs.Ba, s, a, gx); }
+      }
+      if (DIFF)
+      {
+         double c1[D], c2[D];
+#pragma unroll
+         for (int dx = 0; dx < D; dx++)
+         {
+            c1[dx] = C0[C::SC * (D + dx)];
+            c2[dx] = C0[C::SC * (2 * D + dx)];
+         }
+         if (COLLOC)
+         {
+#pragma unroll
+            for (int q = 0; q < Q; q++) { gy[q] = c1[q < D ? q : 0]; gz[q] = c2[q < D ? q : 0]; }
+         }
+         else
+         {
+            double s[DH], a[DH];
+            eo_split<D, false>(c1, s, a);
+            eo_fwd<D, Q, false>(bs.Bs, bs.Ba, s, a, gy);
+            eo_split<D, false>(c2, s, a);
+            eo_fwd<D, Q, false>(bs.Bs, bs.Ba, s, a, gz);
+         }
+      }
+      // quadrature data of this line: NQD rows of Q doubles from the TMA-filled slab
+      if constexpr (C::TMA_OK) { mbar_wait(bar, 0); }
+      const double *dq = qd + e * C::DS + Q * (qy + Q * qz);
+      if (DIFF)
+      {
+         double dv[C::NQD][Q];
+#pragma unroll
+         for (int k = 0; k < C::NQD; k++)
+         {
+            if constexpr (C::VEC) { load_row<Q, false>(dq + k * Q3, dv[k]); }
+            else
+            {
+#pragma unroll
+               for (int qx = 0; qx < Q; qx++) { dv[k][qx] = dq[k * Q3 + qx]; }
+            }
+         }
+#pragma unroll
+         for (int qx = 0; qx < Q; qx++)
+         {
+            const double O11 = dv[0][qx], O12 = dv[1 % C::NQD][qx], O13 = dv[2 % C::NQD][qx];
+            const double O22 = dv[3 % C::NQD][qx], O23 = dv[4 % C::NQD][qx], O33 = dv[5 % C::NQD][qx];
+            const double ux = gx[qx], uy = gy[qx], uz = gz[qx];
+            gx[qx] = (O11 * ux) + (O12 * uy) + (O13 * uz);
+            gy[qx] = (O12 * ux) + (O22 * uy) + (O23 * uz);
+            gz[qx] = (O13 * ux) + (O23 * uy) + (O33 * uz);
+         }
+      }
+      else
+      {
+         double dv[Q];
+         if constexpr (C::VEC) { load_row<Q, false>(dq, dv); }
+         else
+         {
+#pragma unroll
+            for (int qx = 0; qx < Q; qx++) { dv[qx] = dq[qx]; }
+         }
+#pragma unroll
+         for (int qx = 0; qx < Q; qx++) { gx[qx] *= dv[qx]; }
+      }
+      // x^T, written over this thread's own input column
+      {
+         double s[QH], a[QH], es[DH], ea[DH], o[D];
+         zero(es); zero(ea);
+         if (DIFF)
+         {
+            eo_split<Q, true>(gx, s, a);
+            eo_bwd_acc<D, Q, true>(bs.Gs, bs.Ga, s, a, es, ea);
+            eo_bwd_out<D>(es, ea, o);
+         }
+         else if (COLLOC)
+         {
+#pragma unroll
+            for (int dx = 0; dx < D; dx++) { o[dx] = gx[dx]; }
+         }
+         else
+         {
+            eo_split<Q, false>(gx, s, a);
+            eo_bwd_acc<D, Q, false>(bs.Bs, bs.Ba, s, a, es, ea);
+            eo_bwd_out<D>(es, ea, o);
+         }
+#pragma unroll
+         for (int dx = 0; dx < D; dx++) { C0[C::SC * dx] = o[dx]; }
+      }
+      if (DIFF)
+      {
+         double s[QH], a[QH], es[DH], ea[DH], o[D];
+         if (COLLOC)
+         {
+#pragma unroll
+            for (int dx = 0; dx < D; dx++) { C0[C::SC * (D + dx)] = gy[dx]; C0[C::SC * (2 * D + dx)] = gz[dx]; }
+         }
+         else
+         {
+            zero(es); zero(ea);
+            eo_split<Q, false>(gy, s, a);
+            eo_bwd_acc<D, Q, false>(bs.Bs, bs.Ba, s, a, es, ea);
+            eo_bwd_out<D>(es, ea, o);
+#pragma unroll
+            for (int dx = 0; dx < D; dx++) { C0[C::SC * (D + dx)] = o[dx]; }
+            zero(es); zero(ea);
+            eo_split<Q, false>(gz, s, a);
+            eo_bwd_acc<D, Q, false>(bs.Bs, bs.Ba, s, a, es, ea);
+            eo_bwd_out<D>(es, ea, o);
+#pragma unroll
+            for (int dx = 0; dx < D; dx++) { C0[C::SC * (2 * D + dx)] = o[dx]; }
+         }
+      }
+   }
+   __syncthreads();
+
+   // ---- stage 4 (z^T): line t2 = (yq, dx) ----------------------------------------------------
+   if (t < C::T2)
+   {
+      const int yq = t % YQ, dx = t / YQ;
+      const double *E0 = r2 + yq + C::SC * dx;
+      double ev[Q], s[QH], a[QH], es[DH], ea[DH], p0[D], p1[D];
+      zero(es); zero(ea);
+#pragma unroll
+      for (int qz = 0; qz < Q; qz++) { ev[qz] = E0[YQ * qz]; }
+      if (COLLOC)
+      {
+#pragma unroll
+         for (int dz = 0; dz < D; dz++) { p0[dz] = ev[dz]; }
+      }
+      else
+      {
+         eo_split<Q, false>(ev, s, a);
+         eo_bwd_acc<D, Q, false>(bs.Bs, bs.Ba, s, a, es, ea);
+      }
+      if (DIFF)
+      {
+#pragma unroll
+         for (int qz = 0; qz < Q; qz++) { ev[qz] = E0[2 * D * C::SC + YQ * qz]; }
+         eo_split<Q, true>(ev, s, a);
+         eo_bwd_acc<D, Q, true>(bs.Gs, bs.Ga, s, a, es, ea); // + G^T (d/dz part)
+      }
+      if (COLLOC)
+      {
+         double g[D];
+         if (DIFF)
+         {
+            eo_bwd_out<D>(es, ea, g);
+#pragma unroll
+            for (int dz = 0; dz < D; dz++) { p0[dz] += g[dz]; }
+         }
+      }
+      else { eo_bwd_out<D>(es, ea, p0); }
+      if (DIFF)
+      {
+#pragma unroll
+         for (int qz = 0; qz < Q; qz++) { ev[qz] = E0[D * C::SC + YQ * qz]; }
+         if (COLLOC)
+         {
+#pragma unroll
+            for (int dz = 0; dz < D; dz++) { p1[dz] = ev[dz]; }
+         }
+         else
+         {
+            zero(es); zero(ea);
+            eo_split<Q, false>(ev, s, a);
+            eo_bwd_acc<D, Q, false>(bs.Bs, bs.Ba, s, a, es, ea);
+            eo_bwd_out<D>(es, ea, p1);
+         }
+      }
+#pragma unroll
+      for (int dz = 0; dz < D; dz++)
+      {
+         r1[t + C::SA * dz] = p0[dz];
+         if (DIFF) { r1[t + C::SA * (D + dz)] = p1[dz]; }
+      }
+   }
+   __syncthreads();
+
+   // ---- stage 5 (y^T) + scatter: line (dx, dz, e) -------------------------------------------
+   if (act1)
+   {
+      const double *F0 = r1 + a1;
+      double f[Q], s[QH], a[QH], es[DH], ea[DH], v[D];
+      zero(es); zero(ea);
+#pragma unroll
+      for (int qy = 0; qy < Q; qy++) { f[qy] = F0[qy]; }
+      if (COLLOC)
+      {
+#pragma unroll
+         for (int dy = 0; dy < D; dy++) { v[dy] = f[dy]; }
+      }
+      else
+      {
+         eo_split<Q, false>(f, s, a);
+         eo_bwd_acc<D, Q, false>(bs.Bs, bs.Ba, s, a, es, ea);
+      }
+      if (DIFF)
+      {
+#pragma unroll
+         for (int qy = 0; qy < Q; qy++) { f[qy] = F0[D * C::SA + qy]; }
+         eo_split<Q, true>(f, s, a);
+         eo_bwd_acc<D, Q, true>(bs.Gs, bs.Ga, s, a, es, ea);
+      }
+      if (COLLOC)
+      {
+         if (DIFF)
+         {
+            double g[D];
+            eo_bwd_out<D>(es, ea, g);
+#pragma unroll
+            for (int dy = 0; dy < D; dy++) { v[dy] += g[dy]; }
+         }
+      }
+      else { eo_bwd_out<D>(es, ea, v); }
+      double *ye = y + (e0 + e1) * D3 + loc1; // E-vector form
+#pragma unroll
+      for (int dy = 0; dy < D; dy++)
+      {
+         if (FUSED)
+         {
+            if (gi[dy] >= 0) { atomicAdd(y + gi[dy], v[dy]); }
+         }
+         else { ye[D * dy] += v[dy]; }
+      }
+   }
+}
+
+// host: even-odd tables from the (Q x D, q fastest) tables; returns false when the basis does
+// not have the required symmetry (relative 1e-12)
+template <int D, int Q>
+inline bool fill_eo_basis(const b2f_pa *pa, EOBasis<D, Q> &bs)
+{
+   constexpr int DH = (D + 1) / 2, QH = (Q + 1) / 2;
+   double bmax = 0.0, gmax = 0.0, asym = 0.0;
+   auto B = [&](int q, int d) { return pa->B[q + Q * d]; };
+   auto G = [&](int q, int d) { return pa->G[q + Q * d]; };
+   for (int q = 0; q < Q; q++)
+      for (int d = 0; d < D; d++)
+      {
+         bmax = fmax(bmax, fabs(B(q, d)));
+         gmax = fmax(gmax, fabs(G(q, d)));
+      }
+   for (int q = 0; q < Q; q++)
+      for (int d = 0; d < D; d++)
+      {
+         asym = fmax(asym, fabs(B(q, d) - B(Q - 1 - q, D - 1 - d)) / (bmax > 0 ? bmax : 1));
+         if (gmax > 0) { asym = fmax(asym, fabs(G(q, d) + G(Q - 1 - q, D - 1 - d)) / gmax); }
+      }
+   if (asym > 1e-12) { return false; }
+   for (int q = 0; q < QH; q++)
+      for (int i = 0; i < DH; i++)
+      {
+         const int j = D - 1 - i;
+         // symmetrised entries
+         const double bi = 0.5 * (B(q, i) + B(Q - 1 - q, j)), bj = 0.5 * (B(q, j) + B(Q - 1 - q, i));
+         const double gi = 0.5 * (G(q, i) - G(Q - 1 - q, j)), gj = 0.5 * (G(q, j) - G(Q - 1 - q, i));
+         if (i == j)
+         {
+            bs.Bs[q][i] = bi; bs.Ba[q][i] = 0.0;
+            bs.Gs[q][i] = gi; bs.Ga[q][i] = 0.0;
+         }
+         else
+         {
+            bs.Bs[q][i] = 0.5 * (bi + bj); bs.Ba[q][i] = 0.5 * (bi - bj);
+            bs.Gs[q][i] = 0.5 * (gi + gj); bs.Ga[q][i] = 0.5 * (gi - gj);
+         }
+      }
+   return true;
+}
+
+template <int KIND, int D, int Q, int NEB, int MINB = 1, int FUSEDSEL = 1>
+int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx)
+{
+   using C = PipeCfg<KIND, D, Q, NEB>;
+   b2f_ctx *ctx = pa->ctx;
+   if ((int)C::SMEM > ctx->max_smem_optin)
+   {
+      set_error("pa_apply_3d_eo<D=%d,Q=%d,NEB=%d> needs %zu B of shared memory", D, Q, NEB, C::SMEM);
+      return B2F_ERR_UNSUPPORTED;
+   }
+   EOBasis<D, Q> bs;
+   if (!fill_eo_basis(pa, bs))
+   {
+      set_error("pa_apply_3d_eo: the basis tables are not symmetric");
+      return B2F_ERR_UNSUPPORTED;
+   }
+   const int64_t grid = cdiv(pa->ne, NEB);
+   auto go = [&](auto kern) -> int
+   {
+      static int resident = 0;
+      if (resident == 0)
+      {
+         B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+         int occ = 0;
+         B2F_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NT, C::SMEM));
+         resident = (occ < 1 ? 1 : occ) * ctx->sm_count;
+      }
+      const char *pfs = getenv("B2F_PF");
+      const int pf = pfs ? atoi(pfs) : resident;
+      timing_mark(ctx);
+      kern<<<(unsigned)grid, C::NT, C::SMEM, ctx->stream>>>(bs, pa->data, x, y, idx, pa->ne, pf);
+      timing_mark(ctx);
+      B2F_LAUNCH_CHECK(ctx);
+      return B2F_OK;
+   };
+   const bool fused = idx != nullptr;
+   if ((fused && FUSEDSEL == 0) || (!fused && FUSEDSEL == 1))
+   {
+      set_error("pa_apply_3d_eo: kernel form not instantiated");
+      return B2F_ERR_UNSUPPORTED;
+   }
+   constexpr bool CL = (D == Q);
+   if (pa->collocated && CL)
+   {
+      if constexpr (FUSEDSEL != 0) { if (fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, CL, MINB>); } }
+      if constexpr (FUSEDSEL != 1) { if (!fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, CL, MINB>); } }
+   }
+   if constexpr (FUSEDSEL != 0) { if (fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, false, MINB>); } }
+   if constexpr (FUSEDSEL != 1) { if (!fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, false, MINB>); } }
+   return B2F_ERR_UNSUPPORTED;
+}
+
+} // namespace b2f
