@@ -352,7 +352,7 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None,
-                         "kernel": "pa_apply_3d_kernel (fused gather + G^T D G + scatter)",
+                         "kernel": "pa_apply_3d_eo_kernel (fused gather + even-odd G^T D G + scatter)",
                          "kernel_ms": k_ms, "kernel_launches": kt[1],
                          "kernel_share_of_step": kt[0] / ms,
                          "algorithmic_bytes_per_launch": ab,

@@ -1,7 +1,6 @@
 // 3D diffusion PA kernels, D1D = 2..5 (split for parallel compilation)
 #include <cstdlib>
 #include "pa_dispatch.cuh"
-#include "pa_apply_eo.cuh"
 namespace b2f
 {
 // experiment hook: B2F_VARIANT selects a kernel variant for (D1D,Q1D) = (5,6)
@@ -30,6 +29,13 @@ int pa_apply_3d_diffusion_2(b2f_pa *pa, const double *x, double *y, const int *i
          case 33: return launch_3d_eo<K, 5, 6, 6, 2>(pa, x, y, idx);
          case 34: return launch_3d_eo<K, 5, 6, 2, 5>(pa, x, y, idx);
          case 35: return launch_3d_eo<K, 5, 6, 3, 5>(pa, x, y, idx);
+         case 40: return launch_3d_eo<K, 5, 6, 3, 4, 1, true>(pa, x, y, idx);
+         case 41: return launch_3d_eo<K, 5, 6, 3, 3, 1, true>(pa, x, y, idx);
+         case 42: return launch_3d_eo<K, 5, 6, 4, 3, 1, true>(pa, x, y, idx);
+         case 43: return launch_3d_eo<K, 5, 6, 6, 2, 1, true>(pa, x, y, idx);
+         case 44: return launch_3d_eo<K, 5, 6, 5, 2, 1, true>(pa, x, y, idx);
+         case 45: return launch_3d_eo<K, 5, 6, 5, 2>(pa, x, y, idx);
+         case 46: return launch_3d_eo<K, 5, 6, 2, 5, 1, true>(pa, x, y, idx);
          case 20: return launch_3d_pipe<K, 5, 6, 6, 1>(pa, x, y, idx);
          case 21: return launch_3d_pipe<K, 5, 6, 6, 2>(pa, x, y, idx);
          case 22: return launch_3d_pipe<K, 5, 6, 3, 1>(pa, x, y, idx);

@@ -126,117 +126,38 @@ __device__ __forceinline__ void zero(double (&v)[N])
    for (int i = 0; i < N; i++) { v[i] = 0.0; }
 }
 
-template <int KIND, int D, int Q, int NEB, bool FUSED, bool COLLOC, int MINB>
-__global__ void __launch_bounds__(PipeCfg<KIND, D, Q, NEB>::NT, MINB)
-pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__restrict__ qdata,
-                      const double *__restrict__ x, double *__restrict__ y,
-                      const int *__restrict__ idx, const int64_t ne, const int pf)
+// ---- the five stages as device functions (shared by the one-shot and persistent kernels) ----
+template <int KIND, int D, int Q, int NEB, bool COLLOC>
+struct EOStages
 {
    using C = PipeCfg<KIND, D, Q, NEB>;
-   constexpr bool DIFF = C::DIFF;
-   constexpr int D2 = C::D2, D3 = C::D3, Q3 = C::Q3, YQ = C::YQ;
-   constexpr int DH = (D + 1) / 2, QH = (Q + 1) / 2;
-   extern __shared__ __align__(16) unsigned char smem_raw[];
-   uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-   double *qd = reinterpret_cast<double *>(smem_raw + 16);
-   double *r1 = qd + C::QD;
-   double *r2 = r1 + C::R1;
+   static constexpr bool DIFF = C::DIFF;
+   static constexpr int Q3 = C::Q3, YQ = C::YQ;
+   static constexpr int DH = (D + 1) / 2, QH = (Q + 1) / 2;
+   using BS = EOBasis<D, Q>;
 
-   const int t = threadIdx.x;
-   const int64_t e0 = (int64_t)blockIdx.x * NEB;
-   const int nev = (int)((ne - e0) < NEB ? (ne - e0) : NEB);
-
-   // ---- quadrature-data stream: TMA per element + L2 prefetch for the CTA `pf` blocks on ----
-   const double *qslab = qdata + e0 * (int64_t)(C::NQD * Q3);
-   if constexpr (C::TMA_OK)
+   // stage 1 (y): line (dx, dz, e): u[dy] -> B u, G u at qy, written to A at a1 + qy
+   static __device__ __forceinline__ void stage1(const BS &bs, const double (&u)[D], double *A0)
    {
-      if (t == 0)
+      double s[DH], a[DH], vb[Q], vg[Q];
+      eo_split<D, false>(u, s, a);
+      if (COLLOC)
       {
-         mbar_init(bar, 1);
-         mbar_expect_tx(bar, (uint32_t)(nev * C::NQD * Q3) * 8u);
-         for (int e = 0; e < nev; e++)
-         {
-            bulk_g2s(qd + e * C::DS, qslab + (int64_t)e * (C::NQD * Q3), (uint32_t)(C::NQD * Q3) * 8u, bar);
-         }
+#pragma unroll
+         for (int q = 0; q < Q; q++) { vb[q] = u[q < D ? q : 0]; }
       }
-   }
-   else
-   {
-      for (int i = t; i < nev * C::NQD * Q3; i += C::NT) { cp_async8(qd + i, qslab + i); }
-   }
-   if (pf > 0 && t == 32 % C::NT)
-   {
-      const int64_t ep = e0 + (int64_t)pf * NEB;
-      if (ep + NEB <= ne)
+      else { eo_fwd<D, Q, false>(bs.Bs, bs.Ba, s, a, vb); }
+      if (DIFF) { eo_fwd<D, Q, true>(bs.Gs, bs.Ga, s, a, vg); }
+#pragma unroll
+      for (int qy = 0; qy < Q; qy++)
       {
-         const uintptr_t q = reinterpret_cast<uintptr_t>(qdata + ep * (int64_t)(C::NQD * Q3)) & ~(uintptr_t)15;
-         l2_prefetch_bulk(reinterpret_cast<const void *>(q), ((uint32_t)(NEB * C::NQD * Q3) * 8u) & ~15u);
-         if (FUSED)
-         {
-            const uintptr_t a = reinterpret_cast<uintptr_t>(idx + ep * D3) & ~(uintptr_t)15;
-            l2_prefetch_bulk(reinterpret_cast<const void *>(a), ((uint32_t)(NEB * D3) * 4u) & ~15u);
-         }
+         A0[qy] = vb[qy];
+         if (DIFF) { A0[D * C::SA + qy] = vg[qy]; }
       }
    }
 
-   // ---- task coordinates of stages 1 and 5: line (dx, dz, e) --------------------------------
-   int e1, dx1, dz1;
-   if (C::L.order == 0) { e1 = t % NEB; dx1 = (t / NEB) % D; dz1 = t / (NEB * D); }
-   else if (C::L.order == 1) { dx1 = t % D; dz1 = (t / D) % D; e1 = t / D2; }
-   else if (C::L.order == 2) { e1 = t % NEB; dz1 = (t / NEB) % D; dx1 = t / (NEB * D); }
-   else { dz1 = t % D; e1 = (t / D) % NEB; dx1 = t / (NEB * D); }
-   const bool has1 = t < C::T1;
-   const bool act1 = has1 && e1 < nev;
-   const int loc1 = dx1 + D2 * dz1;                // + D*dy : position inside the element
-   const int a1 = Q * e1 + YQ * dx1 + C::SA * dz1; // + qy   : A/F address of this line
-
-   // ---- stage 1 (y): gather, u[dy] -> B u, G u at qy ---------------------------------------
-   int gi[D];
-   {
-      double u[D];
-#pragma unroll
-      for (int dy = 0; dy < D; dy++) { gi[dy] = -1; u[dy] = 0.0; }
-      if (act1)
-      {
-         if constexpr (FUSED)
-         {
-            const int *ip = idx + (e0 + e1) * D3 + loc1;
-#pragma unroll
-            for (int dy = 0; dy < D; dy++) { gi[dy] = __ldg(ip + D * dy); }
-#pragma unroll
-            for (int dy = 0; dy < D; dy++) { u[dy] = gi[dy] >= 0 ? __ldg(x + gi[dy]) : 0.0; }
-         }
-         else
-         {
-            const double *xe = x + (e0 + e1) * D3 + loc1;
-#pragma unroll
-            for (int dy = 0; dy < D; dy++) { u[dy] = __ldg(xe + D * dy); }
-         }
-      }
-      if (has1)
-      {
-         double s[DH], a[DH], vb[Q], vg[Q];
-         eo_split<D, false>(u, s, a);
-         if (COLLOC)
-         {
-#pragma unroll
-            for (int q = 0; q < Q; q++) { vb[q] = u[q < D ? q : 0]; }
-         }
-         else { eo_fwd<D, Q, false>(bs.Bs, bs.Ba, s, a, vb); }
-         if (DIFF) { eo_fwd<D, Q, true>(bs.Gs, bs.Ga, s, a, vg); }
-         double *A0 = r1 + a1;
-#pragma unroll
-         for (int qy = 0; qy < Q; qy++)
-         {
-            A0[qy] = vb[qy];
-            if (DIFF) { A0[D * C::SA + qy] = vg[qy]; }
-         }
-      }
-   }
-   __syncthreads();
-
-   // ---- stage 2 (z): line t2 = (yq, dx), contraction over dz -------------------------------
-   if (t < C::T2)
+   // stage 2 (z): line t2 = (yq, dx), contraction over dz
+   static __device__ __forceinline__ void stage2(const BS &bs, const double *r1, double *r2, int t)
    {
       double a0[D], a1v[D];
 #pragma unroll
@@ -276,11 +197,10 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
          }
       }
    }
-   if constexpr (!C::TMA_OK) { cp_async_wait_all(); }
-   __syncthreads();
 
-   // ---- stage 3 (x, D, x^T) in place: line t3 = (yq, qz) ------------------------------------
-   if (t < C::T3)
+   // stage 3 (x, D, x^T) in place: line t3 = (yq, qz)
+   static __device__ __forceinline__ void stage3(const BS &bs, double *r2, const double *qd, int t,
+                                                 uint64_t *bar, uint32_t parity)
    {
       const int yq = t % YQ, qz = t / YQ;
       const int e = yq / Q, qy = yq - e * Q;
@@ -323,7 +243,7 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
          }
       }
       // quadrature data of this line: NQD rows of Q doubles from the TMA-filled slab
-      if constexpr (C::TMA_OK) { mbar_wait(bar, 0); }
+      if constexpr (C::TMA_OK) { mbar_wait(bar, parity); }
       const double *dq = qd + e * C::DS + Q * (qy + Q * qz);
       if (DIFF)
       {
@@ -410,10 +330,9 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
          }
       }
    }
-   __syncthreads();
 
-   // ---- stage 4 (z^T): line t2 = (yq, dx) ----------------------------------------------------
-   if (t < C::T2)
+   // stage 4 (z^T): line t2 = (yq, dx)
+   static __device__ __forceinline__ void stage4(const BS &bs, const double *r2, double *r1, int t)
    {
       const int yq = t % YQ, dx = t / YQ;
       const double *E0 = r2 + yq + C::SC * dx;
@@ -440,9 +359,9 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
       }
       if (COLLOC)
       {
-         double g[D];
          if (DIFF)
          {
+            double g[D];
             eo_bwd_out<D>(es, ea, g);
 #pragma unroll
             for (int dz = 0; dz < D; dz++) { p0[dz] += g[dz]; }
@@ -473,13 +392,11 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
          if (DIFF) { r1[t + C::SA * (D + dz)] = p1[dz]; }
       }
    }
-   __syncthreads();
 
-   // ---- stage 5 (y^T) + scatter: line (dx, dz, e) -------------------------------------------
-   if (act1)
+   // stage 5 (y^T): line (dx, dz, e): F at F0 + qy -> v[dy]
+   static __device__ __forceinline__ void stage5(const BS &bs, const double *F0, double (&v)[D])
    {
-      const double *F0 = r1 + a1;
-      double f[Q], s[QH], a[QH], es[DH], ea[DH], v[D];
+      double f[Q], s[QH], a[QH], es[DH], ea[DH];
       zero(es); zero(ea);
 #pragma unroll
       for (int qy = 0; qy < Q; qy++) { f[qy] = F0[qy]; }
@@ -511,6 +428,115 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
          }
       }
       else { eo_bwd_out<D>(es, ea, v); }
+   }
+};
+
+// stage 1/5 lane -> (e, dx, dz)
+template <int D, int NEB, int ORDER>
+__device__ __forceinline__ void eo_line_coords(int t, int &e1, int &dx1, int &dz1)
+{
+   if (ORDER == 0) { e1 = t % NEB; dx1 = (t / NEB) % D; dz1 = t / (NEB * D); }
+   else if (ORDER == 1) { dx1 = t % D; dz1 = (t / D) % D; e1 = t / (D * D); }
+   else if (ORDER == 2) { e1 = t % NEB; dz1 = (t / NEB) % D; dx1 = t / (NEB * D); }
+   else { dz1 = t % D; e1 = (t / D) % NEB; dx1 = t / (NEB * D); }
+}
+
+// ---- one tile per CTA; next CTA's slab prefetched into L2 --------------------------------------
+template <int KIND, int D, int Q, int NEB, bool FUSED, bool COLLOC, int MINB>
+__global__ void __launch_bounds__(PipeCfg<KIND, D, Q, NEB>::NT, MINB)
+pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__restrict__ qdata,
+                      const double *__restrict__ x, double *__restrict__ y,
+                      const int *__restrict__ idx, const int64_t ne, const int pf)
+{
+   using C = PipeCfg<KIND, D, Q, NEB>;
+   using S = EOStages<KIND, D, Q, NEB, COLLOC>;
+   constexpr int D2 = C::D2, D3 = C::D3, Q3 = C::Q3, YQ = C::YQ;
+   extern __shared__ __align__(16) unsigned char smem_raw[];
+   uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+   double *qd = reinterpret_cast<double *>(smem_raw + 16);
+   double *r1 = qd + C::QD;
+   double *r2 = r1 + C::R1;
+
+   const int t = threadIdx.x;
+   const int64_t e0 = (int64_t)blockIdx.x * NEB;
+   const int nev = (int)((ne - e0) < NEB ? (ne - e0) : NEB);
+
+   // quadrature-data stream: TMA per element + L2 prefetch for the CTA `pf` blocks on
+   const double *qslab = qdata + e0 * (int64_t)(C::NQD * Q3);
+   if constexpr (C::TMA_OK)
+   {
+      if (t == 0)
+      {
+         mbar_init(bar, 1);
+         mbar_expect_tx(bar, (uint32_t)(nev * C::NQD * Q3) * 8u);
+         for (int e = 0; e < nev; e++)
+         {
+            bulk_g2s(qd + e * C::DS, qslab + (int64_t)e * (C::NQD * Q3), (uint32_t)(C::NQD * Q3) * 8u, bar);
+         }
+      }
+   }
+   else
+   {
+      for (int i = t; i < nev * C::NQD * Q3; i += C::NT) { cp_async8(qd + i, qslab + i); }
+   }
+   if (pf > 0 && t == 32 % C::NT)
+   {
+      const int64_t ep = e0 + (int64_t)pf * NEB;
+      if (ep + NEB <= ne)
+      {
+         const uintptr_t q = reinterpret_cast<uintptr_t>(qdata + ep * (int64_t)(C::NQD * Q3)) & ~(uintptr_t)15;
+         l2_prefetch_bulk(reinterpret_cast<const void *>(q), ((uint32_t)(NEB * C::NQD * Q3) * 8u) & ~15u);
+         if (FUSED)
+         {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(idx + ep * D3) & ~(uintptr_t)15;
+            l2_prefetch_bulk(reinterpret_cast<const void *>(a), ((uint32_t)(NEB * D3) * 4u) & ~15u);
+         }
+      }
+   }
+
+   int e1, dx1, dz1;
+   eo_line_coords<D, NEB, C::L.order>(t, e1, dx1, dz1);
+   const bool has1 = t < C::T1;
+   const bool act1 = has1 && e1 < nev;
+   const int loc1 = dx1 + D2 * dz1;                // + D*dy : position inside the element
+   const int a1 = Q * e1 + YQ * dx1 + C::SA * dz1; // + qy   : A/F address of this line
+
+   int gi[D];
+   {
+      double u[D];
+#pragma unroll
+      for (int dy = 0; dy < D; dy++) { gi[dy] = -1; u[dy] = 0.0; }
+      if (act1)
+      {
+         if constexpr (FUSED)
+         {
+            const int *ip = idx + (e0 + e1) * D3 + loc1;
+#pragma unroll
+            for (int dy = 0; dy < D; dy++) { gi[dy] = __ldg(ip + D * dy); }
+#pragma unroll
+            for (int dy = 0; dy < D; dy++) { u[dy] = gi[dy] >= 0 ? __ldg(x + gi[dy]) : 0.0; }
+         }
+         else
+         {
+            const double *xe = x + (e0 + e1) * D3 + loc1;
+#pragma unroll
+            for (int dy = 0; dy < D; dy++) { u[dy] = __ldg(xe + D * dy); }
+         }
+      }
+      if (has1) { S::stage1(bs, u, r1 + a1); }
+   }
+   __syncthreads();
+   if (t < C::T2) { S::stage2(bs, r1, r2, t); }
+   if constexpr (!C::TMA_OK) { cp_async_wait_all(); }
+   __syncthreads();
+   if (t < C::T3) { S::stage3(bs, r2, qd, t, bar, 0); }
+   __syncthreads();
+   if (t < C::T2) { S::stage4(bs, r2, r1, t); }
+   __syncthreads();
+   if (act1)
+   {
+      double v[D];
+      S::stage5(bs, r1 + a1, v);
       double *ye = y + (e0 + e1) * D3 + loc1; // E-vector form
 #pragma unroll
       for (int dy = 0; dy < D; dy++)
@@ -521,6 +547,151 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
          }
          else { ye[D * dy] += v[dy]; }
       }
+   }
+}
+
+// ---- persistent CTAs, every stream prefetched one tile ahead (see pa_apply_pipe.cuh) -----------
+template <int KIND, int D, int Q, int NEB, bool FUSED, bool COLLOC, int MINB>
+__global__ void __launch_bounds__(PipeCfg<KIND, D, Q, NEB>::NT, MINB)
+pa_apply_3d_eop_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__restrict__ qdata,
+                       const double *__restrict__ x, double *__restrict__ y,
+                       const int *__restrict__ idx, const int64_t ne, const int pf)
+{
+   using C = PipeCfg<KIND, D, Q, NEB>;
+   using S = EOStages<KIND, D, Q, NEB, COLLOC>;
+   constexpr int D2 = C::D2, D3 = C::D3, Q3 = C::Q3, YQ = C::YQ;
+   extern __shared__ __align__(16) unsigned char smem_raw[];
+   uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+   double *qd = reinterpret_cast<double *>(smem_raw + 16);
+   double *r1 = qd + C::QD;
+   double *r2 = r1 + C::R1;
+   int *idx_s = reinterpret_cast<int *>(r2 + C::R2);
+   (void)pf;
+
+   const int t = threadIdx.x;
+   const int64_t ntiles = (ne + NEB - 1) / NEB;
+   int e1, dx1, dz1;
+   eo_line_coords<D, NEB, C::L.order>(t, e1, dx1, dz1);
+   const bool has1 = t < C::T1;
+   const int loc1 = dx1 + D2 * dz1;
+   const int a1 = Q * e1 + YQ * dx1 + C::SA * dz1;
+
+   auto issue_qdata = [&](int64_t tile)
+   {
+      const int64_t e0 = tile * NEB;
+      const int nev = (int)((ne - e0) < NEB ? (ne - e0) : NEB);
+      const double *src = qdata + e0 * (int64_t)(C::NQD * Q3);
+      if constexpr (C::TMA_OK)
+      {
+         if (t == 0)
+         {
+            fence_proxy_async(); // the slab was just read through the generic proxy
+            mbar_expect_tx(bar, (uint32_t)(nev * C::NQD * Q3) * 8u);
+            for (int e = 0; e < nev; e++)
+            {
+               bulk_g2s(qd + e * C::DS, src + (int64_t)e * (C::NQD * Q3), (uint32_t)(C::NQD * Q3) * 8u, bar);
+            }
+         }
+      }
+      else
+      {
+         for (int i = t; i < nev * C::NQD * Q3; i += C::NT) { cp_async8(qd + i, src + i); }
+      }
+   };
+   auto issue_idx = [&](int64_t tile)
+   {
+      if constexpr (FUSED)
+      {
+         const int64_t e0 = tile * NEB;
+         const int nev = (int)((ne - e0) < NEB ? (ne - e0) : NEB);
+         const int *src = idx + e0 * D3;
+         for (int i = t; i < nev * D3; i += C::NT) { cp_async4(idx_s + i, src + i); }
+      }
+   };
+   auto load_inputs = [&](int64_t tile, int (&gi)[D], double (&u)[D])
+   {
+      const int64_t e0 = tile * NEB;
+      const int nev = (int)((ne - e0) < NEB ? (ne - e0) : NEB);
+#pragma unroll
+      for (int dy = 0; dy < D; dy++) { gi[dy] = -1; u[dy] = 0.0; }
+      if (has1 && e1 < nev)
+      {
+         if constexpr (FUSED)
+         {
+#pragma unroll
+            for (int dy = 0; dy < D; dy++) { gi[dy] = idx_s[e1 * D3 + loc1 + D * dy]; }
+#pragma unroll
+            for (int dy = 0; dy < D; dy++) { u[dy] = gi[dy] >= 0 ? __ldg(x + gi[dy]) : 0.0; }
+         }
+         else
+         {
+            const double *xe = x + (e0 + e1) * D3 + loc1;
+#pragma unroll
+            for (int dy = 0; dy < D; dy++) { gi[dy] = 0; u[dy] = __ldg(xe + D * dy); }
+         }
+      }
+   };
+
+   int64_t tile = blockIdx.x;
+   if (tile >= ntiles) { return; }
+   if (t == 0) { mbar_init(bar, 1); }
+   __syncthreads();
+   issue_qdata(tile);
+   issue_idx(tile);
+   cp_async_wait_all();
+   __syncthreads();
+   int gi[D], gi_n[D];
+   double u[D], u_n[D];
+   load_inputs(tile, gi, u);
+   uint32_t parity = 0;
+
+   for (; tile < ntiles; tile += gridDim.x)
+   {
+      const int64_t e0 = tile * NEB;
+      const int nev = (int)((ne - e0) < NEB ? (ne - e0) : NEB);
+      const int64_t next = tile + gridDim.x;
+      const bool more = next < ntiles;
+
+      if (has1) { S::stage1(bs, u, r1 + a1); }
+      if (more) { issue_idx(next); } // idx_s was consumed when this tile's inputs were gathered
+      __syncthreads();
+      if (t < C::T2) { S::stage2(bs, r1, r2, t); }
+      if constexpr (!C::TMA_OK) { cp_async_wait_all(); }
+      __syncthreads();
+      if (t < C::T3) { S::stage3(bs, r2, qd, t, bar, parity); }
+      parity ^= 1u;
+      if (FUSED && more) { cp_async_wait_all(); } // this thread's share of the next indices landed
+      __syncthreads();
+      // the slab is free: stream the next tile's quadrature data while stages 4, 5 and the next
+      // tile's stages 1, 2 run; gather the next tile's inputs into registers
+      if (more)
+      {
+         issue_qdata(next);
+         load_inputs(next, gi_n, u_n);
+      }
+      if (t < C::T2) { S::stage4(bs, r2, r1, t); }
+      __syncthreads();
+      if (has1 && e1 < nev)
+      {
+         double v[D];
+         S::stage5(bs, r1 + a1, v);
+         double *ye = y + (e0 + e1) * D3 + loc1;
+#pragma unroll
+         for (int dy = 0; dy < D; dy++)
+         {
+            if (FUSED)
+            {
+               if (gi[dy] >= 0) { atomicAdd(y + gi[dy], v[dy]); }
+            }
+            else { ye[D * dy] += v[dy]; }
+         }
+      }
+      if (more)
+      {
+#pragma unroll
+         for (int dy = 0; dy < D; dy++) { gi[dy] = gi_n[dy]; u[dy] = u_n[dy]; }
+      }
+      __syncthreads(); // F consumed before the next tile's stage 1 overwrites the region
    }
 }
 
@@ -567,7 +738,7 @@ inline bool fill_eo_basis(const b2f_pa *pa, EOBasis<D, Q> &bs)
    return true;
 }
 
-template <int KIND, int D, int Q, int NEB, int MINB = 1, int FUSEDSEL = 1>
+template <int KIND, int D, int Q, int NEB, int MINB = 1, int FUSEDSEL = 1, bool PERSIST = false>
 int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx)
 {
    using C = PipeCfg<KIND, D, Q, NEB>;
@@ -583,7 +754,7 @@ int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx)
       set_error("pa_apply_3d_eo: the basis tables are not symmetric");
       return B2F_ERR_UNSUPPORTED;
    }
-   const int64_t grid = cdiv(pa->ne, NEB);
+   int64_t grid = cdiv(pa->ne, NEB);
    auto go = [&](auto kern) -> int
    {
       static int resident = 0;
@@ -596,6 +767,7 @@ int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx)
       }
       const char *pfs = getenv("B2F_PF");
       const int pf = pfs ? atoi(pfs) : resident;
+      if (PERSIST && grid > resident) { grid = resident; }
       timing_mark(ctx);
       kern<<<(unsigned)grid, C::NT, C::SMEM, ctx->stream>>>(bs, pa->data, x, y, idx, pa->ne, pf);
       timing_mark(ctx);
@@ -609,13 +781,26 @@ int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx)
       return B2F_ERR_UNSUPPORTED;
    }
    constexpr bool CL = (D == Q);
-   if (pa->collocated && CL)
+   if constexpr (PERSIST)
    {
-      if constexpr (FUSEDSEL != 0) { if (fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, CL, MINB>); } }
-      if constexpr (FUSEDSEL != 1) { if (!fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, CL, MINB>); } }
+      if (pa->collocated && CL)
+      {
+         if constexpr (FUSEDSEL != 0) { if (fused) { return go(pa_apply_3d_eop_kernel<KIND, D, Q, NEB, true, CL, MINB>); } }
+         if constexpr (FUSEDSEL != 1) { if (!fused) { return go(pa_apply_3d_eop_kernel<KIND, D, Q, NEB, false, CL, MINB>); } }
+      }
+      if constexpr (FUSEDSEL != 0) { if (fused) { return go(pa_apply_3d_eop_kernel<KIND, D, Q, NEB, true, false, MINB>); } }
+      if constexpr (FUSEDSEL != 1) { if (!fused) { return go(pa_apply_3d_eop_kernel<KIND, D, Q, NEB, false, false, MINB>); } }
    }
-   if constexpr (FUSEDSEL != 0) { if (fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, false, MINB>); } }
-   if constexpr (FUSEDSEL != 1) { if (!fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, false, MINB>); } }
+   else
+   {
+      if (pa->collocated && CL)
+      {
+         if constexpr (FUSEDSEL != 0) { if (fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, CL, MINB>); } }
+         if constexpr (FUSEDSEL != 1) { if (!fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, CL, MINB>); } }
+      }
+      if constexpr (FUSEDSEL != 0) { if (fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, false, MINB>); } }
+      if constexpr (FUSEDSEL != 1) { if (!fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, false, MINB>); } }
+   }
    return B2F_ERR_UNSUPPORTED;
 }
 

@@ -30,27 +30,25 @@
 //    essential dof: it reads 0 and is not scattered (ConstrainedOperator, operator.cpp:601).
 #pragma once
 #include "pa_apply.cuh"
+#include "pa_layout_table.h"
 
 namespace b2f
 {
 
-// stage-1/5 lane order and slab-stride residue, chosen offline with tools/smem_conflicts.py
+// stage-1/5 lane order, slab-stride residue and quadrature-slab padding: generated offline by
+// tools/gen_layout_table.py (simulation of every shared-memory access pattern)
 struct PipeLayout
 {
    int order; // 0: (e, dx, dz) e fastest   1: (dx, dz, e)   2: (e, dz, dx)   3: (dz, e, dx)
    int ra;    // SA % 16
+   int dpad;  // doubles appended to each element's quadrature-data slab
 };
 
-__host__ __device__ constexpr PipeLayout pipe_layout(int D, int Q, int NEB)
+__host__ __device__ constexpr PipeLayout pipe_layout(int kind, int D, int Q, int NEB)
 {
-   (void)NEB;
-   if (D == 5 && Q == 6) { return NEB == 3 ? PipeLayout{1, 13} : NEB == 8 ? PipeLayout{2, 1} : PipeLayout{0, 5}; }
-   if (D == 4 && Q == 5) { return {0, 8}; }
-   if (D == 6 && Q == 7) { return {0, 8}; }
-   if (D == 5 && Q == 5) { return {0, 6}; }
-   if (D == 8 && Q == 8) { return {2, 1}; }
-   if (D == 7 && Q == 8) { return {3, 9}; }
-   return {0, (D * Q * NEB) % 16 == 0 ? 1 : 0};
+   if (D < 2 || D > 9 || Q < D || Q > D + 2 || NEB < 1 || NEB > 32) { return {0, 0, 0}; }
+   const LayoutEntry e = kLayoutTable[kind == B2F_KIND_DIFFUSION ? 0 : 1][D - 2][Q - D][NEB - 1];
+   return {e.order, e.ra, e.dpad};
 }
 
 template <int KIND, int D, int Q, int NEB>
@@ -66,7 +64,7 @@ struct PipeCfg
    static constexpr int T2 = D * YQ;    // z, z^T tasks (yq, dx)
    static constexpr int T3 = Q * YQ;    // x / D / x^T tasks (yq, qz)
    static constexpr int NT = ((T3 + 31) / 32) * 32;
-   static constexpr PipeLayout L = pipe_layout(D, Q, NEB);
+   static constexpr PipeLayout L = pipe_layout(KIND, D, Q, NEB);
    static constexpr int SA = pad16(D * YQ, L.ra); // A,F[f][dz][dx][yq]
    static constexpr int SC = pad16(Q * YQ, YQ);   // C,E[f][dx][qz][yq]
    static constexpr int R1 = NA * D * SA;
@@ -75,18 +73,7 @@ struct PipeCfg
    // lanes (qy fastest, then e) hit distinct bank groups across element boundaries
    static constexpr bool TMA_OK = ((NQD * Q3) % 2) == 0; // slab bytes multiple of 16
    static constexpr bool VEC = TMA_OK && (Q % 2 == 0);   // rows 16-byte aligned
-   static constexpr int dpad()
-   {
-      if (!TMA_OK) { return 0; }
-      if (!VEC) { return 0; }
-      // want (DS/2) == (Q/2)*Q (mod 8) in 16-byte units
-      for (int p = 0; p < 16; p += 2)
-      {
-         if ((((NQD * Q3 + p) / 2) % 8) == (((Q / 2) * Q) % 8)) { return p; }
-      }
-      return 0;
-   }
-   static constexpr int DS = NQD * Q3 + dpad();
+   static constexpr int DS = NQD * Q3 + (TMA_OK ? L.dpad : 0);
    static constexpr int QD = NEB * DS;
    static constexpr int NIDX = ((NEB * D3 + 3) / 4) * 4; // ints
    static constexpr size_t SMEM = 16 + sizeof(double) * (size_t)(QD + R1 + R2) + sizeof(int) * NIDX;

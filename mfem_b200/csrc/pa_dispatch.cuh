@@ -3,7 +3,7 @@
 // thread-per-element fallback: every CEED BP order p = 1..8 has a specialised kernel
 // (MFEM's tables miss (9,10), i.e. p = 8, for both mass and diffusion).
 #pragma once
-#include "pa_apply.cuh"
+#include "pa_apply_eo.cuh"
 
 namespace b2f
 {
@@ -71,25 +71,89 @@ constexpr int neb_2d(int kind, int D, int Q)
    case (D_) * 100 + (Q_):                                                             \
       return launch_2d<KIND, D_, Q_, neb_2d(KIND, D_, Q_)>(pa, x, y, idx);
 
-// One (kind, D, Q): the E-vector form (AddMultPA seam) has one instantiation; the fused
-// L-vector form (the hot path) has three elements-per-CTA candidates, selected by the tuned
-// table or, for experiments, by the environment variable B2F_NEB_CAND = 0|1|2.
+// ---- even-odd kernel (pa_apply_eo.cuh) sizing: mirrors PipeCfg::SMEM --------------------------
+constexpr int smem_eo(int kind, int D, int Q, int n)
+{
+   const int nqd = kind == B2F_KIND_DIFFUSION ? 6 : 1;
+   const int na = kind == B2F_KIND_DIFFUSION ? 2 : 1;
+   const int nc = kind == B2F_KIND_DIFFUSION ? 3 : 1;
+   const int yq = Q * n;
+   const PipeLayout L = pipe_layout(kind, D, Q, n);
+   const int sa = pad16(D * yq, L.ra), sc = pad16(Q * yq, yq);
+   const int q3 = Q * Q * Q;
+   const int dp = (nqd * q3) % 2 == 0 ? L.dpad : 0;
+   return 16 + 8 * (n * (nqd * q3 + dp) + na * D * sa + nc * D * sc) + 4 * (((n * D * D * D + 3) / 4) * 4);
+}
+
+// Elements per CTA, candidate i: 0 -> >= 4 CTAs per SM, 1 -> 3 CTAs, 2 -> 2 CTAs; <= 512 threads
+constexpr int neb_eo(int kind, int D, int Q, int cand)
+{
+   const int budget = cand == 0 ? 55 * 1024 : cand == 1 ? 74 * 1024 : 112 * 1024;
+   int n = 1;
+   while (n < 32 && smem_eo(kind, D, Q, n + 1) <= budget && (n + 1) * Q * Q <= 512) { n++; }
+   return n;
+}
+
+constexpr int minb_eo(int kind, int D, int Q, int n)
+{
+   const int nt = ((n * Q * Q + 31) / 32) * 32;
+   const int by_smem = (227 * 1024) / (smem_eo(kind, D, Q, n) + 1024);
+   const int by_regs = 65536 / (nt * 120);
+   int b = by_smem < by_regs ? by_smem : by_regs;
+   if (b > 8) { b = 8; }
+   return b < 1 ? 1 : b;
+}
+
+// measured choice of the candidate per (kind, D, Q) (tools/opbench.py sweeps, profiles/)
+constexpr int tuned_cand_eo(int kind, int D, int Q)
+{
+   // profiles/r01_sweep_eo_kernel.txt: the smallest tile (>= 4 CTAs per SM) wins except at the
+   // lowest orders, where a CTA of the smallest tile has too few threads
+   if (kind == B2F_KIND_DIFFUSION) { return (D <= 3 && Q >= D + 1) ? 1 : 0; }
+   return D <= 4 ? 1 : 0;
+}
+
+inline bool basis_is_symmetric(const b2f_pa *pa)
+{
+   const int D = pa->d1d, Q = pa->q1d;
+   double bmax = 0.0, gmax = 0.0, asym = 0.0;
+   for (int i = 0; i < D * Q; i++) { bmax = fmax(bmax, fabs(pa->B[i])); gmax = fmax(gmax, fabs(pa->G[i])); }
+   for (int q = 0; q < Q; q++)
+      for (int d = 0; d < D; d++)
+      {
+         const int a = q + Q * d, b = (Q - 1 - q) + Q * (D - 1 - d);
+         if (bmax > 0) { asym = fmax(asym, fabs(pa->B[a] - pa->B[b]) / bmax); }
+         if (gmax > 0) { asym = fmax(asym, fabs(pa->G[a] + pa->G[b]) / gmax); }
+      }
+   return asym <= 1e-12;
+}
+
+// One (kind, D, Q).  Symmetric bases (every H1 basis on symmetric nodes with a symmetric rule:
+// all CEED BPs) run the even-odd kernel: the fused L-vector form (the hot path) with three
+// elements-per-CTA candidates -- the tuned table picks one, B2F_NEB_CAND = 0|1|2 overrides it
+// for experiments -- and the E-vector form (AddMultPA seam) with one.  A basis without the
+// symmetry falls back to the general pencil kernel of pa_apply.cuh.
 template <int KIND, int D, int Q>
 int run_3d(b2f_pa *pa, const double *x, double *y, const int *idx)
 {
-   constexpr int N0 = neb_3d(KIND, D, Q, 0), N1 = neb_3d(KIND, D, Q, 1), N2 = neb_3d(KIND, D, Q, 2);
-   if (!idx) { return launch_3d<KIND, D, Q, N1, 1, 1, 0>(pa, x, y, idx); }
+   if (!basis_is_symmetric(pa) || getenv("B2F_GENERAL_KERNEL"))
+   {
+      constexpr int NG = neb_3d(KIND, D, Q, 1);
+      return launch_3d<KIND, D, Q, NG, 1, 1, 2>(pa, x, y, idx);
+   }
+   constexpr int N0 = neb_eo(KIND, D, Q, 0), N1 = neb_eo(KIND, D, Q, 1), N2 = neb_eo(KIND, D, Q, 2);
+   if (!idx) { return launch_3d_eo<KIND, D, Q, N1, 1, 0>(pa, x, y, idx); }
    const char *s = getenv("B2F_NEB_CAND");
-   const int cand = s ? atoi(s) : tuned_cand_3d(KIND, D, Q);
+   const int cand = s ? atoi(s) : tuned_cand_eo(KIND, D, Q);
    if (cand == 0 || (cand == 1 && N1 == N0) || (cand == 2 && N2 == N0))
    {
-      return launch_3d<KIND, D, Q, N0, 1, minb_3d(KIND, D, Q, N0), 1>(pa, x, y, idx);
+      return launch_3d_eo<KIND, D, Q, N0, minb_eo(KIND, D, Q, N0), 1>(pa, x, y, idx);
    }
    if (cand == 1 || (cand == 2 && N2 == N1))
    {
-      if constexpr (N1 != N0) { return launch_3d<KIND, D, Q, N1, 1, minb_3d(KIND, D, Q, N1), 1>(pa, x, y, idx); }
+      if constexpr (N1 != N0) { return launch_3d_eo<KIND, D, Q, N1, minb_eo(KIND, D, Q, N1), 1>(pa, x, y, idx); }
    }
-   if constexpr (N2 != N1 && N2 != N0) { return launch_3d<KIND, D, Q, N2, 1, minb_3d(KIND, D, Q, N2), 1>(pa, x, y, idx); }
+   if constexpr (N2 != N1 && N2 != N0) { return launch_3d_eo<KIND, D, Q, N2, minb_eo(KIND, D, Q, N2), 1>(pa, x, y, idx); }
    return B2F_ERR_UNSUPPORTED;
 }
 

@@ -57,13 +57,15 @@ def run_case(bp, p, n, variants, reps):
     ab = (k * ir.nq1d ** 3 * 8 + 4 * (p + 1) ** 3) * fes.ne + 16 * N
     print(f"BP{bp} p={p} n={n}: NE={fes.ne} dofs={N} algorithmic bytes/apply={ab/1e9:.3f} GB", flush=True)
     for v in variants:
-        for key in ("B2F_VARIANT", "B2F_PF", "B2F_NEB_CAND"):
+        for key in ("B2F_VARIANT", "B2F_PF", "B2F_NEB_CAND", "B2F_GENERAL_KERNEL"):
             os.environ.pop(key, None)
         for kv in v.split("+"):
             if kv.startswith("c"):
                 os.environ["B2F_NEB_CAND"] = kv[1:]
             elif kv.startswith("pf"):
                 os.environ["B2F_PF"] = kv[2:]
+            elif kv == "g":
+                os.environ["B2F_GENERAL_KERNEL"] = "1"
             elif kv.startswith("v"):
                 os.environ["B2F_VARIANT"] = kv[1:]
         try:
