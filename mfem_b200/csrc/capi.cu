@@ -585,6 +585,7 @@ void b2f_operator_destroy(b2f_operator *op)
    cudaFree(op->xl); cudaFree(op->yl);
    for (double *p : op->pcg_vec) { cudaFree(p); }
    cudaFree(op->pcg_hist);
+   cudaFree(op->dot_acc);
    delete op;
 }
 
@@ -595,12 +596,24 @@ static int ensure(double **p, int64_t n)
 }
 
 // y_l = R^T (sum_i A_i) R x_l on LOCAL vectors; idx selects the (masked) gather index
-static int local_mult_fused(b2f_operator *op, const double *x_l, double *y_l, const int *idx)
+static int local_mult_fused(b2f_operator *op, const double *x_l, double *y_l, const int *idx,
+                            double *dot_acc = nullptr)
 {
    b2f_ctx *ctx = op->ctx;
    B2F_CUDA(cudaMemsetAsync(y_l, 0, sizeof(double) * (size_t)op->r->ndofs, ctx->stream));
-   for (b2f_pa *pa : op->integ) { B2F_TRY(pa_apply(pa, x_l, y_l, idx)); }
+   for (b2f_pa *pa : op->integ) { B2F_TRY(pa_apply(pa, x_l, y_l, idx, dot_acc)); }
    return B2F_OK;
+}
+
+// every integrator can accumulate x.(Ax) inside its kernel (and the gather map is unsigned).
+// Opt-in (B2F_FUSED_DOT=1): on B200 the solver loop runs at the 1 kW power cap, where the
+// 16 B/dof pass it saves is paid back by the slightly heavier operator kernel (measured:
+// 17.0 vs 17.0 GDOF/s for BP3 p=4), so the plain two-kernel form stays the default.
+static bool operator_has_fused_dot(const b2f_operator *op)
+{
+   if (op->signed_map || !getenv("B2F_FUSED_DOT")) { return false; }
+   for (const b2f_pa *pa : op->integ) { if (!pa_has_fused_dot(pa)) { return false; } }
+   return true;
 }
 
 static int local_mult_unfused(b2f_operator *op, const double *x_l, double *y_l)
@@ -616,7 +629,8 @@ static int local_mult_unfused(b2f_operator *op, const double *x_l, double *y_l)
    return restriction_scatter(r, op->ye, y_l, 0);                      // :557
 }
 
-static int local_mult(b2f_operator *op, const double *x_l, double *y_l, bool constrained_mask)
+static int local_mult(b2f_operator *op, const double *x_l, double *y_l, bool constrained_mask,
+                      double *dot_acc = nullptr)
 {
    if (op->signed_map)
    {
@@ -624,7 +638,7 @@ static int local_mult(b2f_operator *op, const double *x_l, double *y_l, bool con
       return local_mult_unfused(op, x_l, y_l);
    }
    const int *idx = (constrained_mask && op->fused_idx) ? op->fused_idx : op->r->gather_map;
-   return local_mult_fused(op, x_l, y_l, idx);
+   return local_mult_fused(op, x_l, y_l, idx, dot_acc);
 }
 
 // A on the operator's own vectors (true-dof vectors when a halo is attached):
@@ -632,9 +646,10 @@ static int local_mult(b2f_operator *op, const double *x_l, double *y_l, bool con
 // lcap: x and y are caller-owned buffers with room for n_ldofs entries (the PCG work
 // vectors); with the owned-first numbering P and P^T then run in place and no vector is
 // copied.  Otherwise the true-dof vectors go through the L-vector scratch xl / yl.
-static int rap_mult(b2f_operator *op, const double *x, double *y, bool constrained_mask, bool lcap = false)
+static int rap_mult(b2f_operator *op, const double *x, double *y, bool constrained_mask, bool lcap = false,
+                    double *dot_acc = nullptr)
 {
-   if (!op->halo) { return local_mult(op, x, y, constrained_mask); }
+   if (!op->halo) { return local_mult(op, x, y, constrained_mask, dot_acc); }
    b2f_ctx *ctx = op->ctx;
    const int nl = op->r->ndofs;
    if (halo_is_prefix(op->halo))
@@ -650,7 +665,7 @@ static int rap_mult(b2f_operator *op, const double *x, double *y, bool constrain
          B2F_CUDA(cudaMemcpyAsync(xl, x, sizeof(double) * nt, cudaMemcpyDeviceToDevice, ctx->stream));
       }
       B2F_TRY(halo_mult_inplace(op->halo, xl));
-      B2F_TRY(local_mult(op, xl, yl, constrained_mask));
+      B2F_TRY(local_mult(op, xl, yl, constrained_mask, dot_acc));
       B2F_TRY(halo_mult_transpose_inplace(op->halo, yl));
       if (!lcap) { B2F_CUDA(cudaMemcpyAsync(y, yl, sizeof(double) * nt, cudaMemcpyDeviceToDevice, ctx->stream)); }
       return B2F_OK;
@@ -658,7 +673,7 @@ static int rap_mult(b2f_operator *op, const double *x, double *y, bool constrain
    B2F_TRY(ensure(&op->xl, nl));
    B2F_TRY(ensure(&op->yl, nl));
    B2F_TRY(halo_mult(op->halo, x, op->xl));
-   B2F_TRY(local_mult(op, op->xl, op->yl, constrained_mask));
+   B2F_TRY(local_mult(op, op->xl, op->yl, constrained_mask, dot_acc));
    return halo_mult_transpose(op->halo, op->yl, y);
 }
 
@@ -688,9 +703,16 @@ int b2f_operator_mult_unfused(b2f_operator *op, const double *x_l, double *y_l)
    return local_mult_unfused(op, x_l, y_l);
 }
 
-static int mult_constrained(b2f_operator *op, const double *x, double *y, bool lcap)
+// dot_acc != nullptr: additionally leave (x, y) = sum_e z_e.(A_e z_e) + sum_ess x_i^2 in dot_acc
+// (local part; z = x with the constrained entries zeroed)
+static int mult_constrained(b2f_operator *op, const double *x, double *y, bool lcap, double *dot_acc = nullptr)
 {
    b2f_ctx *ctx = op->ctx;
+   if (dot_acc)
+   {
+      B2F_TRY(rap_mult(op, x, y, true, lcap, dot_acc));
+      return copy_entries_sqsum(ctx, y, x, op->ess, op->n_ess, dot_acc);
+   }
    if (op->signed_map && op->n_ess)
    {
       // operator.cpp:601-660 literally: z = x; z[ess] = 0; y = A z; y[ess] = x[ess]
@@ -830,6 +852,23 @@ int b2f_pcg(b2f_operator *op, const double *dinv, const double *b, double *x,
       B2F_CUDA(cudaMemsetAsync(hist, 0, sizeof(double) * history_capacity, ctx->stream));
    }
    auto reduce = [&]() -> int { return halo ? halo_allreduce_sum(halo, pcg_dot_slot(st), 1) : B2F_OK; };
+   // q = A d and (d, q): one fused kernel when every integrator supports it, else two passes
+   const bool fdot = operator_has_fused_dot(op);
+   if (fdot && !op->dot_acc)
+   {
+      B2F_CUDA(cudaMalloc((void **)&op->dot_acc, sizeof(double) * 64));
+      B2F_CUDA(cudaMemsetAsync(op->dot_acc, 0, sizeof(double) * 64, ctx->stream));
+   }
+   auto apply_and_dot = [&]() -> int
+   {
+      if (fdot)
+      {
+         B2F_TRY(mult_constrained(op, d, q, true, op->dot_acc));
+         return collect_dot(ctx, op->dot_acc, pcg_dot_slot(st));
+      }
+      B2F_TRY(mult_constrained(op, d, q, true));
+      return dot_to_device(ctx, n, d, q, pcg_dot_slot(st));
+   };
 
    // r = b; x = 0   (iterative_mode = false, solvers.cpp:881-884)
    B2F_CUDA(cudaMemcpyAsync(r, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -845,8 +884,7 @@ int b2f_pcg(b2f_operator *op, const double *dinv, const double *b, double *x,
    B2F_TRY(reduce());
    B2F_TRY(pcg_after_nom0(ctx, st, opt->rel_tol, opt->abs_tol, opt->max_iter, hist,
                           hist ? history_capacity : 0));
-   B2F_TRY(mult_constrained(op, d, q, true)); // z = A d
-   B2F_TRY(dot_to_device(ctx, n, q, d, pcg_dot_slot(st)));
+   B2F_TRY(apply_and_dot()); // z = A d, den = (z, d)
    B2F_TRY(reduce());
    B2F_TRY(pcg_after_den0(ctx, st));
 
@@ -870,8 +908,7 @@ int b2f_pcg(b2f_operator *op, const double *dinv, const double *b, double *x,
       B2F_TRY(reduce());
       B2F_TRY(pcg_after_betanom(ctx, st, hist, hist ? history_capacity : 0));
       B2F_TRY(pcg_direction(ctx, st, n, zz, d));
-      B2F_TRY(mult_constrained(op, d, q, true));
-      B2F_TRY(dot_to_device(ctx, n, d, q, pcg_dot_slot(st)));
+      B2F_TRY(apply_and_dot());
       B2F_TRY(reduce());
       B2F_TRY(pcg_after_den(ctx, st));
       if (++enq >= check_every) { B2F_TRY(poll()); enq = 0; }

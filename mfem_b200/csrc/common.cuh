@@ -129,12 +129,16 @@ struct b2f_operator
    double *pcg_vec[4] = {nullptr, nullptr, nullptr, nullptr}; // r, d, z, q
    double *pcg_hist = nullptr;
    int pcg_hist_cap = 0;
+   double *dot_acc = nullptr;           // 64 partial sums of the fused (d, A d)
 };
 
 namespace b2f
 {
 // pa_apply_*.cu : E-vector (idx == nullptr) or fused L-vector (idx = gather index, -1 = skip)
-int pa_apply(b2f_pa *pa, const double *x, double *y, const int *idx);
+// dot_acc (64 doubles, or nullptr): also accumulate x . (A x) (fused form only; see
+// pa_has_fused_dot)
+int pa_apply(b2f_pa *pa, const double *x, double *y, const int *idx, double *dot_acc = nullptr);
+bool pa_has_fused_dot(const b2f_pa *pa);
 // pa_diag.cu
 int pa_diag(b2f_pa *pa, double *diag_e);
 // pa_setup.cu
@@ -150,5 +154,9 @@ int setup_from_nodes(b2f_ctx *ctx, int kind, int dim, int q1d, int64_t ne, const
 int fill(b2f_ctx *ctx, double *x, double v, int64_t n);
 int set_entries(b2f_ctx *ctx, double *x, const int *idx, int n, double v);
 int copy_entries(b2f_ctx *ctx, double *dst, const double *src, const int *idx, int n);
+// dst[idx] = src[idx] and acc[0] += sum src[idx]^2
+int copy_entries_sqsum(b2f_ctx *ctx, double *dst, const double *src, const int *idx, int n, double *acc);
+// *out = sum acc[0..63]; acc[] = 0
+int collect_dot(b2f_ctx *ctx, double *acc, double *out);
 int dot_to_device(b2f_ctx *ctx, int64_t n, const double *x, const double *y, double *d_out);
 } // namespace b2f

@@ -2,14 +2,14 @@
 #include "pa_dispatch.cuh"
 namespace b2f
 {
-int pa_apply_3d_diffusion_2(b2f_pa *, const double *, double *, const int *);
-int pa_apply_3d_diffusion_6(b2f_pa *, const double *, double *, const int *);
-int pa_apply_3d_diffusion_8(b2f_pa *, const double *, double *, const int *);
-int pa_apply_3d_mass_2(b2f_pa *, const double *, double *, const int *);
-int pa_apply_3d_mass_6(b2f_pa *, const double *, double *, const int *);
-int pa_apply_3d_mass_8(b2f_pa *, const double *, double *, const int *);
+int pa_apply_3d_diffusion_2(b2f_pa *, const double *, double *, const int *, double *);
+int pa_apply_3d_diffusion_6(b2f_pa *, const double *, double *, const int *, double *);
+int pa_apply_3d_diffusion_8(b2f_pa *, const double *, double *, const int *, double *);
+int pa_apply_3d_mass_2(b2f_pa *, const double *, double *, const int *, double *);
+int pa_apply_3d_mass_6(b2f_pa *, const double *, double *, const int *, double *);
+int pa_apply_3d_mass_8(b2f_pa *, const double *, double *, const int *, double *);
 
-int pa_apply(b2f_pa *pa, const double *x, double *y, const int *idx)
+int pa_apply(b2f_pa *pa, const double *x, double *y, const int *idx, double *dot_acc)
 {
    if (pa->ne == 0) { return B2F_OK; }
    if (!pa->symmetric)
@@ -17,16 +17,22 @@ int pa_apply(b2f_pa *pa, const double *x, double *y, const int *idx)
       set_error("non-symmetric matrix coefficients have no apply kernel yet");
       return B2F_ERR_UNSUPPORTED;
    }
+   if (dot_acc && !pa_apply_has_fused_dot(pa))
+   {
+      set_error("pa_apply: fused dot not available for this integrator");
+      return B2F_ERR_UNSUPPORTED;
+   }
    if (pa->dim == 2) { return pa_apply_2d(pa, x, y, idx); }
    const int d = pa->d1d;
    if (pa->kind == B2F_KIND_DIFFUSION)
    {
-      return d <= 5 ? pa_apply_3d_diffusion_2(pa, x, y, idx)
-             : d <= 7 ? pa_apply_3d_diffusion_6(pa, x, y, idx)
-             : pa_apply_3d_diffusion_8(pa, x, y, idx);
+      return d <= 5 ? pa_apply_3d_diffusion_2(pa, x, y, idx, dot_acc)
+             : d <= 7 ? pa_apply_3d_diffusion_6(pa, x, y, idx, dot_acc)
+             : pa_apply_3d_diffusion_8(pa, x, y, idx, dot_acc);
    }
-   return d <= 5 ? pa_apply_3d_mass_2(pa, x, y, idx)
-          : d <= 7 ? pa_apply_3d_mass_6(pa, x, y, idx)
-          : pa_apply_3d_mass_8(pa, x, y, idx);
+   return d <= 5 ? pa_apply_3d_mass_2(pa, x, y, idx, dot_acc)
+          : d <= 7 ? pa_apply_3d_mass_6(pa, x, y, idx, dot_acc)
+          : pa_apply_3d_mass_8(pa, x, y, idx, dot_acc);
 }
+bool pa_has_fused_dot(const b2f_pa *pa) { return pa_apply_has_fused_dot(pa); }
 } // namespace b2f

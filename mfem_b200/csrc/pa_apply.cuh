@@ -27,6 +27,7 @@
 //  * FUSED: x is gathered straight into registers (index -1 = essential dof: reads 0 and
 //    is not scattered), y is scattered with FP64 atomics (RED.ADD.F64 in L2).
 #pragma once
+#include <map>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -767,7 +768,10 @@ int launch_3d(b2f_pa *pa, const double *x, double *y, const int *idx)
       // once per instantiation: opt in to the shared memory size and find how many CTAs are
       // resident on the device -- that is the L2 prefetch distance (the slab a CTA prefetches
       // belongs to the CTA that takes over its slot)
-      static int resident = 0;
+      // (keyed by the kernel's address: instantiations that differ only in bool template
+      // arguments share one function-pointer type, hence one lambda specialisation)
+      static std::map<const void *, int> cache;
+      int &resident = cache[(const void *)kern];
       if (resident == 0)
       {
          B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));

@@ -10,7 +10,7 @@ static int variant()
    return s ? atoi(s) : 0;
 }
 
-int pa_apply_3d_diffusion_2(b2f_pa *pa, const double *x, double *y, const int *idx)
+int pa_apply_3d_diffusion_2(b2f_pa *pa, const double *x, double *y, const int *idx, double *dot_acc)
 {
    if (pa->d1d == 5 && pa->q1d == 6 && idx)
    {

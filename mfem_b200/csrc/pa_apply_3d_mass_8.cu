@@ -2,7 +2,7 @@
 #include "pa_dispatch.cuh"
 namespace b2f
 {
-int pa_apply_3d_mass_8(b2f_pa *pa, const double *x, double *y, const int *idx)
+int pa_apply_3d_mass_8(b2f_pa *pa, const double *x, double *y, const int *idx, double *dot_acc)
 {
    switch (pa->d1d * 100 + pa->q1d)
    {

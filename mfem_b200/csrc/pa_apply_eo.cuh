@@ -25,6 +25,7 @@
 // this SM slot (`pf` blocks ahead).  Requires the symmetry above (checked on the host when
 // the integrator is set up; otherwise pa_apply.cuh's general kernel runs).
 #pragma once
+#include <map>
 #include "pa_apply_pipe.cuh"
 
 namespace b2f
@@ -127,7 +128,7 @@ __device__ __forceinline__ void zero(double (&v)[N])
 }
 
 // ---- the five stages as device functions (shared by the one-shot and persistent kernels) ----
-template <int KIND, int D, int Q, int NEB, bool COLLOC>
+template <int KIND, int D, int Q, int NEB, bool COLLOC, bool WITH_ENERGY = false>
 struct EOStages
 {
    using C = PipeCfg<KIND, D, Q, NEB>;
@@ -198,10 +199,12 @@ struct EOStages
       }
    }
 
-   // stage 3 (x, D, x^T) in place: line t3 = (yq, qz)
-   static __device__ __forceinline__ void stage3(const BS &bs, double *r2, const double *qd, int t,
-                                                 uint64_t *bar, uint32_t parity)
+   // stage 3 (x, D, x^T) in place: line t3 = (yq, qz).  Returns this line's share of the
+   // energy x.(Ax) = sum_q (grad u)^T D (grad u)  (mass: sum_q u D u), free at this point
+   static __device__ __forceinline__ double stage3(const BS &bs, double *r2, const double *qd, int t,
+                                                   uint64_t *bar, uint32_t parity)
    {
+      double energy = 0.0;
       const int yq = t % YQ, qz = t / YQ;
       const int e = yq / Q, qy = yq - e * Q;
       double *C0 = r2 + yq + YQ * qz;
@@ -267,6 +270,7 @@ struct EOStages
             gx[qx] = (O11 * ux) + (O12 * uy) + (O13 * uz);
             gy[qx] = (O12 * ux) + (O22 * uy) + (O23 * uz);
             gz[qx] = (O13 * ux) + (O23 * uy) + (O33 * uz);
+            if (WITH_ENERGY) { energy = fma(ux, gx[qx], fma(uy, gy[qx], fma(uz, gz[qx], energy))); }
          }
       }
       else
@@ -279,7 +283,12 @@ struct EOStages
             for (int qx = 0; qx < Q; qx++) { dv[qx] = dq[qx]; }
          }
 #pragma unroll
-         for (int qx = 0; qx < Q; qx++) { gx[qx] *= dv[qx]; }
+         for (int qx = 0; qx < Q; qx++)
+         {
+            const double ux = gx[qx];
+            gx[qx] *= dv[qx];
+            if (WITH_ENERGY) { energy = fma(ux, gx[qx], energy); }
+         }
       }
       // x^T, written over this thread's own input column
       {
@@ -329,6 +338,7 @@ struct EOStages
             for (int dx = 0; dx < D; dx++) { C0[C::SC * (2 * D + dx)] = o[dx]; }
          }
       }
+      return energy;
    }
 
    // stage 4 (z^T): line t2 = (yq, dx)
@@ -442,14 +452,19 @@ __device__ __forceinline__ void eo_line_coords(int t, int &e1, int &dx1, int &dz
 }
 
 // ---- one tile per CTA; next CTA's slab prefetched into L2 --------------------------------------
-template <int KIND, int D, int Q, int NEB, bool FUSED, bool COLLOC, int MINB>
+// DOT: additionally accumulate x . (A x) into dot_acc[64] -- the PCG's (d, A d) without another
+// pass over the vectors (IterativeSolver::Dot, linalg/solvers.cpp:58).  It is evaluated as the
+// energy sum_q (grad x)^T D (grad x) at the quadrature points, where both factors are in
+// registers anyway (3 FMAs per point); absent elements of a ragged tile contribute nothing.
+template <int KIND, int D, int Q, int NEB, bool FUSED, bool COLLOC, int MINB, bool DOT = false>
 __global__ void __launch_bounds__(PipeCfg<KIND, D, Q, NEB>::NT, MINB)
 pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__restrict__ qdata,
                       const double *__restrict__ x, double *__restrict__ y,
-                      const int *__restrict__ idx, const int64_t ne, const int pf)
+                      const int *__restrict__ idx, const int64_t ne, const int pf,
+                      double *__restrict__ dot_acc)
 {
    using C = PipeCfg<KIND, D, Q, NEB>;
-   using S = EOStages<KIND, D, Q, NEB, COLLOC>;
+   using S = EOStages<KIND, D, Q, NEB, COLLOC, DOT>;
    constexpr int D2 = C::D2, D3 = C::D3, Q3 = C::Q3, YQ = C::YQ;
    extern __shared__ __align__(16) unsigned char smem_raw[];
    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
@@ -529,7 +544,20 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
    if (t < C::T2) { S::stage2(bs, r1, r2, t); }
    if constexpr (!C::TMA_OK) { cp_async_wait_all(); }
    __syncthreads();
-   if (t < C::T3) { S::stage3(bs, r2, qd, t, bar, 0); }
+   {
+      double part = 0.0;
+      if (t < C::T3)
+      {
+         part = S::stage3(bs, r2, qd, t, bar, 0);
+         if ((t % C::YQ) / Q >= nev) { part = 0.0; } // lines of a ragged tile: absent elements
+      }
+      if constexpr (DOT)
+      {
+#pragma unroll
+         for (int o = 16; o > 0; o >>= 1) { part += __shfl_xor_sync(0xffffffffu, part, o); }
+         if ((t & 31) == 0) { atomicAdd(dot_acc + ((blockIdx.x + (t >> 5)) & 63), part); }
+      }
+   }
    __syncthreads();
    if (t < C::T2) { S::stage4(bs, r2, r1, t); }
    __syncthreads();
@@ -739,7 +767,7 @@ inline bool fill_eo_basis(const b2f_pa *pa, EOBasis<D, Q> &bs)
 }
 
 template <int KIND, int D, int Q, int NEB, int MINB = 1, int FUSEDSEL = 1, bool PERSIST = false>
-int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx)
+int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx, double *dot_acc = nullptr)
 {
    using C = PipeCfg<KIND, D, Q, NEB>;
    b2f_ctx *ctx = pa->ctx;
@@ -757,7 +785,10 @@ int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx)
    int64_t grid = cdiv(pa->ne, NEB);
    auto go = [&](auto kern) -> int
    {
-      static int resident = 0;
+      // (keyed by the kernel's address: instantiations that differ only in bool template
+      // arguments share one function-pointer type, hence one lambda specialisation)
+      static std::map<const void *, int> cache;
+      int &resident = cache[(const void *)kern];
       if (resident == 0)
       {
          B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
@@ -769,13 +800,14 @@ int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx)
       const int pf = pfs ? atoi(pfs) : resident;
       if (PERSIST && grid > resident) { grid = resident; }
       timing_mark(ctx);
-      kern<<<(unsigned)grid, C::NT, C::SMEM, ctx->stream>>>(bs, pa->data, x, y, idx, pa->ne, pf);
+      if constexpr (PERSIST) { kern<<<(unsigned)grid, C::NT, C::SMEM, ctx->stream>>>(bs, pa->data, x, y, idx, pa->ne, pf); }
+      else { kern<<<(unsigned)grid, C::NT, C::SMEM, ctx->stream>>>(bs, pa->data, x, y, idx, pa->ne, pf, dot_acc); }
       timing_mark(ctx);
       B2F_LAUNCH_CHECK(ctx);
       return B2F_OK;
    };
    const bool fused = idx != nullptr;
-   if ((fused && FUSEDSEL == 0) || (!fused && FUSEDSEL == 1))
+   if ((fused && FUSEDSEL == 0) || (!fused && FUSEDSEL == 1) || (dot_acc && (!fused || PERSIST)))
    {
       set_error("pa_apply_3d_eo: kernel form not instantiated");
       return B2F_ERR_UNSUPPORTED;
@@ -795,10 +827,18 @@ int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx)
    {
       if (pa->collocated && CL)
       {
-         if constexpr (FUSEDSEL != 0) { if (fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, CL, MINB>); } }
+         if constexpr (FUSEDSEL != 0)
+         {
+            if (fused && dot_acc) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, CL, MINB, true>); }
+            if (fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, CL, MINB>); }
+         }
          if constexpr (FUSEDSEL != 1) { if (!fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, CL, MINB>); } }
       }
-      if constexpr (FUSEDSEL != 0) { if (fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, false, MINB>); } }
+      if constexpr (FUSEDSEL != 0)
+      {
+         if (fused && dot_acc) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, false, MINB, true>); }
+         if (fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, false, MINB>); }
+      }
       if constexpr (FUSEDSEL != 1) { if (!fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, false, MINB>); } }
    }
    return B2F_ERR_UNSUPPORTED;

@@ -66,7 +66,7 @@ constexpr int neb_2d(int kind, int D, int Q)
 
 #define B2F_CASE_3D(KIND, D_, Q_)                                                      \
    case (D_) * 100 + (Q_):                                                             \
-      return run_3d<KIND, D_, Q_>(pa, x, y, idx);
+      return run_3d<KIND, D_, Q_>(pa, x, y, idx, dot_acc);
 #define B2F_CASE_2D(KIND, D_, Q_)                                                      \
    case (D_) * 100 + (Q_):                                                             \
       return launch_2d<KIND, D_, Q_, neb_2d(KIND, D_, Q_)>(pa, x, y, idx);
@@ -113,6 +113,16 @@ constexpr int tuned_cand_eo(int kind, int D, int Q)
    return D <= 4 ? 1 : 0;
 }
 
+// the even-odd kernel (and with it the fused x.(Ax) accumulation) runs for 3D integrators with
+// a symmetric basis and a (D,Q) in the dispatch tables
+inline bool basis_is_symmetric(const b2f_pa *pa);
+inline bool pa_apply_has_fused_dot(const b2f_pa *pa)
+{
+   const int D = pa->d1d, Q = pa->q1d;
+   return pa->dim == 3 && pa->symmetric && D >= 2 && D <= 9 && Q >= D && Q <= D + 2 &&
+          basis_is_symmetric(pa) && !getenv("B2F_GENERAL_KERNEL");
+}
+
 inline bool basis_is_symmetric(const b2f_pa *pa)
 {
    const int D = pa->d1d, Q = pa->q1d;
@@ -134,10 +144,11 @@ inline bool basis_is_symmetric(const b2f_pa *pa)
 // for experiments -- and the E-vector form (AddMultPA seam) with one.  A basis without the
 // symmetry falls back to the general pencil kernel of pa_apply.cuh.
 template <int KIND, int D, int Q>
-int run_3d(b2f_pa *pa, const double *x, double *y, const int *idx)
+int run_3d(b2f_pa *pa, const double *x, double *y, const int *idx, double *dot_acc)
 {
-   if (!basis_is_symmetric(pa) || getenv("B2F_GENERAL_KERNEL"))
+   if (!pa_apply_has_fused_dot(pa))
    {
+      if (dot_acc) { set_error("pa_apply: fused dot not available for this integrator"); return B2F_ERR_UNSUPPORTED; }
       constexpr int NG = neb_3d(KIND, D, Q, 1);
       return launch_3d<KIND, D, Q, NG, 1, 1, 2>(pa, x, y, idx);
    }
@@ -147,13 +158,13 @@ int run_3d(b2f_pa *pa, const double *x, double *y, const int *idx)
    const int cand = s ? atoi(s) : tuned_cand_eo(KIND, D, Q);
    if (cand == 0 || (cand == 1 && N1 == N0) || (cand == 2 && N2 == N0))
    {
-      return launch_3d_eo<KIND, D, Q, N0, minb_eo(KIND, D, Q, N0), 1>(pa, x, y, idx);
+      return launch_3d_eo<KIND, D, Q, N0, minb_eo(KIND, D, Q, N0), 1>(pa, x, y, idx, dot_acc);
    }
    if (cand == 1 || (cand == 2 && N2 == N1))
    {
-      if constexpr (N1 != N0) { return launch_3d_eo<KIND, D, Q, N1, minb_eo(KIND, D, Q, N1), 1>(pa, x, y, idx); }
+      if constexpr (N1 != N0) { return launch_3d_eo<KIND, D, Q, N1, minb_eo(KIND, D, Q, N1), 1>(pa, x, y, idx, dot_acc); }
    }
-   if constexpr (N2 != N1 && N2 != N0) { return launch_3d_eo<KIND, D, Q, N2, minb_eo(KIND, D, Q, N2), 1>(pa, x, y, idx); }
+   if constexpr (N2 != N1 && N2 != N0) { return launch_3d_eo<KIND, D, Q, N2, minb_eo(KIND, D, Q, N2), 1>(pa, x, y, idx, dot_acc); }
    return B2F_ERR_UNSUPPORTED;
 }
 

@@ -47,6 +47,29 @@ __global__ void copy_entries_kernel(double *dst, const double *__restrict__ src,
    if (i < n) { const int k = idx[i]; dst[k] = src[k]; }
 }
 
+__global__ void __launch_bounds__(256)
+copy_entries_sqsum_kernel(double *dst, const double *__restrict__ src, const int *__restrict__ idx,
+                          int n, double *acc)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   double v = 0.0;
+   if (i < n) { const int k = idx[i]; v = src[k]; dst[k] = v; }
+   v *= v;
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); }
+   if ((threadIdx.x & 31) == 0 && v != 0.0) { atomicAdd(acc + (blockIdx.x & 63), v); }
+}
+
+__global__ void collect_dot_kernel(double *acc, double *out)
+{
+   double v = acc[threadIdx.x] + acc[threadIdx.x + 32];
+   acc[threadIdx.x] = 0.0;
+   acc[threadIdx.x + 32] = 0.0;
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); }
+   if (threadIdx.x == 0) { *out = v; }
+}
+
 __global__ void __launch_bounds__(VT)
 add_kernel(int64_t n, const double *__restrict__ x, double a, const double *__restrict__ y,
            double *z)
@@ -255,6 +278,21 @@ int copy_entries(b2f_ctx *ctx, double *dst, const double *src, const int *idx, i
 {
    if (n == 0) { return B2F_OK; }
    copy_entries_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(dst, src, idx, n);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+int copy_entries_sqsum(b2f_ctx *ctx, double *dst, const double *src, const int *idx, int n, double *acc)
+{
+   if (n == 0) { return B2F_OK; }
+   copy_entries_sqsum_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(dst, src, idx, n, acc);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+int collect_dot(b2f_ctx *ctx, double *acc, double *out)
+{
+   collect_dot_kernel<<<1, 32, 0, ctx->stream>>>(acc, out);
    B2F_LAUNCH_CHECK(ctx);
    return B2F_OK;
 }

@@ -222,6 +222,33 @@ def test_constrained_operator_jacobi_and_pcg(dev, golden):
     a.close(); it.close(); R.close()
 
 
+@pytest.mark.parametrize("name", ["diff3d_p4_n3", "mass3d_p4_n2", "bp5_3d_p7_n2", "diff3d_p8_n2",
+                                  "diff3d_p3_n2_curved"])
+def test_pcg_with_fused_energy_dot(dev, name, monkeypatch):
+    """(d, A d) accumulated inside the operator kernel as the quadrature-point energy
+    (B2F_FUSED_DOT=1) gives the same PCG as the two-kernel form."""
+    import mfem_b200 as m
+    g = load_golden(name)
+    a, it, R = make_form(dev, g, ess=True)
+    ndofs, ess = R.ndofs, g["ess_tdof_list"]
+    A, _, B = a.FormLinearSystem(ess, dev.zeros(ndofs), dev.to_device(g["b"]))
+    M = m.OperatorJacobiSmoother(a, ess)
+    sols = []
+    for fused in (False, True):
+        if fused:
+            monkeypatch.setenv("B2F_FUSED_DOT", "1")
+        cg = m.CGSolver()
+        cg.SetRelTol(float(g["pcg_rtol"][0])); cg.SetMaxIter(2000); cg.SetOperator(A); cg.SetPreconditioner(M)
+        X = dev.zeros(ndofs)
+        cg.Mult(B, X, record_history=True)
+        sols.append((cg.GetNumIterations(), host(X), cg.history.copy()))
+    assert abs(sols[1][0] - int(g["pcg_iters"][0])) <= 1 and abs(sols[1][0] - sols[0][0]) <= 1
+    assert relerr(sols[1][1], sols[0][1]) < 1e-9
+    n = min(len(sols[0][2]), len(sols[1][2]))
+    assert np.allclose(sols[1][2][:n], sols[0][2][:n], rtol=1e-8)
+    a.close(); it.close(); R.close()
+
+
 def test_vector_dot_and_add(dev):
     import mfem_b200 as m
     from mfem_b200.capi import call, vp
