@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--iters", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=None, help="elements per side of the CPU sample")
+    ap.add_argument("--curved", type=int, default=None,
+                    help="1: order-3 nodes displaced by the smooth map of BASELINE config C5 (default for --bp 5)")
     return ap.parse_args()
 
 
@@ -65,7 +67,8 @@ def workload(a):
     grid = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[a.gpus]
     kind = {1: "mass", 3: "diffusion", 5: "diffusion"}[a.bp]
     q = p + 1 if a.bp == 5 else p + 2
-    return dict(bp=a.bp, p=p, n=n, grid=grid, kind=kind, q1d=q, d1d=p + 1, gll=(a.bp == 5))
+    curved = bool(a.curved) if a.curved is not None else a.bp == 5
+    return dict(bp=a.bp, p=p, n=n, grid=grid, kind=kind, q1d=q, d1d=p + 1, gll=(a.bp == 5), curved=curved)
 
 
 def alg_bytes_per_apply(w, ne, nd):
@@ -130,7 +133,8 @@ def run_reference(w, n_cpu, iters, reps):
     if drv:
         env = dict(os.environ, MFEM_DEVICE="omp", OMP_NUM_THREADS=str(cores), OMP_PROC_BIND="true")
         cmd = [drv, "bench", "--mode", "pcg", "--dim", "3", "--n", str(n_cpu), "--p", str(w["p"]),
-               "--kind", w["kind"], "--quad", "gll" if w["gll"] else "gl", "--iters", str(iters),
+               "--kind", w["kind"], "--quad", "gll" if w["gll"] else "gl", "--curved", str(int(w["curved"])),
+               "--iters", str(iters),
                "--reps", str(reps), "--jacobi", "1"]
         out = subprocess.run(cmd, check=True, stdout=subprocess.PIPE, env=env).stdout.decode()
         r = json.loads(out.strip().splitlines()[-1])
@@ -231,6 +235,9 @@ def main():
         mesh = m.Mesh(3, n * px, n * py, n * pz, True, part=(px, py, pz), rank=rank)
     else:
         mesh = m.Mesh.MakeCartesian3D(n, n, n)
+    if w["curved"]:
+        mesh.SetCurvature(3)
+        mesh.Transform(m.curve_map)
     fes = m.FiniteElementSpace(mesh, m.H1_FECollection(p, 3))
     rules = m.IntegrationRules(gll=w["gll"])
     ir = rules.Get(3, 2 * p - 1 if w["gll"] else 2 * p + 3)
@@ -341,7 +348,7 @@ def main():
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"BP{w['bp']} {w['kind']} PA + PCG/Jacobi, p={p}, Q1D={w['q1d']}, "
-                                   f"{n}^3 hexes per GPU on a {px}x{py}x{pz} grid, {nglob} dofs, "
+                                   f"{n}^3 hexes per GPU{' (curved, Q3 nodes)' if w['curved'] else ''} on a {px}x{py}x{pz} grid, {nglob} dofs, "
                                    f"{a.iters} fixed CG iterations per step",
                        "dofs_global": nglob, "dofs_per_gpu": nglob // a.gpus, "elements_per_gpu": fes.ne,
                        "cg_iterations_per_step": a.iters, "l2": "inputs (quadrature data, "
