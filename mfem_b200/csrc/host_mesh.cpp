@@ -235,7 +235,11 @@ struct H1Space
 
 // H1 numbering of a conforming quad/hex mesh given element -> vertex lists (reference
 // vertex order), for any element ordering.
-void h1_number(int dim, int p, int nverts, const std::vector<int> &elem_vert, H1Space &S)
+// `vstride` (optional): vertex-id strides {1, sy, sz} of a structured grid.  With it edges and
+// faces are looked up by direct addressing (slot = 3*lowest vertex + direction) instead of
+// hashing -- same first-encounter numbering, several times faster on 10^6..10^8 elements.
+void h1_number(int dim, int p, int nverts, const std::vector<int> &elem_vert, H1Space &S,
+               const int *vstride = nullptr)
 {
    const int nv = dim == 2 ? 4 : 8, nedge = dim == 2 ? 4 : 12, nface = dim == 2 ? 0 : 6;
    const int ne = (int)(elem_vert.size() / nv);
@@ -243,8 +247,11 @@ void h1_number(int dim, int p, int nverts, const std::vector<int> &elem_vert, H1
    const int dof = dim == 2 ? (p + 1) * (p + 1) : (p + 1) * (p + 1) * (p + 1);
    // --- edges: first-encounter numbering
    std::unordered_map<uint64_t, int, PairHash> edge_id;
-   edge_id.reserve((size_t)ne * 4);
+   std::vector<int> edge_slot; // direct table: 3*min vertex + direction
+   if (vstride) { edge_slot.assign((size_t)3 * nverts, -1); }
+   else { edge_id.reserve((size_t)ne * 4); }
    std::vector<int> el_edge((size_t)ne * nedge);
+   int nedges = 0;
    for (int e = 0; e < ne; e++)
    {
       const int *v = &elem_vert[(size_t)e * nv];
@@ -253,15 +260,25 @@ void h1_number(int dim, int p, int nverts, const std::vector<int> &elem_vert, H1
          const int *ev = dim == 2 ? kQuadEdge[j] : kHexEdge[j];
          int a = v[ev[0]], b = v[ev[1]];
          if (a > b) { std::swap(a, b); }
-         const uint64_t key = ((uint64_t)(uint32_t)a << 32) | (uint32_t)b;
-         auto it = edge_id.find(key);
          int id;
-         if (it == edge_id.end()) { id = (int)edge_id.size(); edge_id.emplace(key, id); }
-         else { id = it->second; }
+         if (vstride)
+         {
+            const int d = b - a;
+            int &slot = edge_slot[(size_t)3 * a + (d == vstride[0] ? 0 : d == vstride[1] ? 1 : 2)];
+            if (slot < 0) { slot = nedges++; }
+            id = slot;
+         }
+         else
+         {
+            const uint64_t key = ((uint64_t)(uint32_t)a << 32) | (uint32_t)b;
+            auto it = edge_id.find(key);
+            if (it == edge_id.end()) { id = nedges++; edge_id.emplace(key, id); }
+            else { id = it->second; }
+         }
          el_edge[(size_t)e * nedge + j] = id;
       }
    }
-   const int nedges = (int)edge_id.size();
+   std::vector<int>().swap(edge_slot);
    // edge -> number of incident elements is not needed; boundary comes from faces (3D) or
    // from edges with a single element (2D)
    std::vector<int> edge_count;
@@ -277,7 +294,9 @@ void h1_number(int dim, int p, int nverts, const std::vector<int> &elem_vert, H1
    if (dim == 3)
    {
       std::unordered_map<FaceKey, int, FaceHash> face_id;
-      face_id.reserve((size_t)ne * 3 + 16);
+      std::vector<int> face_slot; // direct table: 3*min vertex + normal direction
+      if (vstride) { face_slot.assign((size_t)3 * nverts, -1); }
+      else { face_id.reserve((size_t)ne * 3 + 16); }
       el_face.resize((size_t)ne * 6);
       for (int e = 0; e < ne; e++)
       {
@@ -288,21 +307,36 @@ void h1_number(int dim, int p, int nverts, const std::vector<int> &elem_vert, H1
                                      v[kHexFace[j][3]]};
             std::array<int, 4> s = fv;
             std::sort(s.begin(), s.end());
-            const FaceKey key{s[0], s[1], s[2]};
-            auto it = face_id.find(key);
             int id;
-            if (it == face_id.end())
+            bool fresh;
+            if (vstride)
             {
-               id = (int)face_id.size();
-               face_id.emplace(key, id);
+               // the two smallest offsets from the lowest vertex tell the face's normal
+               const int d1 = s[1] - s[0];
+               const int nrm = d1 == vstride[1] ? 0 : (s[2] - s[0] == vstride[2] ? 1 : 2);
+               int &slot = face_slot[(size_t)3 * s[0] + nrm];
+               fresh = slot < 0;
+               if (fresh) { slot = nfaces; }
+               id = slot;
+            }
+            else
+            {
+               const FaceKey key{s[0], s[1], s[2]};
+               auto it = face_id.find(key);
+               fresh = it == face_id.end();
+               if (fresh) { id = nfaces; face_id.emplace(key, id); }
+               else { id = it->second; }
+            }
+            if (fresh)
+            {
+               nfaces++;
                face_base.push_back(fv);
                face_count.push_back(1);
             }
-            else { id = it->second; face_count[id]++; }
+            else { face_count[id]++; }
             el_face[(size_t)e * 6 + j] = id;
          }
       }
-      nfaces = (int)face_id.size();
    }
    // --- dof layout
    const int nvdofs = nverts;
@@ -458,7 +492,8 @@ extern "C" int b2f_cartesian_h1_space_h(int dim, int nx, int ny, int nz, int p, 
    }
    if (!elem_dof_h && !bdr_dofs_h && !nbdr) { return B2F_OK; }
    H1Space S;
-   h1_number(dim, p, nverts, ev, S);
+   const int vstride[3] = {1, nx + 1, (nx + 1) * (ny + 1)};
+   h1_number(dim, p, nverts, ev, S, vstride);
    if (S.ndofs != *ndofs)
    {
       set_error("b2f_cartesian_h1_space_h: internal dof count mismatch (%d vs %d)", S.ndofs, *ndofs);
