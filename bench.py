@@ -343,6 +343,16 @@ def main():
         ab = alg_bytes_per_apply(w, fes.ne, fes.ndofs)
         k_ms = kt[0] / max(kt[1], 1)
         achieved = ab / (k_ms * 1e-3) / 1e9
+        # DRAM traffic of the operator kernel from the committed ncu capture of this workload
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "operator_traffic.json")) as f:
+                tj = json.load(f)
+            key = f"bp{w['bp']}_p{p}_n{n}"
+            if key in tj:
+                traffic = tj[key]["dram_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": "GDOF/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
@@ -358,7 +368,7 @@ def main():
                     "d2h_bytes_per_step": nt * 8 * a.gpus, "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": traffic,
                          "kernel": "pa_apply_3d_eo_kernel (fused gather + even-odd G^T D G + scatter)",
                          "kernel_ms": k_ms, "kernel_launches": kt[1],
                          "kernel_share_of_step": kt[0] / ms,
