@@ -362,3 +362,130 @@ def test_large_properties(dev, kind, p, n):
     else:
         assert float(torch.linalg.norm(az)) < 1e-10 * nrm  # constants are in the kernel
     a.close(); it.close()
+
+
+# ---- edge cases and error behaviour ---------------------------------------------------------
+def test_empty_mesh_and_bad_arguments(dev):
+    import ctypes as C
+    import mfem_b200 as m
+    from mfem_b200.capi import B2FError, call, vp, lib
+    g = load_golden("diff3d_p2_n3")
+    dim, D1D, Q1D, NE, ndofs, _ = meta(g)
+    # zero elements: every entry point is a no-op that succeeds
+    R0 = m.ElementRestriction.from_tables(dev, 0, D1D ** 3, 0, np.zeros(0, np.int32), np.zeros(1, np.int32),
+                                          np.zeros(0, np.int32))
+    it0 = m.DiffusionIntegrator()
+    it0.assemble_from_factors(dev, 3, D1D, Q1D, 0, g["B"], g["G"], g["W"], J=np.zeros(0), detJ=np.zeros(0))
+    e = dev.zeros(1)
+    R0.Mult(e, e); it0.AddMultPA(e, e); it0.AssembleDiagonalPA(e)
+    dev.sync()
+    R0.close(); it0.close()
+    # (D1D, Q1D) outside the tables -> B2F_ERR_UNSUPPORTED, nothing launched, context still usable
+    it = m.DiffusionIntegrator()
+    nq = 7
+    qp, qw = m.gauss_legendre(nq)
+    B, G = m.h1_dof_to_quad(2, qp)
+    J = np.ascontiguousarray(np.tile(np.repeat(np.eye(3).reshape(9), nq ** 3), 2))
+    it.assemble_from_factors(dev, 3, 3, nq, 2, B, G, m.tensor_weights(3, qw), J=J)
+    xe, ye = dev.zeros(2 * 27), dev.zeros(2 * 27)
+    with pytest.raises(B2FError) as ei:
+        it.AddMultPA(xe, ye)
+    assert ei.value.code == 3
+    it.close()
+    # aliasing x and y is refused, NULL handles are refused
+    a, it2, R = make_form(dev, g)
+    x = dev.to_device(g["x"])
+    with pytest.raises(B2FError) as ei:
+        a.Mult(x, x)
+    assert ei.value.code == 1
+    assert lib().b2f_operator_mult(None, None, None) == 1
+    # essential dof out of range
+    with pytest.raises(B2FError):
+        a._make_op(np.array([ndofs + 5], np.int32))
+    # the context survived all of it
+    y = dev.empty(ndofs)
+    a._make_op(np.zeros(0, np.int32))
+    a.Mult(x, y)
+    assert relerr(host(y), g["y"]) < TOL
+    a.close(); it2.close(); R.close()
+
+
+def test_non_symmetric_basis_uses_the_general_kernel(dev):
+    """A basis without the even-odd symmetry (perturbed B) must still give B^T D B exactly:
+    the dispatcher falls back to the general pencil kernel."""
+    import mfem_b200 as m
+    from oracle import oracle as orc
+    g = load_golden("mass3d_p4_n2")
+    dim, D1D, Q1D, NE, ndofs, _ = meta(g)
+    B = g["B"].copy()
+    B[3] += 0.01  # breaks B[Q-1-q][D-1-d] == B[q][d]
+    it = m.MassIntegrator()
+    it.assemble_from_factors(dev, dim, D1D, Q1D, NE, B, None, g["W"], detJ=g["detJ"])
+    xe = dev.to_device(g["xE"])
+    ye = dev.zeros(xe.numel())
+    it.AddMultPA(xe, ye)
+    ref = orc.mass_apply(dim, D1D, Q1D, NE, B, g["pa_data"], g["xE"])
+    assert relerr(host(ye), ref) < TOL
+    R = m.ElementRestriction.from_tables(dev, NE, D1D ** 3, ndofs, g["gather_map"], g["offsets"], g["indices"])
+
+    class _Fes:
+        pass
+    fes = _Fes()
+    fes.ne, fes.dof, fes.ndofs = NE, D1D ** 3, ndofs
+    fes.GetElementRestriction = lambda d: R
+    a = m.BilinearForm(dev, fes)
+    a.AddDomainIntegrator(it)
+    a.Assemble()
+    y = dev.empty(ndofs)
+    a.Mult(dev.to_device(g["x"]), y)
+    yref = orc.restriction_mult_transpose(ndofs, D1D ** 3, g["offsets"], g["indices"],
+                                          orc.mass_apply(dim, D1D, Q1D, NE, B, g["pa_data"], g["xE"]))
+    assert relerr(host(y), yref) < TOL
+    a.close(); it.close(); R.close()
+
+
+@pytest.mark.parametrize("ne", [1, 2, 4, 5, 7, 31])
+def test_ragged_tiles(dev, ne):
+    """Element counts that are not a multiple of the elements-per-CTA tile."""
+    import mfem_b200 as m
+    from oracle import oracle as orc
+    g = load_golden("diff3d_p4_n3")
+    dim, D1D, Q1D, NE, ndofs, _ = meta(g)
+    dof, nq = D1D ** 3, Q1D ** 3
+    sel = np.arange(ne) % NE
+    J = g["J"].reshape(NE, 9 * nq)[sel].reshape(-1)
+    it = m.DiffusionIntegrator()
+    it.assemble_from_factors(dev, dim, D1D, Q1D, ne, g["B"], g["G"], g["W"], J=J)
+    xE = orc.randomize(ne * dof, 9)
+    xe = dev.to_device(xE)
+    ye = dev.zeros(ne * dof)
+    it.AddMultPA(xe, ye)
+    D = orc.diffusion_setup(dim, Q1D, 1, ne, g["W"], J, [1.0])
+    assert np.array_equal(it.pa_data(), D)
+    ref = orc.diffusion_apply(dim, D1D, Q1D, ne, g["B"], g["G"], D, xE)
+    assert relerr(host(ye), ref) < TOL
+    # fused form on a gather map that sends every element to its own dofs plus a shared block
+    gmap = (np.arange(ne * dof) % (ne * dof - 7)).astype(np.int32)
+    nd = ne * dof - 7
+    order = np.argsort(gmap, kind="stable")
+    off = np.zeros(nd + 1, np.int32)
+    np.add.at(off, gmap + 1, 1)
+    off = np.cumsum(off).astype(np.int32)
+    ind = order.astype(np.int32)
+    R = m.ElementRestriction.from_tables(dev, ne, dof, nd, gmap, off, ind)
+
+    class _Fes:
+        pass
+    fes = _Fes()
+    fes.ne, fes.dof, fes.ndofs = ne, dof, nd
+    fes.GetElementRestriction = lambda d: R
+    a = m.BilinearForm(dev, fes)
+    a.AddDomainIntegrator(it)
+    a.Assemble()
+    xl = orc.randomize(nd, 4)
+    y = dev.empty(nd)
+    a.Mult(dev.to_device(xl), y)
+    yE = orc.diffusion_apply(dim, D1D, Q1D, ne, g["B"], g["G"], D, xl[gmap])
+    yref = orc.restriction_mult_transpose(nd, dof, off, ind, yE)
+    assert relerr(host(y), yref) < TOL
+    a.close(); it.close(); R.close()
