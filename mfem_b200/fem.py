@@ -503,6 +503,7 @@ class BilinearForm:
     def _make_op(self, ess):
         if self.op:
             capi.lib().b2f_operator_destroy(self.op)
+            self.op = None
         ess = _i32(ess)
         arr = (vp * len(self.integrators))(*[it.h for it in self.integrators])
         h = vp()
