@@ -251,6 +251,8 @@ def main():
         ids = [m.Halo.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         halo = m.Halo(dev, rank, world, fes.ndofs, fes.halo_tables, ids[0])
+        if os.environ.get("B2F_HALO", "p2p") != "nccl":
+            halo.connect_p2p(dist)  # shared dofs: peer-memory stores over NVLink, no NCCL send/recv
         form.SetHalo(halo)
     ess = fes.GetEssentialTrueDofs()
     b_l = m.LinearForm(dev, fes).Assemble()
@@ -361,7 +363,10 @@ def main():
                                    f"{n}^3 hexes per GPU{' (curved, Q3 nodes)' if w['curved'] else ''} on a {px}x{py}x{pz} grid, {nglob} dofs, "
                                    f"{a.iters} fixed CG iterations per step",
                        "dofs_global": nglob, "dofs_per_gpu": nglob // a.gpus, "elements_per_gpu": fes.ne,
-                       "cg_iterations_per_step": a.iters, "l2": "inputs (quadrature data, "
+                       "cg_iterations_per_step": a.iters,
+                       "halo": ("none" if not halo else "peer-memory stores (CUDA IPC over NVLink) + ncclAllReduce dots"
+                                if os.environ.get("B2F_HALO", "p2p") != "nccl" else "ncclSend/Recv + ncclAllReduce dots"),
+                       "l2": "inputs (quadrature data, "
                        f"{it_bytes(w, fes.ne) / 1e9:.1f} GB per GPU) far exceed the 126 MB L2",
                        "final_norm": final_norm, "setup_seconds": round(t_setup, 1)},
             "e2e": {"value": e2e, "unit": "GDOF/s", "h2d_bytes_per_step": nt * 8 * a.gpus,

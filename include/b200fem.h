@@ -257,6 +257,17 @@ int b2f_halo_create(b2f_ctx *ctx, const void *nccl_id128_h, int rank, int nranks
                     const int *ext_ldof_h,           /* ldofs owned by each neighbour      */
                     b2f_halo **out);
 void b2f_halo_destroy(b2f_halo *h);
+/* Peer-memory exchange (one process per GPU on one NVLink/NVSwitch node): instead of
+ * pack + MPI_Isend/Irecv (pfespace.cpp:5786-5803) or pack + ncclSend/ncclRecv, the pack
+ * kernel stores straight into the neighbour's receive buffer through a CUDA-IPC mapping and
+ * publishes an epoch flag that the neighbour's unpack / assembly kernel waits on: the
+ * exchange is two small kernels on the solver's stream, no library call, no host sync.
+ * Every rank exports a blob of b2f_halo_p2p_blob_bytes() bytes, the caller gathers the blobs
+ * of all ranks (MPI_Allgather / torch.distributed) into blobs_h[rank] and connects.  Used by
+ * the in-place P / P^T of the operator (owned-first numbering). */
+int b2f_halo_p2p_blob_bytes(void);
+int b2f_halo_p2p_export(b2f_halo *h, void *blob_h);
+int b2f_halo_p2p_connect(b2f_halo *h, const void *blobs_h, int nranks);
 /* P: true-dof vector -> local-dof vector (pfespace.cpp:5760-5816) */
 int b2f_halo_mult(b2f_halo *h, const double *x_t, double *y_l);
 /* P^T: local-dof vector -> true-dof vector, fixed summation order (pfespace.cpp:5818-5927) */

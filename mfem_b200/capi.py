@@ -98,6 +98,9 @@ PROTOTYPES = {
     "b2f_halo_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp,
                                   vp, vp, C.POINTER(vp)]),
     "b2f_halo_destroy": (None, [vp]),
+    "b2f_halo_p2p_blob_bytes": (C.c_int, []),
+    "b2f_halo_p2p_export": (C.c_int, [vp, vp]),
+    "b2f_halo_p2p_connect": (C.c_int, [vp, vp, C.c_int]),
     "b2f_halo_mult": (C.c_int, [vp, vp, vp]),
     "b2f_halo_mult_transpose": (C.c_int, [vp, vp, vp]),
     "b2f_halo_dot": (C.c_int, [vp, i64, vp, vp, c_double_p]),

@@ -105,6 +105,27 @@ struct b2f_halo
    int *unq_j = nullptr;          // [n_shr] positions in shr_buf, ascending per row
    double *shr_buf = nullptr, *ext_buf = nullptr;
    bool prefix = false;           // ltdof_ldof is the identity: a T-vector is the head of an L-vector
+   // ---- peer-memory exchange (b2f_halo_p2p_connect): the pack kernel stores straight into
+   // the neighbour's receive buffer over NVLink and publishes an epoch flag; no NCCL call
+   bool p2p = false;
+   unsigned long long *flags = nullptr;      // [64] local: [k] P epoch of neighbour k, [32+k] P^T epoch
+   unsigned int *tickets = nullptr;          // [64] local block tickets of the push kernels
+   int *shr_off_d = nullptr, *ext_off_d = nullptr;
+   double **peer_ext_dst = nullptr;          // [n_nbr] where my shared values land in neighbour k
+   double **peer_shr_dst = nullptr;          // [n_nbr] where my contributions land in neighbour k
+   unsigned long long **peer_flag_p = nullptr, **peer_flag_pt = nullptr;
+   unsigned long long epoch_p = 0, epoch_pt = 0;
+   int max_shr = 0, max_ext = 0;
+   std::vector<void *> opened;               // cudaIpcOpenMemHandle results to close
+};
+
+// what a rank publishes so that its neighbours can address its receive buffers
+struct b2f_p2p_blob
+{
+   int rank, n_nbr;
+   int nbr_rank[32];
+   int shr_off[33], ext_off[33];
+   cudaIpcMemHandle_t ext_buf, shr_buf, flags;
 };
 
 namespace b2f
@@ -135,6 +156,116 @@ assemble_shared_kernel(int n, const int *__restrict__ unq_ltdof, const int *__re
    double v = y[t];
    for (int j = unq_i[i]; j < unq_i[i + 1]; ++j) { v += buf[unq_j[j]]; }
    y[t] = v;
+}
+
+// ---- peer-memory exchange -----------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+   unsigned long long v;
+   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+   return v;
+}
+
+// Fused pack + send: block column blockIdx.y serves neighbour k and stores
+// x[src_idx[off[k] + i]] straight into that neighbour's receive buffer (a peer pointer mapped
+// over NVLink).  The last block of a column to finish publishes `epoch` in the neighbour's flag.
+__global__ void __launch_bounds__(256)
+p2p_push_kernel(const int *__restrict__ src_idx, const int *__restrict__ off,
+                const double *__restrict__ x, double *const *__restrict__ peer_dst,
+                unsigned long long *const *__restrict__ peer_flag, unsigned int *tickets,
+                unsigned long long epoch)
+{
+   const int k = blockIdx.y;
+   const int b = off[k], n = off[k + 1] - b;
+   double *dst = peer_dst[k];
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+   {
+      dst[i] = __ldg(x + __ldg(src_idx + b + i));
+   }
+   __threadfence_system();
+   __syncthreads();
+   if (threadIdx.x == 0)
+   {
+      const unsigned int t = atomicAdd(tickets + k, 1u);
+      if (t == gridDim.x - 1)
+      {
+         tickets[k] = 0;
+         __threadfence_system();
+         st_release_sys(peer_flag[k], epoch);
+      }
+   }
+}
+
+// every block first waits until all neighbours have published `epoch`
+__device__ __forceinline__ void p2p_wait(const unsigned long long *flags, int n_nbr,
+                                         unsigned long long epoch)
+{
+   if (threadIdx.x < n_nbr)
+   {
+      while (ld_acquire_sys(flags + threadIdx.x) < epoch) { __nanosleep(64); }
+   }
+   __syncthreads();
+}
+
+// P, receiving side: wait, then y[ext_ldof[i]] = ext_buf[i]
+__global__ void __launch_bounds__(256)
+p2p_wait_scatter_kernel(int n, const int *__restrict__ dst, const double *x, double *y,
+                        const unsigned long long *flags, int n_nbr, unsigned long long epoch)
+{
+   p2p_wait(flags, n_nbr, epoch);
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) { y[__ldg(dst + i)] = x[i]; }
+}
+
+// P^T, receiving side: wait, then the fixed-order assembly of assemble_shared_kernel
+__global__ void __launch_bounds__(256)
+p2p_wait_assemble_kernel(int n, const int *__restrict__ unq_ltdof, const int *__restrict__ unq_i,
+                         const int *__restrict__ unq_j, const double *buf, double *y,
+                         const unsigned long long *flags, int n_nbr, unsigned long long epoch)
+{
+   p2p_wait(flags, n_nbr, epoch);
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) { return; }
+   const int t = unq_ltdof[i];
+   double v = y[t];
+   for (int j = unq_i[i]; j < unq_i[i + 1]; ++j) { v += buf[unq_j[j]]; }
+   y[t] = v;
+}
+
+static int p2p_mult_inplace(b2f_halo *h, double *v)
+{
+   b2f_ctx *ctx = h->ctx;
+   cudaStream_t s = ctx->stream;
+   if (h->n_nbr == 0) { return B2F_OK; }
+   const unsigned long long ep = ++h->epoch_p;
+   const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(h->max_shr, 256), 64)), h->n_nbr);
+   p2p_push_kernel<<<grid, 256, 0, s>>>(h->shr_ltdof, h->shr_off_d, v, h->peer_ext_dst, h->peer_flag_p,
+                                        h->tickets, ep);
+   B2F_LAUNCH_CHECK(ctx);
+   p2p_wait_scatter_kernel<<<(unsigned)std::max<int64_t>(1, cdiv(h->n_ext, 256)), 256, 0, s>>>(
+      h->n_ext, h->ext_ldof, h->ext_buf, v, h->flags, h->n_nbr, ep);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+static int p2p_mult_transpose_inplace(b2f_halo *h, double *v)
+{
+   b2f_ctx *ctx = h->ctx;
+   cudaStream_t s = ctx->stream;
+   if (h->n_nbr == 0) { return B2F_OK; }
+   const unsigned long long ep = ++h->epoch_pt;
+   const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(h->max_ext, 256), 64)), h->n_nbr);
+   p2p_push_kernel<<<grid, 256, 0, s>>>(h->ext_ldof, h->ext_off_d, v, h->peer_shr_dst, h->peer_flag_pt,
+                                        h->tickets + 32, ep);
+   B2F_LAUNCH_CHECK(ctx);
+   p2p_wait_assemble_kernel<<<(unsigned)std::max<int64_t>(1, cdiv(h->n_unq, 256)), 256, 0, s>>>(
+      h->n_unq, h->unq_ltdof, h->unq_i, h->unq_j, h->shr_buf, v, h->flags + 32, h->n_nbr, ep);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
 }
 
 static int exchange(b2f_halo *h, const double *send, const std::vector<int> &send_off,
@@ -213,6 +344,7 @@ bool halo_is_prefix(const b2f_halo *h) { return h->prefix; }
 
 int halo_mult_inplace(b2f_halo *h, double *v)
 {
+   if (h->p2p) { return p2p_mult_inplace(h, v); }
    b2f_ctx *ctx = h->ctx;
    cudaStream_t s = ctx->stream;
    if (h->n_shr)
@@ -232,6 +364,7 @@ int halo_mult_inplace(b2f_halo *h, double *v)
 
 int halo_mult_transpose_inplace(b2f_halo *h, double *v)
 {
+   if (h->p2p) { return p2p_mult_transpose_inplace(h, v); }
    b2f_ctx *ctx = h->ctx;
    cudaStream_t s = ctx->stream;
    if (h->n_ext)
@@ -394,9 +527,83 @@ int b2f_halo_create(b2f_ctx *ctx, const void *nccl_id128_h, int rank, int nranks
    return B2F_OK;
 }
 
+int b2f_halo_p2p_blob_bytes(void) { return (int)sizeof(b2f_p2p_blob); }
+
+int b2f_halo_p2p_export(b2f_halo *h, void *blob_h)
+{
+   B2F_REQUIRE(h && blob_h, "b2f_halo_p2p_export: NULL argument");
+   B2F_REQUIRE(h->n_nbr <= 32, "b2f_halo_p2p_export: more than 32 neighbours");
+   b2f_p2p_blob b;
+   memset(&b, 0, sizeof(b));
+   b.rank = h->rank; b.n_nbr = h->n_nbr;
+   for (int k = 0; k < h->n_nbr; k++) { b.nbr_rank[k] = h->nbr_rank[k]; }
+   for (int k = 0; k <= h->n_nbr; k++) { b.shr_off[k] = h->shr_off[k]; b.ext_off[k] = h->ext_off[k]; }
+   if (!h->flags)
+   {
+      B2F_CUDA(cudaMalloc((void **)&h->flags, sizeof(unsigned long long) * 64));
+      B2F_CUDA(cudaMemset(h->flags, 0, sizeof(unsigned long long) * 64));
+      B2F_CUDA(cudaMalloc((void **)&h->tickets, sizeof(unsigned int) * 64));
+      B2F_CUDA(cudaMemset(h->tickets, 0, sizeof(unsigned int) * 64));
+   }
+   B2F_CUDA(cudaIpcGetMemHandle(&b.ext_buf, h->ext_buf));
+   B2F_CUDA(cudaIpcGetMemHandle(&b.shr_buf, h->shr_buf));
+   B2F_CUDA(cudaIpcGetMemHandle(&b.flags, h->flags));
+   memcpy(blob_h, &b, sizeof(b));
+   return B2F_OK;
+}
+
+int b2f_halo_p2p_connect(b2f_halo *h, const void *blobs_h, int nranks)
+{
+   B2F_REQUIRE(h && blobs_h && nranks == h->nranks, "b2f_halo_p2p_connect: bad arguments");
+   B2F_REQUIRE(h->prefix, "b2f_halo_p2p_connect: needs the owned-first local numbering");
+   B2F_REQUIRE(h->flags, "b2f_halo_p2p_connect: call b2f_halo_p2p_export first");
+   const b2f_p2p_blob *blobs = (const b2f_p2p_blob *)blobs_h;
+   std::vector<double *> ext_dst(h->n_nbr), shr_dst(h->n_nbr);
+   std::vector<unsigned long long *> fp(h->n_nbr), fpt(h->n_nbr);
+   h->max_shr = h->max_ext = 0;
+   for (int k = 0; k < h->n_nbr; k++)
+   {
+      const b2f_p2p_blob &nb = blobs[h->nbr_rank[k]];
+      B2F_REQUIRE(nb.rank == h->nbr_rank[k], "b2f_halo_p2p_connect: blob %d is from rank %d", h->nbr_rank[k], nb.rank);
+      int j = -1;
+      for (int q = 0; q < nb.n_nbr; q++) { if (nb.nbr_rank[q] == h->rank) { j = q; } }
+      B2F_REQUIRE(j >= 0, "b2f_halo_p2p_connect: rank %d does not list rank %d as a neighbour", nb.rank, h->rank);
+      const int my_shr = h->shr_off[k + 1] - h->shr_off[k], my_ext = h->ext_off[k + 1] - h->ext_off[k];
+      B2F_REQUIRE(my_shr == nb.ext_off[j + 1] - nb.ext_off[j] && my_ext == nb.shr_off[j + 1] - nb.shr_off[j],
+                  "b2f_halo_p2p_connect: message sizes with rank %d do not match", nb.rank);
+      void *pe = nullptr, *ps = nullptr, *pf = nullptr;
+      B2F_CUDA(cudaIpcOpenMemHandle(&pe, nb.ext_buf, cudaIpcMemLazyEnablePeerAccess));
+      h->opened.push_back(pe);
+      B2F_CUDA(cudaIpcOpenMemHandle(&ps, nb.shr_buf, cudaIpcMemLazyEnablePeerAccess));
+      h->opened.push_back(ps);
+      B2F_CUDA(cudaIpcOpenMemHandle(&pf, nb.flags, cudaIpcMemLazyEnablePeerAccess));
+      h->opened.push_back(pf);
+      ext_dst[k] = (double *)pe + nb.ext_off[j];
+      shr_dst[k] = (double *)ps + nb.shr_off[j];
+      fp[k] = (unsigned long long *)pf + j;
+      fpt[k] = (unsigned long long *)pf + 32 + j;
+      h->max_shr = std::max(h->max_shr, my_shr);
+      h->max_ext = std::max(h->max_ext, my_ext);
+   }
+   int rc = B2F_OK;
+   if (!rc) { rc = up(h->shr_off, &h->shr_off_d); }
+   if (!rc) { rc = up(h->ext_off, &h->ext_off_d); }
+   if (!rc) { rc = up(ext_dst, &h->peer_ext_dst); }
+   if (!rc) { rc = up(shr_dst, &h->peer_shr_dst); }
+   if (!rc) { rc = up(fp, &h->peer_flag_p); }
+   if (!rc) { rc = up(fpt, &h->peer_flag_pt); }
+   if (rc) { return rc; }
+   h->p2p = true;
+   return B2F_OK;
+}
+
 void b2f_halo_destroy(b2f_halo *h)
 {
    if (!h) { return; }
+   cudaStreamSynchronize(h->ctx->stream);
+   for (void *p : h->opened) { cudaIpcCloseMemHandle(p); }
+   cudaFree(h->flags); cudaFree(h->tickets); cudaFree(h->shr_off_d); cudaFree(h->ext_off_d);
+   cudaFree(h->peer_ext_dst); cudaFree(h->peer_shr_dst); cudaFree(h->peer_flag_p); cudaFree(h->peer_flag_pt);
    if (h->comm) { cudaStreamSynchronize(h->ctx->stream); g_nccl.CommDestroy(h->comm); }
    cudaFree(h->ltdof_ldof); cudaFree(h->shr_ltdof); cudaFree(h->ext_ldof);
    cudaFree(h->unq_ltdof); cudaFree(h->unq_i); cudaFree(h->unq_j);

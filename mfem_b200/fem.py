@@ -451,6 +451,18 @@ class Halo:
              _np_ptr(_i32(t["ext_offsets"])), _np_ptr(_i32(t["ext_ldof"])), C.byref(h))
         self.h = h
 
+    def connect_p2p(self, dist):
+        """Switch the exchange to peer-memory stores over NVLink (CUDA IPC): gathers every rank's
+        buffer handles with torch.distributed and maps the neighbours' receive buffers."""
+        nb = int(capi.lib().b2f_halo_p2p_blob_bytes())
+        blob = (C.c_char * nb)()
+        call("b2f_halo_p2p_export", self.h, blob)
+        blobs = [None] * dist.get_world_size()
+        dist.all_gather_object(blobs, bytes(blob))
+        allb = (C.c_char * (nb * len(blobs))).from_buffer_copy(b"".join(blobs))
+        call("b2f_halo_p2p_connect", self.h, allb, len(blobs))
+        dist.barrier()
+
     @staticmethod
     def unique_id():
         buf = (C.c_char * 128)()

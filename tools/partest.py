@@ -75,54 +75,64 @@ x_l = dev.empty(fes.ndofs)
 halo.Mult(x_t, x_l)
 dev.sync()
 assert torch.equal(x_l, xs[l2s]), "P does not reproduce the global field"
-# y = P^T A P x
-y_t, ys = dev.empty(fes.ntdofs), dev.empty(nlat)
-form.Mult(x_t, y_t)
-sform.Mult(xs, ys)
-dev.sync()
-e1 = rel(y_t, ys[t2s])
-assert e1 < 1e-12, f"RAP operator parity {e1}"
-# constrained operator + diagonal
-ess, sess = fes.GetEssentialTrueDofs(), sfes.GetEssentialTrueDofs()
-b_l = m.LinearForm(dev, fes).Assemble()
-b_t = dev.empty(fes.ntdofs)
-halo.MultTranspose(b_l, b_t)
-bs = m.LinearForm(dev, sfes).Assemble()
-dev.sync()
-assert rel(b_t, bs[t2s]) < 1e-12
-A, _, B = form.FormLinearSystem(ess, dev.zeros(fes.ntdofs), b_t)
-As, _, Bs = sform.FormLinearSystem(sess, dev.zeros(nlat), bs)
-A.Mult(x_t, y_t)
-As.Mult(xs, ys)
-dev.sync()
-e2 = rel(y_t, ys[t2s])
-assert e2 < 1e-12, f"constrained operator parity {e2}"
-dg, dgs = dev.empty(fes.ntdofs), dev.empty(nlat)
-form.AssembleDiagonal(dg)
-sform.AssembleDiagonal(dgs)
-dev.sync()
-e3 = rel(dg, dgs[t2s])
-assert e3 < 1e-12, f"diagonal parity {e3}"
-# all-reduced dot
-d_par = halo.Dot(x_t, y_t)
-d_ser = float(torch.dot(xs, ys))
-assert abs(d_par - d_ser) < 1e-12 * abs(d_ser), (d_par, d_ser)
-# PCG
-M, Ms = m.OperatorJacobiSmoother(form, ess), m.OperatorJacobiSmoother(sform, sess)
-res = []
-for (AA, MM, BB, n) in ((A, M, B, fes.ntdofs), (As, Ms, Bs, nlat)):
-    cg = m.CGSolver()
-    cg.SetRelTol(1e-8); cg.SetMaxIter(1000); cg.SetOperator(AA); cg.SetPreconditioner(MM)
-    X = dev.zeros(n)
-    cg.Mult(BB, X)
-    res.append((cg.GetNumIterations(), cg.GetConverged(), X))
-(it_p, conv_p, X_p), (it_s, conv_s, X_s) = res
-assert conv_p and conv_s and abs(it_p - it_s) <= 1, (it_p, it_s)
-e4 = rel(X_p, X_s[t2s])
-assert e4 < 1e-6, f"PCG solution {e4}"
+def check(mode):
+    global form
+    # y = P^T A P x
+    y_t, ys = dev.empty(fes.ntdofs), dev.empty(nlat)
+    form.Mult(x_t, y_t)
+    sform.Mult(xs, ys)
+    dev.sync()
+    e1 = rel(y_t, ys[t2s])
+    assert e1 < 1e-12, f"RAP operator parity {e1}"
+    # constrained operator + diagonal
+    ess, sess = fes.GetEssentialTrueDofs(), sfes.GetEssentialTrueDofs()
+    b_l = m.LinearForm(dev, fes).Assemble()
+    b_t = dev.empty(fes.ntdofs)
+    halo.MultTranspose(b_l, b_t)
+    bs = m.LinearForm(dev, sfes).Assemble()
+    dev.sync()
+    assert rel(b_t, bs[t2s]) < 1e-12
+    A, _, B = form.FormLinearSystem(ess, dev.zeros(fes.ntdofs), b_t)
+    As, _, Bs = sform.FormLinearSystem(sess, dev.zeros(nlat), bs)
+    A.Mult(x_t, y_t)
+    As.Mult(xs, ys)
+    dev.sync()
+    e2 = rel(y_t, ys[t2s])
+    assert e2 < 1e-12, f"constrained operator parity {e2}"
+    dg, dgs = dev.empty(fes.ntdofs), dev.empty(nlat)
+    form.AssembleDiagonal(dg)
+    sform.AssembleDiagonal(dgs)
+    dev.sync()
+    e3 = rel(dg, dgs[t2s])
+    assert e3 < 1e-12, f"diagonal parity {e3}"
+    # all-reduced dot
+    d_par = halo.Dot(x_t, y_t)
+    d_ser = float(torch.dot(xs, ys))
+    assert abs(d_par - d_ser) < 1e-12 * abs(d_ser), (d_par, d_ser)
+    # PCG
+    M, Ms = m.OperatorJacobiSmoother(form, ess), m.OperatorJacobiSmoother(sform, sess)
+    res = []
+    for (AA, MM, BB, n) in ((A, M, B, fes.ntdofs), (As, Ms, Bs, nlat)):
+        cg = m.CGSolver()
+        cg.SetRelTol(1e-8); cg.SetMaxIter(1000); cg.SetOperator(AA); cg.SetPreconditioner(MM)
+        X = dev.zeros(n)
+        cg.Mult(BB, X)
+        res.append((cg.GetNumIterations(), cg.GetConverged(), X))
+    (it_p, conv_p, X_p), (it_s, conv_s, X_s) = res
+    assert conv_p and conv_s and abs(it_p - it_s) <= 1, (it_p, it_s)
+    e4 = rel(X_p, X_s[t2s])
+    assert e4 < 1e-6, f"PCG solution {e4}"
+    return e1, e2, e3, it_p, it_s, e4
+
+
+out = {}
+out["nccl"] = check("nccl")
+halo.connect_p2p(dist)  # from here on P / P^T are peer-memory stores + epoch flags, no NCCL send/recv
+out["p2p"] = check("p2p")
+e1, e2, e3, it_p, it_s, e4 = out["p2p"]
 dist.barrier()
 if rank == 0:
-    print(f"PARTEST OK world={world} grid={grid} p={p} n/rank={a.n} kind={a.kind}: RAP {e1:.1e} constrained {e2:.1e} "
+    print(f"PARTEST OK (nccl and p2p halo) world={world} grid={grid} p={p} n/rank={a.n} kind={a.kind}: RAP {e1:.1e} constrained {e2:.1e} "
           f"diag {e3:.1e} pcg its {it_p} vs serial {it_s}, sol {e4:.1e}")
 halo.close()
 dist.destroy_process_group()
