@@ -103,7 +103,8 @@ int b2f_cartesian_h1_space_h(int dim, int nx, int ny, int nz, int p, int sfc_ord
  * lowest rank general/communication.cpp:120-124; true dofs fem/pfespace.cpp:2169; neighbour
  * tables general/communication.cpp:543,579).  No communication: every rank calls it with
  * its own `rank` (= ix + px*(iy + py*iz)).  All array arguments may be NULL;
- * sizes_h[10] = {lnx, lny, lnz, ne, n_ldofs, n_tdofs, n_nbr, n_shr, n_ext, n_bdr}.
+ * sizes_h[11] = {lnx, lny, lnz, ne, n_ldofs, n_tdofs, n_nbr, n_shr, n_ext, n_bdr, n_interior};
+ * the elements are ordered interior-first: [0, n_interior) touch no neighbour-owned dof.
  * The local space is numbered as b2f_cartesian_h1_space_h numbers the local block, then
  * permuted so that the rank's own (true) dofs come first: ltdof_ldof is the identity and a
  * true-dof vector is the head of a local-dof vector (the halo then works in place);
@@ -204,6 +205,11 @@ int b2f_operator_eliminate_rhs(b2f_operator *op, const double *x_l, double *b_l)
  * RAPOperator(P, A, P) (linalg/operator.hpp:981-1033) on true-dof vectors. */
 int b2f_operator_set_halo(b2f_operator *op, b2f_halo *halo);
 int b2f_operator_height(const b2f_operator *op); /* true-dof size if a halo is set */
+/* Declare that elements [0, n_interior) touch no dof owned by another rank (the partition
+ * generator orders elements that way).  With a peer-memory halo the operator then overlaps
+ * the shared-dof exchange with interior-element work (the reference overlaps its local copy
+ * with MPI_Isend/Irecv, pfespace.cpp:5786-5813).  -1 = unknown (no overlap). */
+int b2f_operator_set_interior(b2f_operator *op, int64_t n_interior);
 
 /* ---- OperatorJacobiSmoother (linalg/solvers.cpp:324-450) ----------------------------- */
 /* Setup: dinv = damping / diag; dinv[ess] = damping (solvers.cpp:401-425). */

@@ -89,6 +89,7 @@ PROTOTYPES = {
     "b2f_operator_eliminate_rhs": (C.c_int, [vp, vp, vp]),
     "b2f_operator_set_halo": (C.c_int, [vp, vp]),
     "b2f_operator_height": (C.c_int, [vp]),
+    "b2f_operator_set_interior": (C.c_int, [vp, i64]),
     "b2f_jacobi_setup": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, C.c_double, vp]),
     "b2f_jacobi_mult": (C.c_int, [vp, C.c_int, vp, vp, vp]),
     "b2f_vector_dot": (C.c_int, [vp, i64, vp, vp, c_double_p]),

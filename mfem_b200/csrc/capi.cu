@@ -53,6 +53,11 @@ const int *halo_ldof_to_tdof_h(const b2f_halo *h); // host array [n_ldofs]: tdof
 bool halo_is_prefix(const b2f_halo *h);
 int halo_mult_inplace(b2f_halo *h, double *v);
 int halo_mult_transpose_inplace(b2f_halo *h, double *v);
+bool halo_is_p2p(const b2f_halo *h);
+int halo_p_push(b2f_halo *h, const double *v);
+int halo_p_wait(b2f_halo *h, double *v);
+int halo_pt_push(b2f_halo *h, const double *v);
+int halo_pt_wait(b2f_halo *h, double *v);
 
 template <typename T>
 static int upload(const T *h, size_t n, T **d)
@@ -605,6 +610,27 @@ static int local_mult_fused(b2f_operator *op, const double *x_l, double *y_l, co
    return B2F_OK;
 }
 
+// the elements [eb, ee) only, accumulating into y_l (no zero fill); even-odd kernels only
+static int local_mult_range(b2f_operator *op, const double *x_l, double *y_l, const int *idx,
+                            int64_t eb, int64_t ee, double *dot_acc)
+{
+   for (b2f_pa *pa : op->integ)
+   {
+      pa->rb = eb; pa->re = ee;
+      const int rc = pa_apply(pa, x_l, y_l, idx, dot_acc);
+      pa->rb = 0; pa->re = -1;
+      if (rc) { return rc; }
+   }
+   return B2F_OK;
+}
+
+static bool operator_can_split(const b2f_operator *op)
+{
+   if (op->signed_map || op->n_interior < 0 || getenv("B2F_NO_OVERLAP")) { return false; }
+   for (const b2f_pa *pa : op->integ) { if (!pa_has_fused_dot(pa)) { return false; } }
+   return true;
+}
+
 // every integrator can accumulate x.(Ax) inside its kernel (and the gather map is unsigned).
 // Opt-in (B2F_FUSED_DOT=1): on B200 the solver loop runs at the 1 kW power cap, where the
 // 16 B/dof pass it saves is paid back by the slightly heavier operator kernel (measured:
@@ -664,9 +690,30 @@ static int rap_mult(b2f_operator *op, const double *x, double *y, bool constrain
          xl = op->xl; yl = op->yl;
          B2F_CUDA(cudaMemcpyAsync(xl, x, sizeof(double) * nt, cudaMemcpyDeviceToDevice, ctx->stream));
       }
-      B2F_TRY(halo_mult_inplace(op->halo, xl));
-      B2F_TRY(local_mult(op, xl, yl, constrained_mask, dot_acc));
-      B2F_TRY(halo_mult_transpose_inplace(op->halo, yl));
+      if (halo_is_p2p(op->halo) && operator_can_split(op))
+      {
+         // The exchange is one-sided (peer stores + epoch flags), so on ONE stream it overlaps
+         // with element work by itself: push my shared values, run the first half of the
+         // interior elements (they read no neighbour-owned dof) while the neighbours' values
+         // arrive, unpack, run the boundary elements, push their contributions back, run the
+         // second half of the interior while those travel, then assemble what arrived.
+         const int *idx = (constrained_mask && op->fused_idx) ? op->fused_idx : op->r->gather_map;
+         const int64_t ni = op->n_interior, ne = op->r->ne, half = ni / 2;
+         B2F_TRY(halo_p_push(op->halo, xl));
+         B2F_CUDA(cudaMemsetAsync(yl, 0, sizeof(double) * (size_t)nl, ctx->stream));
+         B2F_TRY(local_mult_range(op, xl, yl, idx, 0, half, dot_acc));
+         B2F_TRY(halo_p_wait(op->halo, xl));
+         B2F_TRY(local_mult_range(op, xl, yl, idx, ni, ne, dot_acc));
+         B2F_TRY(halo_pt_push(op->halo, yl));
+         B2F_TRY(local_mult_range(op, xl, yl, idx, half, ni, dot_acc));
+         B2F_TRY(halo_pt_wait(op->halo, yl));
+      }
+      else
+      {
+         B2F_TRY(halo_mult_inplace(op->halo, xl));
+         B2F_TRY(local_mult(op, xl, yl, constrained_mask, dot_acc));
+         B2F_TRY(halo_mult_transpose_inplace(op->halo, yl));
+      }
       if (!lcap) { B2F_CUDA(cudaMemcpyAsync(y, yl, sizeof(double) * nt, cudaMemcpyDeviceToDevice, ctx->stream)); }
       return B2F_OK;
    }
@@ -675,6 +722,15 @@ static int rap_mult(b2f_operator *op, const double *x, double *y, bool constrain
    B2F_TRY(halo_mult(op->halo, x, op->xl));
    B2F_TRY(local_mult(op, op->xl, op->yl, constrained_mask, dot_acc));
    return halo_mult_transpose(op->halo, op->yl, y);
+}
+
+int b2f_operator_set_interior(b2f_operator *op, int64_t n_interior)
+{
+   B2F_REQUIRE(op, "b2f_operator_set_interior: NULL handle");
+   B2F_REQUIRE(n_interior >= -1 && n_interior <= op->r->ne, "b2f_operator_set_interior: %lld of %d elements",
+               (long long)n_interior, op->r->ne);
+   op->n_interior = n_interior;
+   return B2F_OK;
 }
 
 int b2f_operator_height(const b2f_operator *op)

@@ -110,6 +110,7 @@ struct b2f_pa
    double *data = nullptr; // (Q^dim, ncomp, NE)
    int64_t data_size = 0;
    int collocated = 0;     // B is the identity (BP5): interpolation is skipped
+   int64_t rb = 0, re = -1; // element range of the next apply (re < 0: all), even-odd kernel only
 };
 
 struct b2f_operator
@@ -130,6 +131,7 @@ struct b2f_operator
    double *pcg_hist = nullptr;
    int pcg_hist_cap = 0;
    double *dot_acc = nullptr;           // 64 partial sums of the fused (d, A d)
+   int64_t n_interior = -1;             // elements [0, n_interior) touch no neighbour-owned dof
 };
 
 namespace b2f

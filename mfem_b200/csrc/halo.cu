@@ -236,37 +236,72 @@ p2p_wait_assemble_kernel(int n, const int *__restrict__ unq_ltdof, const int *__
    y[t] = v;
 }
 
-static int p2p_mult_inplace(b2f_halo *h, double *v)
+static int p2p_p_push(b2f_halo *h, const double *v)
+{
+   b2f_ctx *ctx = h->ctx;
+   if (h->n_nbr == 0) { return B2F_OK; }
+   const unsigned long long ep = ++h->epoch_p;
+   const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(h->max_shr, 256), 64)), h->n_nbr);
+   p2p_push_kernel<<<grid, 256, 0, ctx->stream>>>(h->shr_ltdof, h->shr_off_d, v, h->peer_ext_dst,
+                                                  h->peer_flag_p, h->tickets, ep);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+static int p2p_p_wait(b2f_halo *h, double *v)
 {
    b2f_ctx *ctx = h->ctx;
    cudaStream_t s = ctx->stream;
    if (h->n_nbr == 0) { return B2F_OK; }
-   const unsigned long long ep = ++h->epoch_p;
-   const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(h->max_shr, 256), 64)), h->n_nbr);
-   p2p_push_kernel<<<grid, 256, 0, s>>>(h->shr_ltdof, h->shr_off_d, v, h->peer_ext_dst, h->peer_flag_p,
-                                        h->tickets, ep);
-   B2F_LAUNCH_CHECK(ctx);
+   const unsigned long long ep = h->epoch_p;
    p2p_wait_scatter_kernel<<<(unsigned)std::max<int64_t>(1, cdiv(h->n_ext, 256)), 256, 0, s>>>(
       h->n_ext, h->ext_ldof, h->ext_buf, v, h->flags, h->n_nbr, ep);
    B2F_LAUNCH_CHECK(ctx);
    return B2F_OK;
 }
 
-static int p2p_mult_transpose_inplace(b2f_halo *h, double *v)
+static int p2p_mult_inplace(b2f_halo *h, double *v)
+{
+   int rc = p2p_p_push(h, v);
+   return rc ? rc : p2p_p_wait(h, v);
+}
+
+static int p2p_pt_push(b2f_halo *h, const double *v)
+{
+   b2f_ctx *ctx = h->ctx;
+   if (h->n_nbr == 0) { return B2F_OK; }
+   const unsigned long long ep = ++h->epoch_pt;
+   const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(h->max_ext, 256), 64)), h->n_nbr);
+   p2p_push_kernel<<<grid, 256, 0, ctx->stream>>>(h->ext_ldof, h->ext_off_d, v, h->peer_shr_dst,
+                                                  h->peer_flag_pt, h->tickets + 32, ep);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+static int p2p_pt_wait(b2f_halo *h, double *v)
 {
    b2f_ctx *ctx = h->ctx;
    cudaStream_t s = ctx->stream;
    if (h->n_nbr == 0) { return B2F_OK; }
-   const unsigned long long ep = ++h->epoch_pt;
-   const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(h->max_ext, 256), 64)), h->n_nbr);
-   p2p_push_kernel<<<grid, 256, 0, s>>>(h->ext_ldof, h->ext_off_d, v, h->peer_shr_dst, h->peer_flag_pt,
-                                        h->tickets + 32, ep);
-   B2F_LAUNCH_CHECK(ctx);
+   const unsigned long long ep = h->epoch_pt;
    p2p_wait_assemble_kernel<<<(unsigned)std::max<int64_t>(1, cdiv(h->n_unq, 256)), 256, 0, s>>>(
       h->n_unq, h->unq_ltdof, h->unq_i, h->unq_j, h->shr_buf, v, h->flags + 32, h->n_nbr, ep);
    B2F_LAUNCH_CHECK(ctx);
    return B2F_OK;
 }
+
+static int p2p_mult_transpose_inplace(b2f_halo *h, double *v)
+{
+   int rc = p2p_pt_push(h, v);
+   return rc ? rc : p2p_pt_wait(h, v);
+}
+
+// split-phase forms for overlapping the exchange with element work (peer-memory mode only)
+bool halo_is_p2p(const b2f_halo *h) { return h->p2p; }
+int halo_p_push(b2f_halo *h, const double *v) { return p2p_p_push(h, v); }
+int halo_p_wait(b2f_halo *h, double *v) { return p2p_p_wait(h, v); }
+int halo_pt_push(b2f_halo *h, const double *v) { return p2p_pt_push(h, v); }
+int halo_pt_wait(b2f_halo *h, double *v) { return p2p_pt_wait(h, v); }
 
 static int exchange(b2f_halo *h, const double *send, const std::vector<int> &send_off,
                     double *recv, const std::vector<int> &recv_off)

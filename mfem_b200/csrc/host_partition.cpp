@@ -151,6 +151,33 @@ extern "C" int b2f_cartesian_partition_h(int dim, int nx, int ny, int nz, int p,
    {
       if (owner[l] == rank) { l2t[l] = (int)ltdof.size(); ltdof.push_back(l); }
    }
+   // Element order: interior elements (no dof owned by a neighbour) first, in their original
+   // relative order, then the boundary layer -- the operator overlaps the exchange with the
+   // former (b2f_operator_set_interior).
+   int n_interior = 0;
+   {
+      std::vector<char> is_bdr(ne, 0);
+      for (int e = 0; e < ne; e++)
+      {
+         for (int i = 0; i < dof; i++) { if (owner[ed[(size_t)e * dof + i]] != rank) { is_bdr[e] = 1; break; } }
+         n_interior += !is_bdr[e];
+      }
+      if (n_interior != ne)
+      {
+         std::vector<int> ed2(ed.size());
+         std::vector<double> ev2(ev.size());
+         int a = 0, b = n_interior;
+         for (int e = 0; e < ne; e++)
+         {
+            const int t = is_bdr[e] ? b++ : a++;
+            std::copy(ed.begin() + (size_t)e * dof, ed.begin() + (size_t)(e + 1) * dof, ed2.begin() + (size_t)t * dof);
+            std::copy(ev.begin() + (size_t)e * nv * dim, ev.begin() + (size_t)(e + 1) * nv * dim,
+                      ev2.begin() + (size_t)t * nv * dim);
+         }
+         ed.swap(ed2);
+         ev.swap(ev2);
+      }
+   }
    std::vector<int> nbrs;
    for (auto &kv : shr) { nbrs.push_back(kv.first); }
    for (auto &kv : ext) { nbrs.push_back(kv.first); }
@@ -162,7 +189,7 @@ extern "C" int b2f_cartesian_partition_h(int dim, int nx, int ny, int nz, int p,
 
    sizes_h[0] = ln[0]; sizes_h[1] = ln[1]; sizes_h[2] = ln[2]; sizes_h[3] = ne; sizes_h[4] = nl;
    sizes_h[5] = (int)ltdof.size(); sizes_h[6] = (int)nbrs.size(); sizes_h[7] = n_shr;
-   sizes_h[8] = n_ext; sizes_h[9] = (int)bdr.size();
+   sizes_h[8] = n_ext; sizes_h[9] = (int)bdr.size(); sizes_h[10] = n_interior;
    if (elem_dof_h) { std::copy(ed.begin(), ed.end(), elem_dof_h); }
    if (dof_map_h) { std::copy(dm.begin(), dm.end(), dof_map_h); }
    if (bdr_ldofs_h) { std::copy(bdr.begin(), bdr.end(), bdr_ldofs_h); }

@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(PipeCfg<KIND, D, Q, NEB>::NT, MINB)
 pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__restrict__ qdata,
                       const double *__restrict__ x, double *__restrict__ y,
                       const int *__restrict__ idx, const int64_t ne, const int pf,
-                      double *__restrict__ dot_acc)
+                      double *__restrict__ dot_acc, const int64_t e_first)
 {
    using C = PipeCfg<KIND, D, Q, NEB>;
    using S = EOStages<KIND, D, Q, NEB, COLLOC, DOT>;
@@ -473,7 +473,7 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
    double *r2 = r1 + C::R1;
 
    const int t = threadIdx.x;
-   const int64_t e0 = (int64_t)blockIdx.x * NEB;
+   const int64_t e0 = e_first + (int64_t)blockIdx.x * NEB; // elements [e_first, ne) of this launch
    const int nev = (int)((ne - e0) < NEB ? (ne - e0) : NEB);
 
    // quadrature-data stream: TMA per element + L2 prefetch for the CTA `pf` blocks on
@@ -782,7 +782,11 @@ int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx, double 
       set_error("pa_apply_3d_eo: the basis tables are not symmetric");
       return B2F_ERR_UNSUPPORTED;
    }
-   int64_t grid = cdiv(pa->ne, NEB);
+   // element range of this launch (b2f_pa::rb / re; the whole mesh unless the operator splits
+   // interior and boundary elements around the halo exchange)
+   const int64_t e_first = pa->rb, e_last = pa->re < 0 ? pa->ne : pa->re;
+   if (e_last <= e_first) { return B2F_OK; }
+   int64_t grid = cdiv(e_last - e_first, NEB);
    auto go = [&](auto kern) -> int
    {
       // (keyed by the kernel's address: instantiations that differ only in bool template
@@ -801,7 +805,7 @@ int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx, double 
       if (PERSIST && grid > resident) { grid = resident; }
       timing_mark(ctx);
       if constexpr (PERSIST) { kern<<<(unsigned)grid, C::NT, C::SMEM, ctx->stream>>>(bs, pa->data, x, y, idx, pa->ne, pf); }
-      else { kern<<<(unsigned)grid, C::NT, C::SMEM, ctx->stream>>>(bs, pa->data, x, y, idx, pa->ne, pf, dot_acc); }
+      else { kern<<<(unsigned)grid, C::NT, C::SMEM, ctx->stream>>>(bs, pa->data, x, y, idx, e_last, pf, dot_acc, e_first); }
       timing_mark(ctx);
       B2F_LAUNCH_CHECK(ctx);
       return B2F_OK;

@@ -252,10 +252,10 @@ class FiniteElementSpace:
             self.ntdofs = self.ndofs
         else:
             px, py, pz = mesh.part
-            sz = (C.c_int * 10)()
+            sz = (C.c_int * 11)()
             args = (dim, mesh.nx, mesh.ny, mesh.nz, p, int(mesh.sfc), px, py, pz, mesh.rank)
             call("b2f_cartesian_partition_h", *args, sz, *([None] * 11))
-            lnx, lny, lnz, ne, nl, nt, nn, ns, nx_, nb = list(sz)
+            lnx, lny, lnz, ne, nl, nt, nn, ns, nx_, nb, self.n_interior = list(sz)
             self.local_n = (lnx, lny, lnz)
             self.ne, self.ndofs, self.ntdofs = ne, nl, nt
             self.elem_dof = np.empty(ne * self.dof, np.int32)
@@ -524,12 +524,19 @@ class BilinearForm:
         self.op, self.ess = h, ess
         if self.halo is not None:
             call("b2f_operator_set_halo", self.op, self.halo.h)
+            self._set_interior()
 
     def SetHalo(self, halo):
         """ParBilinearForm: the operator becomes P^T A P on true-dof vectors."""
         self.halo = halo
         if self.op:
             call("b2f_operator_set_halo", self.op, halo.h)
+            self._set_interior()
+
+    def _set_interior(self):
+        ni = getattr(self.fes, "n_interior", None)
+        if ni is not None and self.halo is not None:
+            call("b2f_operator_set_interior", self.op, ni)
 
     def Height(self):
         return int(capi.lib().b2f_operator_height(self.op))

@@ -156,6 +156,11 @@ def test_partition_tables_are_consistent(dim, n, p, grid):
         covered[t["ltdof_ldof"]] = True
         covered[t["ext_ldof"]] = True
         assert covered.all() and len(t["ext_ldof"]) + f.ntdofs == f.ndofs
+        # owned-first numbering and interior-first element order
+        assert np.array_equal(t["ltdof_ldof"], np.arange(f.ntdofs))
+        ed = f.elem_dof.reshape(f.ne, f.dof)
+        touches_ext = (ed >= f.ntdofs).any(axis=1)
+        assert not touches_ext[:f.n_interior].any() and touches_ext[f.n_interior:].all()
         for k, s in enumerate(t["nbr_rank"]):
             ts = ranks[s].halo_tables
             ks = list(ts["nbr_rank"]).index(r)
