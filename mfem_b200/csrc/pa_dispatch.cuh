@@ -88,7 +88,10 @@ constexpr int smem_eo(int kind, int D, int Q, int n)
 // Elements per CTA, candidate i: 0 -> >= 4 CTAs per SM, 1 -> 3 CTAs, 2 -> 2 CTAs; <= 512 threads
 constexpr int neb_eo(int kind, int D, int Q, int cand)
 {
-   const int budget = cand == 0 ? 55 * 1024 : cand == 1 ? 74 * 1024 : 112 * 1024;
+   // mass has ~7x less quadrature data per element: smaller tiles, many more CTAs per SM
+   // (its kernel is latency/barrier-bound, profiles/r01_bp1_p4_ncu.txt)
+   const int budget = kind == B2F_KIND_MASS ? (cand == 0 ? 8 * 1024 : cand == 1 ? 14 * 1024 : 27 * 1024)
+                      : (cand == 0 ? 55 * 1024 : cand == 1 ? 74 * 1024 : 112 * 1024);
    int n = 1;
    while (n < 32 && smem_eo(kind, D, Q, n + 1) <= budget && (n + 1) * Q * Q <= 512) { n++; }
    return n;
@@ -98,9 +101,9 @@ constexpr int minb_eo(int kind, int D, int Q, int n)
 {
    const int nt = ((n * Q * Q + 31) / 32) * 32;
    const int by_smem = (227 * 1024) / (smem_eo(kind, D, Q, n) + 1024);
-   const int by_regs = 65536 / (nt * 120);
+   const int by_regs = 65536 / (nt * (kind == B2F_KIND_MASS ? 72 : 120));
    int b = by_smem < by_regs ? by_smem : by_regs;
-   if (b > 8) { b = 8; }
+   if (b > 12) { b = 12; }
    return b < 1 ? 1 : b;
 }
 
@@ -110,7 +113,7 @@ constexpr int tuned_cand_eo(int kind, int D, int Q)
    // profiles/r01_sweep_eo_kernel.txt: the smallest tile (>= 4 CTAs per SM) wins except at the
    // lowest orders, where a CTA of the smallest tile has too few threads
    if (kind == B2F_KIND_DIFFUSION) { return (D <= 3 && Q >= D + 1) ? 1 : 0; }
-   return D <= 4 ? 1 : 0;
+   return 1;
 }
 
 // the even-odd kernel (and with it the fused x.(Ax) accumulation) runs for 3D integrators with
