@@ -175,13 +175,19 @@ int b2f_pa_data(const b2f_pa *pa, const double **data, int64_t *size);
  * Replaces (Smem)PADiffusionApply2D/3D (bilininteg_diffusion_kernels.hpp:514-1215) and
  * (Smem)PAMassApply2D/3D (bilininteg_mass_kernels.hpp:440-1165). */
 int b2f_pa_add_mult(b2f_pa *pa, const double *x_e, double *y_e);
+/* VectorDiffusionIntegrator / VectorMassIntegrator::AddMultPA (fem/integ/
+ * bilininteg_vecdiffusion_pa.cpp, bilininteg_vecmass_pa.cpp; CEED BP2/4/6): the same operator on
+ * every component of an E-vector laid out (dofs, vdim, NE); one quadrature-data load serves
+ * all components. */
+int b2f_pa_add_mult_vec(b2f_pa *pa, int vdim, const double *x_e, double *y_e);
 /* BilinearFormIntegrator::AssembleDiagonalPA (bilininteg.hpp:68): diag_e += diag(A_e).
  * Replaces (Smem)PADiffusionDiagonal2D/3D, (Smem)PAMassAssembleDiagonal2D/3D. */
 int b2f_pa_assemble_diagonal(b2f_pa *pa, double *diag_e);
 
 /* ---- PABilinearFormExtension + ConstrainedOperator ---------------------------------- */
 /* PABilinearFormExtension (fem/bilinearform_ext.cpp:256-564) over one restriction and
- * n integrators; ess_ldofs_h (may be NULL / 0) is the essential dof list that
+ * n integrators.  A restriction with vdim > 1 (byNODES or byVDIM) makes it the vector operator
+ * of Vector{Mass,Diffusion}Integrator on vdof vectors (single rank); ess_ldofs_h (may be NULL / 0) is the essential dof list that
  * FormLinearSystem wraps around it as a ConstrainedOperator (linalg/operator.cpp:526). */
 int b2f_operator_create(b2f_ctx *ctx, b2f_restriction *r, b2f_pa *const *integrators,
                         int n_integrators, const int *ess_dofs_h, int n_ess,

@@ -79,6 +79,7 @@ PROTOTYPES = {
     "b2f_pa_destroy": (None, [vp]),
     "b2f_pa_data": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
     "b2f_pa_add_mult": (C.c_int, [vp, vp, vp]),
+    "b2f_pa_add_mult_vec": (C.c_int, [vp, C.c_int, vp, vp]),
     "b2f_pa_assemble_diagonal": (C.c_int, [vp, vp]),
     "b2f_operator_create": (C.c_int, [vp, vp, C.POINTER(vp), C.c_int, vp, C.c_int, C.POINTER(vp)]),
     "b2f_operator_destroy": (None, [vp]),

@@ -458,6 +458,17 @@ int b2f_pa_add_mult(b2f_pa *pa, const double *x_e, double *y_e)
    return pa_apply(pa, x_e, y_e, nullptr);
 }
 
+int b2f_pa_add_mult_vec(b2f_pa *pa, int vdim, const double *x_e, double *y_e)
+{
+   B2F_REQUIRE(pa && vdim >= 1 && (pa->ne == 0 || (x_e && y_e)), "b2f_pa_add_mult_vec: bad argument");
+   if (vdim == 1) { return pa_apply(pa, x_e, y_e, nullptr); }
+   B2F_REQUIRE(pa_has_fused_dot(pa), "b2f_pa_add_mult_vec: vector E-vectors need the 3D even-odd kernel");
+   pa->vd = vdim;
+   const int rc = pa_apply(pa, x_e, y_e, nullptr);
+   pa->vd = 1;
+   return rc;
+}
+
 int b2f_pa_assemble_diagonal(b2f_pa *pa, double *diag_e)
 {
    B2F_REQUIRE(pa && (pa->ne == 0 || diag_e), "b2f_pa_assemble_diagonal: NULL argument");
@@ -465,13 +476,24 @@ int b2f_pa_assemble_diagonal(b2f_pa *pa, double *diag_e)
 }
 
 // ---- operator ---------------------------------------------------------------------------
-__global__ void mask_gather_map_kernel(int64_t n, const int *__restrict__ gmap,
+// out[c*n + i] = -1 where vdof (gmap[i], c) is essential, else gmap[i]; vdof = g*xs + c*xo
+__global__ void mask_gather_map_kernel(int64_t n, int vd, int64_t xs, int64_t xo,
+                                       const int *__restrict__ gmap,
                                        const unsigned char *__restrict__ is_ess, int *out)
 {
    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= n) { return; }
    const int g = gmap[i];
-   out[i] = (g >= 0 && is_ess[g]) ? -1 : g;
+   for (int c = 0; c < vd; c++) { out[c * n + i] = (g >= 0 && is_ess[g * xs + c * xo]) ? -1 : g; }
+}
+
+// y[vdof(g, c)] = x[g] for all components
+__global__ void replicate_components_kernel(int nd, int vd, int64_t xs, int64_t xo,
+                                            const double *__restrict__ x, double *y)
+{
+   const int g = blockIdx.x * blockDim.x + threadIdx.x;
+   if (g >= nd) { return; }
+   for (int c = 0; c < vd; c++) { y[g * xs + c * xo] = x[g]; }
 }
 __global__ void mark_kernel(int n, const int *__restrict__ idx, unsigned char *flags)
 {
@@ -512,13 +534,16 @@ static int operator_build_masks(b2f_operator *op, const int *ess_ldofs_h, int n_
    {
       int *d_ess_l = nullptr;
       unsigned char *flags = nullptr;
+      const int vd = r->vdim;
+      const int64_t xs = r->byvdim ? vd : 1, xo = r->byvdim ? 1 : r->ndofs;
+      const size_t nflags = (size_t)r->ndofs * vd + 1;
       B2F_TRY(upload(ess_ldofs_h, (size_t)n_ess_l, &d_ess_l));
-      B2F_CUDA(cudaMalloc((void **)&flags, (size_t)r->ndofs + 1));
-      B2F_CUDA(cudaMemsetAsync(flags, 0, (size_t)r->ndofs + 1, ctx->stream));
+      B2F_CUDA(cudaMalloc((void **)&flags, nflags));
+      B2F_CUDA(cudaMemsetAsync(flags, 0, nflags, ctx->stream));
       mark_kernel<<<(unsigned)cdiv(n_ess_l, 256), 256, 0, ctx->stream>>>(n_ess_l, d_ess_l, flags);
       B2F_LAUNCH_CHECK(ctx);
-      B2F_CUDA(cudaMalloc((void **)&op->fused_idx, sizeof(int) * n));
-      mask_gather_map_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(n, r->gather_map,
+      B2F_CUDA(cudaMalloc((void **)&op->fused_idx, sizeof(int) * n * vd));
+      mask_gather_map_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(n, vd, xs, xo, r->gather_map,
                                                                               flags, op->fused_idx);
       B2F_LAUNCH_CHECK(ctx);
       B2F_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -534,7 +559,7 @@ int b2f_operator_create(b2f_ctx *ctx, b2f_restriction *r, b2f_pa *const *integra
    B2F_REQUIRE(ctx && r && out && integrators && n_integrators >= 1,
                "b2f_operator_create: NULL argument");
    B2F_REQUIRE(n_ess == 0 || ess_dofs_h, "b2f_operator_create: ess_dofs_h is NULL");
-   B2F_REQUIRE(r->vdim == 1, "b2f_operator_create: vdim = %d (scalar spaces only)", r->vdim);
+   B2F_REQUIRE(r->vdim >= 1, "b2f_operator_create: vdim = %d", r->vdim);
    int dim_dof = 0;
    for (int i = 0; i < n_integrators; i++)
    {
@@ -550,8 +575,17 @@ int b2f_operator_create(b2f_ctx *ctx, b2f_restriction *r, b2f_pa *const *integra
    (void)dim_dof;
    for (int i = 0; i < n_ess; i++)
    {
-      B2F_REQUIRE(ess_dofs_h[i] >= 0 && ess_dofs_h[i] < r->ndofs,
+      B2F_REQUIRE(ess_dofs_h[i] >= 0 && (int64_t)ess_dofs_h[i] < (int64_t)r->ndofs * r->vdim,
                   "b2f_operator_create: essential dof %d out of range", ess_dofs_h[i]);
+   }
+   if (r->vdim > 1)
+   {
+      for (int i = 0; i < n_integrators; i++)
+      {
+         B2F_REQUIRE(pa_has_fused_dot(integrators[i]),
+                     "b2f_operator_create: vector spaces need the 3D even-odd kernel (symmetric basis, "
+                     "D1D = 2..9, Q1D = D1D..D1D+2)");
+      }
    }
    b2f_operator *op = new b2f_operator;
    op->ctx = ctx;
@@ -626,7 +660,7 @@ static int local_mult_range(b2f_operator *op, const double *x_l, double *y_l, co
 
 static bool operator_can_split(const b2f_operator *op)
 {
-   if (op->signed_map || op->n_interior < 0 || getenv("B2F_NO_OVERLAP")) { return false; }
+   if (op->signed_map || op->r->vdim > 1 || op->n_interior < 0 || getenv("B2F_NO_OVERLAP")) { return false; }
    for (const b2f_pa *pa : op->integ) { if (!pa_has_fused_dot(pa)) { return false; } }
    return true;
 }
@@ -637,7 +671,7 @@ static bool operator_can_split(const b2f_operator *op)
 // 17.0 vs 17.0 GDOF/s for BP3 p=4), so the plain two-kernel form stays the default.
 static bool operator_has_fused_dot(const b2f_operator *op)
 {
-   if (op->signed_map || !getenv("B2F_FUSED_DOT")) { return false; }
+   if (op->signed_map || op->r->vdim > 1 || !getenv("B2F_FUSED_DOT")) { return false; }
    for (const b2f_pa *pa : op->integ) { if (!pa_has_fused_dot(pa)) { return false; } }
    return true;
 }
@@ -646,12 +680,18 @@ static int local_mult_unfused(b2f_operator *op, const double *x_l, double *y_l)
 {
    b2f_ctx *ctx = op->ctx;
    b2f_restriction *r = op->r;
-   const int64_t ne_dof = (int64_t)r->ne * r->dof;
+   const int64_t ne_dof = (int64_t)r->ne * r->dof * r->vdim;
    B2F_TRY(ensure(&op->xe, ne_dof));
    B2F_TRY(ensure(&op->ye, ne_dof));
    B2F_TRY(restriction_gather(r, x_l, op->xe, false));                 // bilinearform_ext.cpp:543
    B2F_CUDA(cudaMemsetAsync(op->ye, 0, sizeof(double) * ne_dof, ctx->stream)); // :545
-   for (b2f_pa *pa : op->integ) { B2F_TRY(pa_apply(pa, op->xe, op->ye, nullptr)); } // :548
+   for (b2f_pa *pa : op->integ)                                        // :548
+   {
+      pa->vd = r->vdim;
+      const int rc = pa_apply(pa, op->xe, op->ye, nullptr);
+      pa->vd = 1;
+      if (rc) { return rc; }
+   }
    return restriction_scatter(r, op->ye, y_l, 0);                      // :557
 }
 
@@ -742,7 +782,7 @@ int b2f_operator_height(const b2f_operator *op)
       halo_sizes(op->halo, &nl, &nt);
       return nt;
    }
-   return op->r->ndofs;
+   return op->r->ndofs * op->r->vdim;
 }
 
 int b2f_operator_mult(b2f_operator *op, const double *x_l, double *y_l)
@@ -803,6 +843,20 @@ int b2f_operator_assemble_diagonal(b2f_operator *op, double *diag)
    B2F_TRY(ensure(&op->ye, ne_dof));
    B2F_CUDA(cudaMemsetAsync(op->ye, 0, sizeof(double) * ne_dof, ctx->stream)); // bilinearform_ext.cpp:385
    for (b2f_pa *pa : op->integ) { B2F_TRY(pa_diag(pa, op->ye)); }
+   if (r->vdim > 1)
+   {
+      // vector integrators: the scalar diagonal for every component
+      // (bilininteg_vecdiffusion_pa.cpp / bilininteg_vecmass_pa.cpp AssembleDiagonalPA)
+      B2F_REQUIRE(!op->halo, "b2f_operator_assemble_diagonal: vector spaces are single-rank for now");
+      B2F_TRY(ensure(&op->z, r->ndofs));
+      b2f_restriction scalar = *r;
+      scalar.vdim = 1; scalar.byvdim = 0;
+      B2F_TRY(restriction_scatter(&scalar, op->ye, op->z, 2));
+      replicate_components_kernel<<<(unsigned)cdiv(r->ndofs, 256), 256, 0, ctx->stream>>>(
+         r->ndofs, r->vdim, r->byvdim ? r->vdim : 1, r->byvdim ? 1 : r->ndofs, op->z, diag);
+      B2F_LAUNCH_CHECK(ctx);
+      return B2F_OK;
+   }
    if (!op->halo) { return restriction_scatter(r, op->ye, diag, 2); } // AbsMultTranspose :426
    // ParBilinearForm::AssembleDiagonal (fem/pbilinearform.cpp:293): P^T of the local diagonal
    B2F_TRY(ensure(&op->yl, r->ndofs));
@@ -833,6 +887,7 @@ int b2f_operator_set_halo(b2f_operator *op, b2f_halo *halo)
    {
       int nl = 0, nt = 0;
       halo_sizes(halo, &nl, &nt);
+      B2F_REQUIRE(op->r->vdim == 1, "b2f_operator_set_halo: vector spaces are single-rank for now");
       B2F_REQUIRE(nl == op->r->ndofs, "b2f_operator_set_halo: halo has %d ldofs, the space %d", nl,
                   op->r->ndofs);
    }

@@ -111,6 +111,10 @@ struct b2f_pa
    int64_t data_size = 0;
    int collocated = 0;     // B is the identity (BP5): interpolation is skipped
    int64_t rb = 0, re = -1; // element range of the next apply (re < 0: all), even-odd kernel only
+   // vector (vdim > 1) form of the next apply, even-odd kernel only: component c of L-dof g is
+   // x[g*vxs + c*vxo]; the gather index of component c starts at idx + c*vics
+   int vd = 1;
+   int64_t vxs = 1, vxo = 0, vics = 0;
 };
 
 struct b2f_operator
@@ -120,7 +124,8 @@ struct b2f_operator
    std::vector<b2f_pa *> integ;
    int n_ess = 0;
    int *ess = nullptr;          // device list of essential ldofs / tdofs
-   int *fused_idx = nullptr;    // gather_map with ess dofs marked -1 (constrained fused path)
+   int *fused_idx = nullptr;    // gather_map with ess dofs marked -1 (constrained fused path);
+                                // vdim copies (one per component) for vector spaces
    double *xe = nullptr, *ye = nullptr; // E-vectors for the unfused path (lazy)
    double *z = nullptr, *w = nullptr;   // L-vector scratch
    b2f_halo *halo = nullptr;

@@ -456,12 +456,22 @@ __device__ __forceinline__ void eo_line_coords(int t, int &e1, int &dx1, int &dz
 // pass over the vectors (IterativeSolver::Dot, linalg/solvers.cpp:58).  It is evaluated as the
 // energy sum_q (grad x)^T D (grad x) at the quadrature points, where both factors are in
 // registers anyway (3 FMAs per point); absent elements of a ragged tile contribute nothing.
-template <int KIND, int D, int Q, int NEB, bool FUSED, bool COLLOC, int MINB, bool DOT = false>
+// vector spaces (vdim > 1: CEED BP2/4/6, Vector{Mass,Diffusion}Integrator): the components are
+// processed one after the other while the element's quadrature data stays in shared memory
+struct VecArgs
+{
+   int vd;               // number of components
+   long long xs, xo;     // component c of L-dof g lives at x[g*xs + c*xo]
+   long long ics;        // gather index of component c starts at idx + c*ics (per-component masks)
+};
+
+template <int KIND, int D, int Q, int NEB, bool FUSED, bool COLLOC, int MINB, bool DOT = false,
+          bool VEC = false>
 __global__ void __launch_bounds__(PipeCfg<KIND, D, Q, NEB>::NT, MINB)
 pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__restrict__ qdata,
                       const double *__restrict__ x, double *__restrict__ y,
                       const int *__restrict__ idx, const int64_t ne, const int pf,
-                      double *__restrict__ dot_acc, const int64_t e_first)
+                      double *__restrict__ dot_acc, const int64_t e_first, const VecArgs va)
 {
    using C = PipeCfg<KIND, D, Q, NEB>;
    using S = EOStages<KIND, D, Q, NEB, COLLOC, DOT>;
@@ -516,65 +526,75 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
    const int loc1 = dx1 + D2 * dz1;                // + D*dy : position inside the element
    const int a1 = Q * e1 + YQ * dx1 + C::SA * dz1; // + qy   : A/F address of this line
 
-   int gi[D];
+   const int ncomp = VEC ? va.vd : 1;
+   for (int c = 0; c < ncomp; c++)
    {
-      double u[D];
+      int gi[D];
+      {
+         double u[D];
 #pragma unroll
-      for (int dy = 0; dy < D; dy++) { gi[dy] = -1; u[dy] = 0.0; }
+         for (int dy = 0; dy < D; dy++) { gi[dy] = -1; u[dy] = 0.0; }
+         if (act1)
+         {
+            if constexpr (FUSED)
+            {
+               const int *ip = idx + (VEC ? c * va.ics : 0) + (e0 + e1) * D3 + loc1;
+#pragma unroll
+               for (int dy = 0; dy < D; dy++) { gi[dy] = __ldg(ip + D * dy); }
+#pragma unroll
+               for (int dy = 0; dy < D; dy++)
+               {
+                  const long long a = VEC ? gi[dy] * va.xs + c * va.xo : gi[dy];
+                  u[dy] = gi[dy] >= 0 ? __ldg(x + a) : 0.0;
+               }
+            }
+            else
+            {
+               const double *xe = x + ((e0 + e1) * ncomp + c) * D3 + loc1;
+#pragma unroll
+               for (int dy = 0; dy < D; dy++) { u[dy] = __ldg(xe + D * dy); }
+            }
+         }
+         if (has1) { S::stage1(bs, u, r1 + a1); }
+      }
+      __syncthreads();
+      if (t < C::T2) { S::stage2(bs, r1, r2, t); }
+      if constexpr (!C::TMA_OK) { cp_async_wait_all(); }
+      __syncthreads();
+      {
+         double part = 0.0;
+         if (t < C::T3)
+         {
+            part = S::stage3(bs, r2, qd, t, bar, 0);
+            if ((t % C::YQ) / Q >= nev) { part = 0.0; } // lines of a ragged tile: absent elements
+         }
+         if constexpr (DOT)
+         {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { part += __shfl_xor_sync(0xffffffffu, part, o); }
+            if ((t & 31) == 0) { atomicAdd(dot_acc + ((blockIdx.x + (t >> 5)) & 63), part); }
+         }
+      }
+      __syncthreads();
+      if (t < C::T2) { S::stage4(bs, r2, r1, t); }
+      __syncthreads();
       if (act1)
       {
-         if constexpr (FUSED)
+         double v[D];
+         S::stage5(bs, r1 + a1, v);
+         double *ye = y + ((e0 + e1) * ncomp + c) * D3 + loc1; // E-vector form
+#pragma unroll
+         for (int dy = 0; dy < D; dy++)
          {
-            const int *ip = idx + (e0 + e1) * D3 + loc1;
-#pragma unroll
-            for (int dy = 0; dy < D; dy++) { gi[dy] = __ldg(ip + D * dy); }
-#pragma unroll
-            for (int dy = 0; dy < D; dy++) { u[dy] = gi[dy] >= 0 ? __ldg(x + gi[dy]) : 0.0; }
-         }
-         else
-         {
-            const double *xe = x + (e0 + e1) * D3 + loc1;
-#pragma unroll
-            for (int dy = 0; dy < D; dy++) { u[dy] = __ldg(xe + D * dy); }
+            if (FUSED)
+            {
+               const long long a = VEC ? gi[dy] * va.xs + c * va.xo : gi[dy];
+               if (gi[dy] >= 0) { atomicAdd(y + a, v[dy]); }
+            }
+            else { ye[D * dy] += v[dy]; }
          }
       }
-      if (has1) { S::stage1(bs, u, r1 + a1); }
-   }
-   __syncthreads();
-   if (t < C::T2) { S::stage2(bs, r1, r2, t); }
-   if constexpr (!C::TMA_OK) { cp_async_wait_all(); }
-   __syncthreads();
-   {
-      double part = 0.0;
-      if (t < C::T3)
-      {
-         part = S::stage3(bs, r2, qd, t, bar, 0);
-         if ((t % C::YQ) / Q >= nev) { part = 0.0; } // lines of a ragged tile: absent elements
-      }
-      if constexpr (DOT)
-      {
-#pragma unroll
-         for (int o = 16; o > 0; o >>= 1) { part += __shfl_xor_sync(0xffffffffu, part, o); }
-         if ((t & 31) == 0) { atomicAdd(dot_acc + ((blockIdx.x + (t >> 5)) & 63), part); }
-      }
-   }
-   __syncthreads();
-   if (t < C::T2) { S::stage4(bs, r2, r1, t); }
-   __syncthreads();
-   if (act1)
-   {
-      double v[D];
-      S::stage5(bs, r1 + a1, v);
-      double *ye = y + (e0 + e1) * D3 + loc1; // E-vector form
-#pragma unroll
-      for (int dy = 0; dy < D; dy++)
-      {
-         if (FUSED)
-         {
-            if (gi[dy] >= 0) { atomicAdd(y + gi[dy], v[dy]); }
-         }
-         else { ye[D * dy] += v[dy]; }
-      }
+      if (VEC && c + 1 < ncomp) { __syncthreads(); } // F consumed before the next component's A
    }
 }
 
@@ -805,13 +825,20 @@ int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx, double 
       if (PERSIST && grid > resident) { grid = resident; }
       timing_mark(ctx);
       if constexpr (PERSIST) { kern<<<(unsigned)grid, C::NT, C::SMEM, ctx->stream>>>(bs, pa->data, x, y, idx, pa->ne, pf); }
-      else { kern<<<(unsigned)grid, C::NT, C::SMEM, ctx->stream>>>(bs, pa->data, x, y, idx, e_last, pf, dot_acc, e_first); }
+      else
+      {
+         const VecArgs va = {pa->vd, (long long)pa->vxs, (long long)pa->vxo, (long long)pa->vics};
+         kern<<<(unsigned)grid, C::NT, C::SMEM, ctx->stream>>>(bs, pa->data, x, y, idx, e_last, pf, dot_acc,
+                                                              e_first, va);
+      }
       timing_mark(ctx);
       B2F_LAUNCH_CHECK(ctx);
       return B2F_OK;
    };
    const bool fused = idx != nullptr;
-   if ((fused && FUSEDSEL == 0) || (!fused && FUSEDSEL == 1) || (dot_acc && (!fused || PERSIST)))
+   const bool vec = pa->vd > 1;
+   if ((fused && FUSEDSEL == 0) || (!fused && FUSEDSEL == 1) || (dot_acc && (!fused || PERSIST || vec)) ||
+       (vec && PERSIST))
    {
       set_error("pa_apply_3d_eo: kernel form not instantiated");
       return B2F_ERR_UNSUPPORTED;
@@ -829,21 +856,32 @@ int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx, double 
    }
    else
    {
+      // (the vector form has its own instantiation so that the scalar hot path is untouched)
       if (pa->collocated && CL)
       {
          if constexpr (FUSEDSEL != 0)
          {
+            if (fused && vec) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, CL, MINB, false, true>); }
             if (fused && dot_acc) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, CL, MINB, true>); }
             if (fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, CL, MINB>); }
          }
-         if constexpr (FUSEDSEL != 1) { if (!fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, CL, MINB>); } }
+         if constexpr (FUSEDSEL != 1)
+         {
+            if (!fused && vec) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, CL, MINB, false, true>); }
+            if (!fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, CL, MINB>); }
+         }
       }
       if constexpr (FUSEDSEL != 0)
       {
+         if (fused && vec) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, false, MINB, false, true>); }
          if (fused && dot_acc) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, false, MINB, true>); }
          if (fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, false, MINB>); }
       }
-      if constexpr (FUSEDSEL != 1) { if (!fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, false, MINB>); } }
+      if constexpr (FUSEDSEL != 1)
+      {
+         if (!fused && vec) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, false, MINB, false, true>); }
+         if (!fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, false, MINB>); }
+      }
    }
    return B2F_ERR_UNSUPPORTED;
 }

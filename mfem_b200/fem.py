@@ -296,8 +296,8 @@ class FiniteElementSpace:
 class ElementRestriction:
     """fem/restriction.hpp:40 -- L-vector <-> E-vector."""
 
-    def __init__(self, device, handle, ne, dof, ndofs):
-        self.dev, self.h, self.ne, self.dof, self.ndofs = device, handle, ne, dof, ndofs
+    def __init__(self, device, handle, ne, dof, ndofs, vdim=1):
+        self.dev, self.h, self.ne, self.dof, self.ndofs, self.vdim = device, handle, ne, dof, ndofs, vdim
 
     @classmethod
     def from_space(cls, device, fes):
@@ -307,12 +307,12 @@ class ElementRestriction:
         return cls(device, h, fes.ne, fes.dof, fes.ndofs)
 
     @classmethod
-    def from_tables(cls, device, ne, dof, ndofs, gather_map, offsets, indices):
+    def from_tables(cls, device, ne, dof, ndofs, gather_map, offsets, indices, vdim=1, byvdim=False):
         h = vp()
         g, o, i = _i32(gather_map), _i32(offsets), _i32(indices)
-        call("b2f_restriction_create", device.ctx, ne, dof, ndofs, 1, 0, _np_ptr(g), _np_ptr(o),
-             _np_ptr(i), C.byref(h))
-        return cls(device, h, ne, dof, ndofs)
+        call("b2f_restriction_create", device.ctx, ne, dof, ndofs, vdim, int(bool(byvdim)), _np_ptr(g),
+             _np_ptr(o), _np_ptr(i), C.byref(h))
+        return cls(device, h, ne, dof, ndofs, vdim)
 
     def tables(self):
         """(gather_map, offsets, indices) copied back to the host."""
@@ -328,7 +328,7 @@ class ElementRestriction:
         return tuple(out)
 
     def Height(self):
-        return self.ne * self.dof
+        return self.ne * self.dof * self.vdim
 
     def Mult(self, x, y):
         call("b2f_restriction_mult", self.h, _dp(x), _dp(y))
@@ -412,8 +412,12 @@ class _PAIntegrator:
         self.dev.sync()
         return a
 
-    def AddMultPA(self, x_e, y_e):
-        call("b2f_pa_add_mult", self.h, _dp(x_e), _dp(y_e))
+    def AddMultPA(self, x_e, y_e, vdim=1):
+        """vdim > 1: Vector{Diffusion,Mass}Integrator::AddMultPA on (dofs, vdim, NE) E-vectors"""
+        if vdim == 1:
+            call("b2f_pa_add_mult", self.h, _dp(x_e), _dp(y_e))
+        else:
+            call("b2f_pa_add_mult_vec", self.h, vdim, _dp(x_e), _dp(y_e))
 
     def AssembleDiagonalPA(self, diag_e):
         call("b2f_pa_assemble_diagonal", self.h, _dp(diag_e))

@@ -54,15 +54,26 @@ CASES = {
     "mass2d_p2_n3": dict(dim=2, n=3, p=2, kind="mass"),
     "mass2d_p5_n2_curved": dict(dim=2, n=2, p=5, kind="mass", curved=1),
     "bp5_2d_p6_n2": dict(dim=2, n=2, p=6, kind="diffusion", quad="gll"),
+    # vector problems, CEED BP2 / BP4 / BP6 (vdim = 3; bench_ceed.cpp:131 uses byVDIM)
+    "vec_diff3d_p2_n2_byvdim": dict(dim=3, n=2, p=2, kind="diffusion", vdim=3, byvdim=1),
+    "vec_diff3d_p4_n2_byvdim": dict(dim=3, n=2, p=4, kind="diffusion", vdim=3, byvdim=1),
+    "vec_diff3d_p3_n2_bynodes": dict(dim=3, n=2, p=3, kind="diffusion", vdim=3, byvdim=0),
+    "vec_mass3d_p3_n2_bynodes": dict(dim=3, n=2, p=3, kind="mass", vdim=3, byvdim=0),
+    "vec_mass3d_p4_n2_byvdim": dict(dim=3, n=2, p=4, kind="mass", vdim=3, byvdim=1),
+    "vec_bp6_3d_p3_n3_byvdim": dict(dim=3, n=3, p=3, kind="diffusion", quad="gll", vdim=3, byvdim=1),
+    "vec_diff3d_p5_n2_curved": dict(dim=3, n=2, p=5, kind="diffusion", vdim=3, byvdim=1, curved=1),
 }
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
     os.makedirs(OUT, exist_ok=True)
     if not refio.have_ref_driver():
         raise SystemExit("oracle/_ref/ref_driver missing: run `make -C oracle ref` first")
     total = 0
     for name, kw in CASES.items():
+        if only and not name.startswith(only):
+            continue
         d = refio.run_dump(rtol=1e-8, **kw)
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **d)

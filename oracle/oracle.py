@@ -228,3 +228,89 @@ class Operator:
                 _p(x), C.c_double(rel_tol), C.c_double(abs_tol), max_iter, C.byref(conv),
                 C.byref(fn), _p(hist), len(hist))
         return x, its, bool(conv.value), fn.value, hist[:its + 1]
+
+
+class VectorOperator:
+    """Vector (vdim > 1) PA operator: CEED BP2/BP4/BP6.
+
+    Restatement of the reference's vector path by composition of the pinned scalar pieces:
+      * ElementRestriction::Mult / MultTranspose with vdim (fem/restriction.cpp:116-201):
+        y_E(i, c, e) = x_L(t ? c : j, t ? j : c) with t = byVDIM, j = gather_map index --
+        component c of the L-vector is x[c::vdim] (byVDIM) or x[c*ndofs:(c+1)*ndofs] (byNODES);
+        the E-vector is laid out (dof, vdim, NE);
+      * Vector{Diffusion,Mass}Integrator::AddMultPA (fem/integ/bilininteg_vecdiffusion_pa.cpp,
+        bilininteg_vecmass_pa.cpp): the scalar PA kernel applied to each component with the
+        same quadrature data;
+      * ConstrainedOperator / OperatorJacobiSmoother / CGSolver as for scalars, on vdofs.
+    """
+
+    def __init__(self, scalar_op, vdim, byvdim, ess_vdofs=None):
+        self.op, self.vdim, self.byvdim = scalar_op, vdim, bool(byvdim)
+        self.nd = scalar_op.ndofs
+        self.n = vdim * self.nd
+        self.ess = _i32(ess_vdofs if ess_vdofs is not None else [])
+
+    def comp(self, x, c):
+        return _f64(x[c::self.vdim] if self.byvdim else x[c * self.nd:(c + 1) * self.nd])
+
+    def put(self, y, c, v):
+        if self.byvdim:
+            y[c::self.vdim] = v
+        else:
+            y[c * self.nd:(c + 1) * self.nd] = v
+
+    def to_evector(self, x, ne, dof, gather_map):
+        """ElementRestriction::Mult with vdim: (dof, vdim, NE)"""
+        out = np.empty((ne, self.vdim, dof))
+        for c in range(self.vdim):
+            out[:, c, :] = restriction_mult(ne, dof, gather_map, self.comp(x, c)).reshape(ne, dof)
+        return out.ravel()
+
+    def mult(self, x):
+        y = np.empty(self.n)
+        for c in range(self.vdim):
+            self.put(y, c, self.op.mult(self.comp(x, c)))
+        return y
+
+    def mult_constrained(self, x):
+        z = _f64(x).copy()
+        z[self.ess] = 0.0
+        y = self.mult(z)
+        y[self.ess] = x[self.ess]
+        return y
+
+    def diag(self):
+        d = self.op.diag()
+        y = np.empty(self.n)
+        for c in range(self.vdim):
+            self.put(y, c, d)
+        return y
+
+    def pcg(self, b, dinv, rel_tol=1e-8, max_iter=2000):
+        """linalg/solvers.cpp:869-1050 on vdofs (numpy vectors, oracle operator)"""
+        x = np.zeros(self.n)
+        r = _f64(b).copy()
+        z = dinv * r
+        d = z.copy()
+        nom0 = nom = float(np.dot(d, r))
+        r0 = max(nom * rel_tol * rel_tol, 0.0)
+        if nom <= r0:
+            return x, 0, True
+        q = self.mult_constrained(d)
+        den = float(np.dot(q, d))
+        i = 1
+        while True:
+            alpha = nom / den
+            x += alpha * d
+            r -= alpha * q
+            z = dinv * r
+            betanom = float(np.dot(r, z))
+            if betanom <= r0:
+                return x, i, True
+            i += 1
+            if i > max_iter:
+                return x, max_iter, False
+            d = z + (betanom / nom) * d
+            q = self.mult_constrained(d)
+            den = float(np.dot(d, q))
+            nom = betanom

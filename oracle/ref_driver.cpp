@@ -108,7 +108,7 @@ static void curve_map(const Vector &x, Vector &y)
 
 struct Problem
 {
-   int dim, n, p, nz;
+   int dim, n, p, nz, vdim, byvdim;
    bool mass, gll, curved, sfc;
    Mesh mesh;
    H1_FECollection *fec = nullptr;
@@ -127,6 +127,8 @@ struct Problem
       gll = A.gets("quad", "gl") == "gll";
       curved = A.geti("curved", 0) != 0;
       sfc = A.geti("sfc", 1) != 0;
+      vdim = A.geti("vdim", 1);
+      byvdim = A.geti("byvdim", vdim == 3 ? 1 : 0); // bench_ceed.cpp:131: byVDIM for VDIM == 3
       const int ny = A.geti("ny", n);
       string meshfile = A.gets("mesh", "");
       if (!meshfile.empty())
@@ -146,7 +148,8 @@ struct Problem
       }
       if (curved) { mesh.SetCurvature(A.geti("node_order", 3)); mesh.Transform(curve_map); }
       fec = new H1_FECollection(p, dim);
-      fes = new FiniteElementSpace(&mesh, fec);
+      fes = vdim == 1 ? new FiniteElementSpace(&mesh, fec)
+            : new FiniteElementSpace(&mesh, fec, vdim, byvdim ? Ordering::byVDIM : Ordering::byNODES);
       const Geometry::Type g = dim == 3 ? Geometry::CUBE : Geometry::SQUARE;
       // bench_ceed.cpp:121,133-137 : GL order 2p+3 (Q=p+2) or GLL order 2p-1 (Q=p+1)
       const int q_extra = A.geti("qorder", -1);
@@ -154,7 +157,13 @@ struct Problem
       else { ir = &IntRules.Get(g, q_extra >= 0 ? q_extra : 2 * p + 3); }
       a = new BilinearForm(fes);
       a->SetAssemblyLevel(AssemblyLevel::PARTIAL);
-      if (mass) { bfi = new MassIntegrator(one, ir); }
+      if (vdim > 1)
+      {
+         // CEED BP2 / BP4 / BP6 (bench_ceed.cpp: VectorMassIntegrator / VectorDiffusionIntegrator)
+         if (mass) { auto v = new VectorMassIntegrator(one); v->SetIntRule(ir); bfi = v; }
+         else { bfi = new VectorDiffusionIntegrator(one, ir); }
+      }
+      else if (mass) { bfi = new MassIntegrator(one, ir); }
       else { bfi = new DiffusionIntegrator(one, ir); }
       a->AddDomainIntegrator(bfi);
    }
@@ -356,6 +365,78 @@ static int do_dump(const Args &A, const char *out)
    return 0;
 }
 
+// Vector problems (vdim > 1): only what differs from the scalar dump -- the vdof layout, the
+// operator action, the diagonal and the constrained solve.
+static int do_dump_vector(const Args &A, const char *out)
+{
+   Problem P(A);
+   Dump D(out);
+   P.a->Assemble();
+   FiniteElementSpace &fes = *P.fes;
+   const FiniteElement &fe = *fes.GetTypicalFE();
+   const DofToQuad &maps = fe.GetDofToQuad(*P.ir, DofToQuad::TENSOR);
+   const int D1D = maps.ndof, Q1D = maps.nqpt, NE = fes.GetNE(), ndofs = fes.GetNDofs();
+   const int nv = fes.GetVSize();
+   D.scalar("dim", P.dim); D.scalar("n", P.n); D.scalar("p", P.p);
+   D.scalar("D1D", D1D); D.scalar("Q1D", Q1D); D.scalar("NE", NE); D.scalar("ndofs", ndofs);
+   D.scalar("vdim", P.vdim); D.scalar("byvdim", P.byvdim);
+   D.scalar("is_mass", (int)P.mass); D.scalar("is_gll", (int)P.gll); D.scalar("curved", (int)P.curved);
+   auto R = dynamic_cast<const ElementRestriction *>(
+               fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC));
+   D.ints("gather_map", R->GatherMap());
+   D.ints("offsets", R->Offsets());
+   D.ints("indices", R->Indices());
+   D.dbls("B", maps.B); D.dbls("G", maps.G);
+   D.dbls("W", P.ir->GetWeights());
+   const GeometricFactors *geom = P.mesh.GetGeometricFactors(
+                                     *P.ir, GeometricFactors::JACOBIANS | GeometricFactors::DETERMINANTS);
+   D.dbls("J", geom->J); D.dbls("detJ", geom->detJ);
+   Vector x(nv); x.Randomize(1);
+   D.dbls("x", x);
+   Vector xE(R->Height()), yE(R->Height());
+   R->Mult(x, xE);
+   D.dbls("xE", xE);
+   yE = 0.0;
+   P.bfi->AddMultPA(xE, yE);
+   D.dbls("yE", yE);
+   Vector y(nv);
+   P.a->Mult(x, y);
+   D.dbls("y", y);
+   Vector diag(nv);
+   P.a->AssembleDiagonal(diag);
+   D.dbls("diag", diag);
+   Array<int> ess_bdr(P.mesh.bdr_attributes.Max()); ess_bdr = 1;
+   Array<int> ess;
+   fes.GetEssentialTrueDofs(ess_bdr, ess);
+   D.ints("ess_tdof_list", ess);
+   Vector b(nv); b.Randomize(2); // bench_ceed uses a vector load; any RHS pins the solver
+   GridFunction u(&fes); u = 0.0;
+   OperatorPtr Aop; Vector B, X;
+   D.dbls("b", b);
+   P.a->FormLinearSystem(ess, u, b, Aop, X, B);
+   D.dbls("B_rhs", B);
+   {
+      Vector cy(nv);
+      Aop->Mult(x, cy);
+      D.dbls("y_constrained", cy);
+   }
+   const double rtol = A.getd("rtol", 1e-8);
+   OperatorJacobiSmoother M(*P.a, ess);
+   CGSolver cg;
+   cg.SetRelTol(rtol); cg.SetAbsTol(0.0); cg.SetMaxIter(2000); cg.SetPrintLevel(-1);
+   cg.SetOperator(*Aop);
+   cg.SetPreconditioner(M);
+   X = 0.0;
+   cg.Mult(B, X);
+   D.scalar("pcg_iters", cg.GetNumIterations());
+   D.scalar("pcg_converged", (int)cg.GetConverged());
+   D.scalar("pcg_rtol", rtol);
+   D.dbls("X_sol", X);
+   std::printf("dump %s: vdim=%d byvdim=%d NE=%d p=%d ndofs=%d |y|=%.17g pcg_iters=%d\n", out, P.vdim,
+               P.byvdim, NE, P.p, ndofs, y.Norml2(), cg.GetNumIterations());
+   return 0;
+}
+
 // Timing of the reference CPU path.  Prints one JSON object.
 //   mode=mult : y = A x (BilinearForm::Mult, PA) repeated `reps` times
 //   mode=pcg  : bench_ceed.cpp BP style: CG (optionally Jacobi), fixed `iters` iterations
@@ -368,7 +449,7 @@ static int do_bench(const Args &A)
    Problem P(A);
    P.a->Assemble();
    FiniteElementSpace &fes = *P.fes;
-   const int ndofs = fes.GetNDofs();
+   const int ndofs = fes.GetVSize();
    double t_setup = now() - t0;
    Vector x(ndofs), y(ndofs);
    x.UseDevice(true); y.UseDevice(true);
@@ -387,9 +468,15 @@ static int do_bench(const Args &A)
       Array<int> ess_bdr(P.mesh.bdr_attributes.Max()); ess_bdr = 1;
       Array<int> ess;
       fes.GetEssentialTrueDofs(ess_bdr, ess);
-      LinearForm b(&fes);
-      b.AddDomainIntegrator(new DomainLFIntegrator(P.one));
-      b.Assemble();
+      Vector b(fes.GetVSize());
+      if (P.vdim == 1)
+      {
+         LinearForm lf(&fes);
+         lf.AddDomainIntegrator(new DomainLFIntegrator(P.one));
+         lf.Assemble();
+         b = lf;
+      }
+      else { b.Randomize(2); }
       GridFunction u(&fes); u = 0.0;
       OperatorPtr Aop; Vector B, X;
       P.a->FormLinearSystem(ess, u, b, Aop, X, B);
@@ -430,7 +517,11 @@ int main(int argc, char **argv)
    const char *dev = getenv("MFEM_DEVICE"); // "omp" uses all host threads (device.cpp:145)
    Device device(dev ? dev : "cpu");
    string cmd = argv[1];
-   if (cmd == "dump") { Args A(argc, argv, 3); return do_dump(A, argv[2]); }
+   if (cmd == "dump")
+   {
+      Args A(argc, argv, 3);
+      return A.geti("vdim", 1) > 1 ? do_dump_vector(A, argv[2]) : do_dump(A, argv[2]);
+   }
    if (cmd == "bench") { Args A(argc, argv, 2); return do_bench(A); }
    std::fprintf(stderr, "unknown command %s\n", cmd.c_str());
    return 1;

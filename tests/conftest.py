@@ -15,7 +15,14 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    """scalar fixtures (every table of the path); vector ones are in vector_golden_names()"""
+    return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+                  if not n.startswith("vec_"))
+
+
+def vector_golden_names():
+    return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+                  if n.startswith("vec_"))
 
 
 _cache = {}
