@@ -628,19 +628,40 @@ void b2f_operator_destroy(b2f_operator *op)
    delete op;
 }
 
-static int ensure(double **p, int64_t n)
+// scratch vector of at least n doubles (grown on demand; capacities live in the operator)
+static int ensure_cap(b2f_operator *op, double **p, int64_t n)
 {
-   if (!*p) { B2F_CUDA(cudaMalloc((void **)p, sizeof(double) * (n ? n : 1))); }
+   int64_t &cap = op->scratch_cap[(const void *)p];
+   if (*p && cap >= n) { return B2F_OK; }
+   if (*p) { B2F_CUDA(cudaStreamSynchronize(op->ctx->stream)); cudaFree(*p); *p = nullptr; cap = 0; }
+   B2F_CUDA(cudaMalloc((void **)p, sizeof(double) * (n ? n : 1)));
+   cap = n;
    return B2F_OK;
 }
+#define ensure(p, n) ensure_cap(op, p, n)
 
 // y_l = R^T (sum_i A_i) R x_l on LOCAL vectors; idx selects the (masked) gather index
 static int local_mult_fused(b2f_operator *op, const double *x_l, double *y_l, const int *idx,
                             double *dot_acc = nullptr)
 {
    b2f_ctx *ctx = op->ctx;
-   B2F_CUDA(cudaMemsetAsync(y_l, 0, sizeof(double) * (size_t)op->r->ndofs, ctx->stream));
-   for (b2f_pa *pa : op->integ) { B2F_TRY(pa_apply(pa, x_l, y_l, idx, dot_acc)); }
+   const b2f_restriction *r = op->r;
+   B2F_CUDA(cudaMemsetAsync(y_l, 0, sizeof(double) * (size_t)r->ndofs * r->vdim, ctx->stream));
+   for (b2f_pa *pa : op->integ)
+   {
+      if (r->vdim > 1)
+      {
+         // Vector{Mass,Diffusion}Integrator: the scalar kernel per component, one quadrature-data
+         // load for all of them; masked gather maps are per component, the plain one is shared
+         pa->vd = r->vdim;
+         pa->vxs = r->byvdim ? r->vdim : 1;
+         pa->vxo = r->byvdim ? 1 : r->ndofs;
+         pa->vics = idx == r->gather_map ? 0 : (int64_t)r->ne * r->dof;
+      }
+      const int rc = pa_apply(pa, x_l, y_l, idx, dot_acc);
+      pa->vd = 1; pa->vxs = 1; pa->vxo = 0; pa->vics = 0;
+      if (rc) { return rc; }
+   }
    return B2F_OK;
 }
 
@@ -848,7 +869,7 @@ int b2f_operator_assemble_diagonal(b2f_operator *op, double *diag)
       // vector integrators: the scalar diagonal for every component
       // (bilininteg_vecdiffusion_pa.cpp / bilininteg_vecmass_pa.cpp AssembleDiagonalPA)
       B2F_REQUIRE(!op->halo, "b2f_operator_assemble_diagonal: vector spaces are single-rank for now");
-      B2F_TRY(ensure(&op->z, r->ndofs));
+      B2F_TRY(ensure(&op->z, (int64_t)r->ndofs * r->vdim)); // (z is also the vdof-sized scratch elsewhere)
       b2f_restriction scalar = *r;
       scalar.vdim = 1; scalar.byvdim = 0;
       B2F_TRY(restriction_scatter(&scalar, op->ye, op->z, 2));

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cmath>
 #include <cstdio>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -137,6 +138,7 @@ struct b2f_operator
    int pcg_hist_cap = 0;
    double *dot_acc = nullptr;           // 64 partial sums of the fused (d, A d)
    int64_t n_interior = -1;             // elements [0, n_interior) touch no neighbour-owned dof
+   std::map<const void *, int64_t> scratch_cap; // capacity of each scratch vector above
 };
 
 namespace b2f

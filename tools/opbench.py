@@ -29,6 +29,7 @@ ap.add_argument("--p", type=int, default=4)
 ap.add_argument("--n", type=int, default=96)
 ap.add_argument("--variants", default="0")
 ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--vdim", type=int, default=1, help="3: vector problem (BP2/4/6), byVDIM ordering")
 ap.add_argument("--sweep", default="", help="comma list of BPs: sweep p=1..8")
 ap.add_argument("--dofs", type=float, default=20e6)
 ap.add_argument("--maxn", type=int, default=100)
@@ -46,15 +47,23 @@ def run_case(bp, p, n, variants, reps):
     fes = m.FiniteElementSpace(m.Mesh.MakeCartesian3D(n, n, n), m.H1_FECollection(p, 3))
     ir = m.IntegrationRules(gll).Get(3, 2 * p - 1 if gll else 2 * p + 3)
     it = (m.MassIntegrator if bp == 1 else m.DiffusionIntegrator)(1.0, ir)
+    vd = a.vdim
+    if vd > 1:
+        # vector space on the same mesh: the scalar tables with vdim components, byVDIM
+        R = m.ElementRestriction.from_space(dev, fes)
+        gm, off, ind = R.tables()
+        R.close()
+        Rv = m.ElementRestriction.from_tables(dev, fes.ne, fes.dof, fes.ndofs, gm, off, ind, vdim=vd, byvdim=True)
+        fes.GetElementRestriction = lambda d: Rv
     form = m.BilinearForm(dev, fes)
     form.AddDomainIntegrator(it)
     form.Assemble()
-    N = fes.ndofs
+    N = fes.ndofs * vd
     x = torch.rand(N, dtype=torch.float64, device=dev.tdev)
     y = dev.empty(N)
     yref = None
     k = 1 if bp == 1 else 6
-    ab = (k * ir.nq1d ** 3 * 8 + 4 * (p + 1) ** 3) * fes.ne + 16 * N
+    ab = (k * ir.nq1d ** 3 * 8 + 4 * (p + 1) ** 3) * fes.ne + 16 * N  # D and indices once per element
     print(f"BP{bp} p={p} n={n}: NE={fes.ne} dofs={N} algorithmic bytes/apply={ab/1e9:.3f} GB", flush=True)
     for v in variants:
         for key in ("B2F_VARIANT", "B2F_PF", "B2F_NEB_CAND", "B2F_GENERAL_KERNEL"):
