@@ -226,8 +226,13 @@ class FiniteElementSpace:
     """Scalar H1 space on a structured Mesh with the reference's dof numbering
     (fem/fespace.cpp:3428-3536), built by the library's host code."""
 
-    def __init__(self, mesh, fec):
+    def __init__(self, mesh, fec, vdim=1, ordering="byNODES"):
+        """vdim > 1: vector space (FiniteElementSpace(mesh, fec, vdim, ordering), fem/fespace.hpp);
+        bench_ceed.cpp:131 uses Ordering::byVDIM for the vector BPs."""
         self.mesh, self.fec = mesh, fec
+        self.vdim, self.byvdim = int(vdim), ordering == "byVDIM"
+        if vdim > 1 and mesh.part is not None:
+            raise ValueError("vector spaces are single-rank for now")
         p, dim = fec.order, mesh.dim
         self.p, self.dim = p, dim
         self.d1d = p + 1
@@ -281,11 +286,21 @@ class FiniteElementSpace:
         return self.ndofs
 
     def GetTrueVSize(self):
-        return self.ntdofs
+        return self.ntdofs * self.vdim
+
+    def GetVSize(self):
+        return self.ndofs * self.vdim
 
     def GetEssentialTrueDofs(self):
-        """All-boundary essential dofs (ex1.cpp:165-183 with ess_bdr = 1): LOCAL dof ids."""
-        return self.bdr_dofs
+        """All-boundary essential dofs (ex1.cpp:165-183 with ess_bdr = 1): LOCAL (v)dof ids."""
+        if self.vdim == 1:
+            return self.bdr_dofs
+        b = self.bdr_dofs.astype(np.int64)
+        if self.byvdim:
+            v = (b[:, None] * self.vdim + np.arange(self.vdim)[None, :]).ravel()
+        else:
+            v = (b[None, :] + (np.arange(self.vdim) * self.ndofs)[:, None]).ravel()
+        return np.sort(v).astype(np.int32)
 
     def GetElementRestriction(self, device):
         if self._restr is None:
@@ -302,9 +317,10 @@ class ElementRestriction:
     @classmethod
     def from_space(cls, device, fes):
         h = vp()
-        call("b2f_restriction_create_from_elem_dof", device.ctx, fes.ne, fes.dof, fes.ndofs, 1, 0,
+        vdim, byvdim = getattr(fes, "vdim", 1), int(getattr(fes, "byvdim", False))
+        call("b2f_restriction_create_from_elem_dof", device.ctx, fes.ne, fes.dof, fes.ndofs, vdim, byvdim,
              _np_ptr(fes.elem_dof), _np_ptr(fes.dof_map), C.byref(h))
-        return cls(device, h, fes.ne, fes.dof, fes.ndofs)
+        return cls(device, h, fes.ne, fes.dof, fes.ndofs, vdim)
 
     @classmethod
     def from_tables(cls, device, ne, dof, ndofs, gather_map, offsets, indices, vdim=1, byvdim=False):
@@ -437,6 +453,12 @@ class MassIntegrator(_PAIntegrator):
 
     def GetRule(self, fes):
         return IntRules.Get(fes.dim, 2 * fes.p + fes.dim - 1)
+
+
+# Vector{Diffusion,Mass}Integrator (fem/integ/bilininteg_vecdiffusion_pa.cpp, bilininteg_vecmass_pa.cpp):
+# the same quadrature data; the operator applies it to every component of a vector space.
+VectorDiffusionIntegrator = DiffusionIntegrator
+VectorMassIntegrator = MassIntegrator
 
 
 # ---- rank-parallel prolongation ----------------------------------------------------------
@@ -677,10 +699,11 @@ class LinearForm:
         m = MassIntegrator(1.0, IntRules.Get(fes.dim, 2 * fes.p))
         m.AssemblePA(dev, fes)
         R = fes.GetElementRestriction(dev)
+        vd = getattr(fes, "vdim", 1)
         xe = dev.empty(R.Height()).fill_(1.0)
         ye = dev.zeros(R.Height())
-        m.AddMultPA(xe, ye)
-        b = dev.empty(fes.ndofs)
+        m.AddMultPA(xe, ye, vdim=vd)
+        b = dev.empty(fes.ndofs * vd)
         R.MultTranspose(ye, b)
         dev.sync()
         m.close()

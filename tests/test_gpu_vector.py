@@ -90,3 +90,41 @@ def test_vector_operator_and_pcg(dev, name):
     assert cg.GetConverged() and abs(cg.GetNumIterations() - int(g["pcg_iters"][0])) <= 1
     assert relerr(host(X), g["X_sol"]) < 1e-6
     a.close(); it.close(); R.close()
+
+
+@pytest.mark.parametrize("name", ["vec_diff3d_p4_n2_byvdim", "vec_mass3d_p3_n2_bynodes", "vec_bp6_3d_p3_n3_byvdim",
+                                  "vec_diff3d_p5_n2_curved"])
+def test_vector_end_to_end_own_tables(dev, name):
+    """mesh -> vector space -> operator -> PCG with the library's own host tables"""
+    import mfem_b200 as m
+    g = load_golden(name)
+    p, n = int(g["p"][0]), int(g["n"][0])
+    mesh = m.Mesh.MakeCartesian3D(n, n, n)
+    if int(g["curved"][0]):
+        mesh.SetCurvature(3)
+        mesh.Transform(m.curve_map)
+    fes = m.FiniteElementSpace(mesh, m.H1_FECollection(p, 3), vdim=3,
+                               ordering="byVDIM" if int(g["byvdim"][0]) else "byNODES")
+    gll = bool(g["is_gll"][0])
+    ir = m.IntegrationRules(gll).Get(3, 2 * p - 1 if gll else 2 * p + 3)
+    it = (m.VectorMassIntegrator if g["is_mass"][0] else m.VectorDiffusionIntegrator)(1.0, ir)
+    a = m.BilinearForm(dev, fes)
+    a.AddDomainIntegrator(it)
+    a.Assemble()
+    nv = fes.GetVSize()
+    assert nv == len(g["x"])
+    ess = fes.GetEssentialTrueDofs()
+    assert np.array_equal(ess, g["ess_tdof_list"])
+    y = dev.empty(nv)
+    a.Mult(dev.to_device(g["x"]), y)
+    assert relerr(host(y), g["y"]) < TOL
+    b = dev.to_device(g["b"])
+    A, _, B = a.FormLinearSystem(ess, dev.zeros(nv), b)
+    M = m.OperatorJacobiSmoother(a, ess)
+    cg = m.CGSolver()
+    cg.SetRelTol(float(g["pcg_rtol"][0])); cg.SetMaxIter(2000); cg.SetOperator(A); cg.SetPreconditioner(M)
+    X = dev.zeros(nv)
+    cg.Mult(B, X)
+    assert abs(cg.GetNumIterations() - int(g["pcg_iters"][0])) <= 1
+    assert relerr(host(X), g["X_sol"]) < 1e-6
+    a.close(); it.close()
