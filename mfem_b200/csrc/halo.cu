@@ -206,7 +206,18 @@ __device__ __forceinline__ void p2p_wait(const unsigned long long *flags, int n_
 {
    if (threadIdx.x < n_nbr)
    {
-      while (ld_acquire_sys(flags + threadIdx.x) < epoch) { __nanosleep(64); }
+      // bounded: a neighbour that never publishes (crashed rank, mismatched call sequence) must
+      // become a CUDA error on this rank, not a hung GPU (~20 s at 256 ns per poll)
+      unsigned int polls = 0;
+      while (ld_acquire_sys(flags + threadIdx.x) < epoch)
+      {
+         __nanosleep(256);
+         if (++polls > 80000000u)
+         {
+            printf("b200fem halo: neighbour %d did not publish epoch %llu\n", (int)threadIdx.x, epoch);
+            __trap();
+         }
+      }
    }
    __syncthreads();
 }
