@@ -17,33 +17,12 @@ int pa_apply_3d_diffusion_2(b2f_pa *pa, const double *x, double *y, const int *i
       constexpr int K = B2F_KIND_DIFFUSION;
       switch (variant())
       {
-         case 1: return launch_3d<K, 5, 6, 6, 0, 1, 1>(pa, x, y, idx);
-         case 2: return launch_3d<K, 5, 6, 2, 1, 6, 1>(pa, x, y, idx);
-         case 3: return launch_3d<K, 5, 6, 2, 1, 5, 1>(pa, x, y, idx);
-         case 4: return launch_3d<K, 5, 6, 3, 1, 3, 1>(pa, x, y, idx);
-         case 5: return launch_3d<K, 5, 6, 4, 1, 3, 1>(pa, x, y, idx);
-         case 6: return launch_3d<K, 5, 6, 1, 1, 8, 1>(pa, x, y, idx);
-         case 30: return launch_3d_eo<K, 5, 6, 3, 4>(pa, x, y, idx);
-         case 31: return launch_3d_eo<K, 5, 6, 3, 3>(pa, x, y, idx);
-         case 32: return launch_3d_eo<K, 5, 6, 4, 3>(pa, x, y, idx);
-         case 33: return launch_3d_eo<K, 5, 6, 6, 2>(pa, x, y, idx);
-         case 34: return launch_3d_eo<K, 5, 6, 2, 5>(pa, x, y, idx);
-         case 35: return launch_3d_eo<K, 5, 6, 3, 5>(pa, x, y, idx);
-         case 40: return launch_3d_eo<K, 5, 6, 3, 4, 1, true>(pa, x, y, idx);
-         case 41: return launch_3d_eo<K, 5, 6, 3, 3, 1, true>(pa, x, y, idx);
+         // kept selectable for A/B measurements (tools/opbench.py --variants vN)
+         case 1: return launch_3d<K, 5, 6, 6, 0, 1, 1>(pa, x, y, idx);          // general kernel, TMA slab, scalar LDS
+         case 4: return launch_3d<K, 5, 6, 3, 1, 3, 1>(pa, x, y, idx);          // general kernel, 128-bit rows, 3 el/CTA
+         case 25: return launch_3d_pipe<K, 5, 6, 4, 3>(pa, x, y, idx);          // persistent pipelined, plain contraction
+         case 40: return launch_3d_eo<K, 5, 6, 3, 4, 1, true>(pa, x, y, idx);   // persistent pipelined, even-odd
          case 42: return launch_3d_eo<K, 5, 6, 4, 3, 1, true>(pa, x, y, idx);
-         case 43: return launch_3d_eo<K, 5, 6, 6, 2, 1, true>(pa, x, y, idx);
-         case 44: return launch_3d_eo<K, 5, 6, 5, 2, 1, true>(pa, x, y, idx);
-         case 45: return launch_3d_eo<K, 5, 6, 5, 2>(pa, x, y, idx);
-         case 46: return launch_3d_eo<K, 5, 6, 2, 5, 1, true>(pa, x, y, idx);
-         case 20: return launch_3d_pipe<K, 5, 6, 6, 1>(pa, x, y, idx);
-         case 21: return launch_3d_pipe<K, 5, 6, 6, 2>(pa, x, y, idx);
-         case 22: return launch_3d_pipe<K, 5, 6, 3, 1>(pa, x, y, idx);
-         case 23: return launch_3d_pipe<K, 5, 6, 3, 4>(pa, x, y, idx);
-         case 24: return launch_3d_pipe<K, 5, 6, 4, 1>(pa, x, y, idx);
-         case 25: return launch_3d_pipe<K, 5, 6, 4, 3>(pa, x, y, idx);
-         case 26: return launch_3d_pipe<K, 5, 6, 8, 1>(pa, x, y, idx);
-         case 27: return launch_3d_pipe<K, 5, 6, 2, 1>(pa, x, y, idx);
          default: break;
       }
    }
