@@ -91,7 +91,7 @@ class PAData
 {
 public:
    b2f_pa *pa = nullptr;
-   int ne = 0, dof = 0;
+   int ne = 0, dof = 0, vdim = 1;
    mutable DeviceVector xe, ye;
    ~PAData() { b2f_pa_destroy(pa); }
 
@@ -117,6 +117,7 @@ public:
       d_nodes.Upload(nodesE);
       ne = fes.GetNE();
       dof = fe.GetDof();
+      vdim = fes.GetVDim();
       b2f_pa_destroy(pa);
       pa = nullptr;
       B200_CHECK(b2f_pa_setup_from_nodes(Context::Get().get(), kind, mesh.Dimension(), maps.ndof,
@@ -128,14 +129,27 @@ public:
    {
       xe.Upload(x);
       ye.Upload(y); // AddMultPA accumulates into y (fem/bilininteg.hpp:78)
-      B200_CHECK(b2f_pa_add_mult(pa, xe.Ptr(), ye.Ptr()));
+      B200_CHECK(b2f_pa_add_mult_vec(pa, vdim, xe.Ptr(), ye.Ptr())); // E-vector (dofs, vdim, NE)
       ye.Download(y);
    }
    void AddDiagonal(mfem::Vector &diag) const
    {
-      ye.Upload(diag);
+      if (vdim == 1)
+      {
+         ye.Upload(diag);
+         B200_CHECK(b2f_pa_assemble_diagonal(pa, ye.Ptr()));
+         ye.Download(diag);
+         return;
+      }
+      // vector integrators: the scalar element diagonal added to every component
+      mfem::Vector d(ne * dof);
+      d = 0.0;
+      ye.Upload(d);
       B200_CHECK(b2f_pa_assemble_diagonal(pa, ye.Ptr()));
-      ye.Download(diag);
+      ye.Download(d);
+      for (int e = 0; e < ne; e++)
+         for (int c = 0; c < vdim; c++)
+            for (int i = 0; i < dof; i++) { diag(i + dof * (c + vdim * e)) += d(i + dof * e); }
    }
 };
 
@@ -185,6 +199,44 @@ public:
    b2f_pa *Handle() const { return data.pa; }
 };
 
+/// seam 3 for vector spaces (CEED BP4/BP6): drop-in for mfem::VectorDiffusionIntegrator.
+class VectorDiffusionIntegrator : public mfem::VectorDiffusionIntegrator
+{
+   PAData data;
+public:
+   using mfem::VectorDiffusionIntegrator::VectorDiffusionIntegrator;
+   using mfem::BilinearFormIntegrator::AssemblePA;
+   void AssemblePA(const mfem::FiniteElementSpace &fes) override
+   {
+      const mfem::FiniteElement &fe = *fes.GetTypicalFE();
+      const mfem::IntegrationRule *ir = GetIntegrationRule();
+      if (!ir) { ir = &mfem::DiffusionIntegrator::GetRule(fe, fe); }
+      data.Assemble(0, fes, *ir, ConstantOf(Q));
+   }
+   void AddMultPA(const mfem::Vector &x, mfem::Vector &y) const override { data.AddMult(x, y); }
+   void AssembleDiagonalPA(mfem::Vector &diag) override { data.AddDiagonal(diag); }
+   b2f_pa *Handle() const { return data.pa; }
+};
+
+/// seam 3 for vector spaces (CEED BP2): drop-in for mfem::VectorMassIntegrator.
+class VectorMassIntegrator : public mfem::VectorMassIntegrator
+{
+   PAData data;
+public:
+   using mfem::VectorMassIntegrator::VectorMassIntegrator;
+   using mfem::BilinearFormIntegrator::AssemblePA;
+   void AssemblePA(const mfem::FiniteElementSpace &fes) override
+   {
+      const mfem::FiniteElement &fe = *fes.GetTypicalFE();
+      const mfem::IntegrationRule *ir = GetIntegrationRule();
+      if (!ir) { ir = &mfem::MassIntegrator::GetRule(fe, fe, *fes.GetMesh()->GetTypicalElementTransformation()); }
+      data.Assemble(1, fes, *ir, ConstantOf(Q));
+   }
+   void AddMultPA(const mfem::Vector &x, mfem::Vector &y) const override { data.AddMult(x, y); }
+   void AssembleDiagonalPA(mfem::Vector &diag) override { data.AddDiagonal(diag); }
+   b2f_pa *Handle() const { return data.pa; }
+};
+
 /// seam 1: the fused PA operator of a BilinearForm whose domain integrators are b200 ones.
 class PAOperator : public mfem::Operator
 {
@@ -208,14 +260,16 @@ public:
       MFEM_VERIFY(R, "tensor-product H1 space expected");
       const int dof = fes.GetTypicalFE()->GetDof();
       // MFEM's own tables (fem/restriction.hpp:104-106) are handed over unchanged
-      B200_CHECK(b2f_restriction_create(Context::Get().get(), fes.GetNE(), dof, fes.GetNDofs(), 1, 0,
-                                        R->GatherMap().HostRead(), R->Offsets().HostRead(),
-                                        R->Indices().HostRead(), &restr));
+      B200_CHECK(b2f_restriction_create(Context::Get().get(), fes.GetNE(), dof, fes.GetNDofs(), fes.GetVDim(),
+                                        fes.GetOrdering() == Ordering::byVDIM, R->GatherMap().HostRead(),
+                                        R->Offsets().HostRead(), R->Indices().HostRead(), &restr));
       for (BilinearFormIntegrator *bfi : *a.GetDBFI())
       {
          if (auto d = dynamic_cast<b200::DiffusionIntegrator *>(bfi)) { integ.push_back(d->Handle()); }
          else if (auto m = dynamic_cast<b200::MassIntegrator *>(bfi)) { integ.push_back(m->Handle()); }
-         else { MFEM_ABORT("PAOperator: only b200::DiffusionIntegrator / MassIntegrator are supported"); }
+         else if (auto vd = dynamic_cast<b200::VectorDiffusionIntegrator *>(bfi)) { integ.push_back(vd->Handle()); }
+         else if (auto vm = dynamic_cast<b200::VectorMassIntegrator *>(bfi)) { integ.push_back(vm->Handle()); }
+         else { MFEM_ABORT("PAOperator: only the b200 integrators are supported"); }
       }
       B200_CHECK(b2f_operator_create(Context::Get().get(), restr, integ.data(), (int)integ.size(),
                                      ess_tdof_list.HostRead(), ess_tdof_list.Size(), &op));

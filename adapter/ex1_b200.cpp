@@ -26,7 +26,7 @@ static double relerr(const Vector &a, const Vector &b)
 
 int main(int argc, char *argv[])
 {
-   int order = 3, n = 6, ref = 0;
+   int order = 3, n = 6, ref = 0, vdim = 1;
    const char *mesh_file = "";
    const char *kind = "diffusion";
    OptionsParser args(argc, argv);
@@ -35,6 +35,7 @@ int main(int argc, char *argv[])
    args.AddOption(&mesh_file, "-m", "--mesh", "mesh file (instead of the Cartesian mesh)");
    args.AddOption(&ref, "-r", "--refine", "uniform refinements of the mesh file");
    args.AddOption(&kind, "-k", "--kind", "diffusion | mass");
+   args.AddOption(&vdim, "-vd", "--vdim", "vector dimension (3: CEED BP2/BP4 style vector problem, byVDIM)");
    args.Parse();
    if (!args.Good()) { args.PrintUsage(std::cout); return 1; }
    Device device("cpu"); // MFEM itself stays on the host ("host-MFEM" mode)
@@ -44,7 +45,7 @@ int main(int argc, char *argv[])
    for (int l = 0; l < ref; l++) { mesh.UniformRefinement(); }
    const int dim = mesh.Dimension();
    H1_FECollection fec(order, dim);
-   FiniteElementSpace fes(&mesh, &fec);
+   FiniteElementSpace fes(&mesh, &fec, vdim, vdim > 1 ? Ordering::byVDIM : Ordering::byNODES);
    Array<int> ess_bdr(mesh.bdr_attributes.Max()), ess;
    ess_bdr = 1;
    fes.GetEssentialTrueDofs(ess_bdr, ess);
@@ -57,7 +58,12 @@ int main(int argc, char *argv[])
    {
       BilinearForm *a = new BilinearForm(&fes);
       a->SetAssemblyLevel(AssemblyLevel::PARTIAL);
-      if (mass) { a->AddDomainIntegrator(b200 ? (BilinearFormIntegrator *)new b200::MassIntegrator(one) : new MassIntegrator(one)); }
+      if (vdim > 1)
+      {
+         if (mass) { a->AddDomainIntegrator(b200 ? (BilinearFormIntegrator *)new b200::VectorMassIntegrator(one) : new VectorMassIntegrator(one)); }
+         else { a->AddDomainIntegrator(b200 ? (BilinearFormIntegrator *)new b200::VectorDiffusionIntegrator(one) : new VectorDiffusionIntegrator(one)); }
+      }
+      else if (mass) { a->AddDomainIntegrator(b200 ? (BilinearFormIntegrator *)new b200::MassIntegrator(one) : new MassIntegrator(one)); }
       else { a->AddDomainIntegrator(b200 ? (BilinearFormIntegrator *)new b200::DiffusionIntegrator(one) : new DiffusionIntegrator(one)); }
       a->Assemble();
       return a;
@@ -89,9 +95,15 @@ int main(int argc, char *argv[])
    check("seam 1: b200::PAOperator::AssembleDiagonal", relerr(d, d_ref), 1e-12);
 
    // the linear system of ex1: b = (1, phi_i), x = 0 on the boundary
-   LinearForm b(&fes);
-   b.AddDomainIntegrator(new DomainLFIntegrator(one));
-   b.Assemble();
+   Vector b(N);
+   if (vdim == 1)
+   {
+      LinearForm lf(&fes);
+      lf.AddDomainIntegrator(new DomainLFIntegrator(one));
+      lf.Assemble();
+      b = lf;
+   }
+   else { b.Randomize(2); }
    GridFunction u(&fes);
    u = 0.0;
    OperatorPtr A;

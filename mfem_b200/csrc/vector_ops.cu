@@ -193,6 +193,93 @@ pcg_update_kernel(int64_t n, PcgState *st, double *x, const double *__restrict__
    grid_sum(s, partials, counter, &st->dot_tmp);
 }
 
+// 128-bit form of the same update (all vectors 16-byte aligned): two entries per access
+template <bool PREC>
+__global__ void __launch_bounds__(VT)
+pcg_update2_kernel(int64_t n, PcgState *st, double *x, const double *__restrict__ d, double *r,
+                   const double *__restrict__ q, const double *__restrict__ dinv, double *z,
+                   double *partials, unsigned int *counter)
+{
+   if (st->done) { return; }
+   const double alpha = st->nom / st->den;
+   double s = 0.0;
+   const int64_t n2 = n >> 1;
+   double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r);
+   double2 *z2 = reinterpret_cast<double2 *>(z);
+   const double2 *d2 = reinterpret_cast<const double2 *>(d), *q2 = reinterpret_cast<const double2 *>(q);
+   const double2 *p2 = reinterpret_cast<const double2 *>(dinv);
+   for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * VT)
+   {
+      double2 xv = x2[i], rv = r2[i];
+      const double2 dv = d2[i], qv = q2[i];
+      xv.x = xv.x + alpha * dv.x; xv.y = xv.y + alpha * dv.y;
+      rv.x = rv.x + (-alpha) * qv.x; rv.y = rv.y + (-alpha) * qv.y;
+      x2[i] = xv;
+      r2[i] = rv;
+      if (PREC)
+      {
+         const double2 pv = p2[i];
+         double2 zv;
+         zv.x = 0.0 + pv.x * rv.x; zv.y = 0.0 + pv.y * rv.y;
+         z2[i] = zv;
+         s = fma(rv.x, zv.x, s);
+         s = fma(rv.y, zv.y, s);
+      }
+      else
+      {
+         s = fma(rv.x, rv.x, s);
+         s = fma(rv.y, rv.y, s);
+      }
+   }
+   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+   {
+      const int64_t i = n - 1;
+      x[i] = x[i] + alpha * d[i];
+      const double ri = r[i] + (-alpha) * q[i];
+      r[i] = ri;
+      if (PREC) { const double zi = 0.0 + dinv[i] * ri; z[i] = zi; s = fma(ri, zi, s); }
+      else { s = fma(ri, ri, s); }
+   }
+   grid_sum(s, partials, counter, &st->dot_tmp);
+}
+
+__global__ void __launch_bounds__(VT)
+pcg_direction2_kernel(int64_t n, const PcgState *st, const double *__restrict__ z, double *d)
+{
+   if (st->done) { return; }
+   const double beta = st->beta;
+   const int64_t n2 = n >> 1;
+   const double2 *z2 = reinterpret_cast<const double2 *>(z);
+   double2 *d2 = reinterpret_cast<double2 *>(d);
+   for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * VT)
+   {
+      const double2 zv = z2[i];
+      double2 dv = d2[i];
+      dv.x = zv.x + beta * dv.x; dv.y = zv.y + beta * dv.y;
+      d2[i] = dv;
+   }
+   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) { d[n - 1] = z[n - 1] + beta * d[n - 1]; }
+}
+
+__global__ void __launch_bounds__(VT)
+dot2_kernel(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
+            double *partials, unsigned int *counter, double *out)
+{
+   double s0 = 0.0, s1 = 0.0;
+   const int64_t n2 = n >> 1;
+   const double2 *x2 = reinterpret_cast<const double2 *>(x), *y2 = reinterpret_cast<const double2 *>(y);
+   for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * VT)
+   {
+      const double2 a = x2[i], b = y2[i];
+      s0 = fma(a.x, b.x, s0);
+      s1 = fma(a.y, b.y, s1);
+   }
+   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) { s0 = fma(x[n - 1], y[n - 1], s0); }
+   grid_sum(s0 + s1, partials, counter, out);
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 // scalar control flow after betanom = (r, z) is known (solvers.cpp:963-1000)
 __global__ void pcg_after_betanom_kernel(PcgState *st, double *history, int history_cap)
 {
@@ -301,6 +388,12 @@ int dot_to_device(b2f_ctx *ctx, int64_t n, const double *x, const double *y, dou
 {
    unsigned grid = stream_grid(ctx, n, 8);
    if ((int)grid > ctx->n_partials) { grid = ctx->n_partials; }
+   if (aligned16(x) && aligned16(y) && n >= 2)
+   {
+      dot2_kernel<<<grid, VT, 0, ctx->stream>>>(n, x, y, ctx->d_partials, ctx->d_counter, d_out);
+      B2F_LAUNCH_CHECK(ctx);
+      return B2F_OK;
+   }
    dot_kernel<<<grid, VT, 0, ctx->stream>>>(n, x, y, ctx->d_partials, ctx->d_counter, d_out);
    B2F_LAUNCH_CHECK(ctx);
    return B2F_OK;
@@ -366,6 +459,21 @@ int pcg_update(b2f_ctx *ctx, void *state, int64_t n, double *x, const double *d,
 {
    unsigned grid = stream_grid(ctx, n, 4);
    if ((int)grid > ctx->n_partials) { grid = ctx->n_partials; }
+   if (aligned16(x) && aligned16(d) && aligned16(r) && aligned16(q) && aligned16(dinv) && aligned16(z) && n >= 2)
+   {
+      if (dinv)
+      {
+         pcg_update2_kernel<true><<<grid, VT, 0, ctx->stream>>>(n, (PcgState *)state, x, d, r, q, dinv, z,
+                                                                ctx->d_partials, ctx->d_counter);
+      }
+      else
+      {
+         pcg_update2_kernel<false><<<grid, VT, 0, ctx->stream>>>(n, (PcgState *)state, x, d, r, q, dinv, z,
+                                                                 ctx->d_partials, ctx->d_counter);
+      }
+      B2F_LAUNCH_CHECK(ctx);
+      return B2F_OK;
+   }
    pcg_update_kernel<<<grid, VT, 0, ctx->stream>>>(n, (PcgState *)state, x, d, r, q, dinv, z,
                                                    ctx->d_partials, ctx->d_counter);
    B2F_LAUNCH_CHECK(ctx);
@@ -381,6 +489,12 @@ int pcg_after_betanom(b2f_ctx *ctx, void *state, double *history, int history_ca
 
 int pcg_direction(b2f_ctx *ctx, void *state, int64_t n, const double *z, double *d)
 {
+   if (aligned16(z) && aligned16(d) && n >= 2)
+   {
+      pcg_direction2_kernel<<<stream_grid(ctx, n, 4), VT, 0, ctx->stream>>>(n, (PcgState *)state, z, d);
+      B2F_LAUNCH_CHECK(ctx);
+      return B2F_OK;
+   }
    pcg_direction_kernel<<<stream_grid(ctx, n, 4), VT, 0, ctx->stream>>>(n, (PcgState *)state, z, d);
    B2F_LAUNCH_CHECK(ctx);
    return B2F_OK;

@@ -27,7 +27,8 @@ def test_adapter_fails_loudly_without_a_gpu():
 @needs_exe
 @pytest.mark.gpu
 @pytest.mark.parametrize("args", [["-n", "6", "-o", "3"], ["-n", "4", "-o", "4"], ["-n", "3", "-o", "8"],
-                                  ["-n", "5", "-o", "2", "-k", "mass"], ["-n", "8", "-o", "1"]])
+                                  ["-n", "5", "-o", "2", "-k", "mass"], ["-n", "8", "-o", "1"],
+                                  ["-n", "4", "-o", "3", "-vd", "3"], ["-n", "3", "-o", "4", "-vd", "3", "-k", "mass"]])
 def test_adapter_matches_mfem_at_all_seams(args):
     r = subprocess.run([EXE] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
     out = r.stdout.decode(errors="replace")
