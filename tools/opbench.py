@@ -66,13 +66,15 @@ def run_case(bp, p, n, variants, reps):
     ab = (k * ir.nq1d ** 3 * 8 + 4 * (p + 1) ** 3) * fes.ne + 16 * N  # D and indices once per element
     print(f"BP{bp} p={p} n={n}: NE={fes.ne} dofs={N} algorithmic bytes/apply={ab/1e9:.3f} GB", flush=True)
     for v in variants:
-        for key in ("B2F_VARIANT", "B2F_PF", "B2F_NEB_CAND", "B2F_GENERAL_KERNEL"):
+        for key in ("B2F_VARIANT", "B2F_PF", "B2F_NEB_CAND", "B2F_GENERAL_KERNEL", "B2F_PERSIST"):
             os.environ.pop(key, None)
         for kv in v.split("+"):
             if kv.startswith("c"):
                 os.environ["B2F_NEB_CAND"] = kv[1:]
             elif kv.startswith("pf"):
                 os.environ["B2F_PF"] = kv[2:]
+            elif kv == "persist":
+                os.environ["B2F_PERSIST"] = "1"
             elif kv == "g":
                 os.environ["B2F_GENERAL_KERNEL"] = "1"
             elif kv.startswith("v"):
