@@ -9,13 +9,28 @@ int pa_apply_3d_mass_2(b2f_pa *, const double *, double *, const int *, double *
 int pa_apply_3d_mass_6(b2f_pa *, const double *, double *, const int *, double *);
 int pa_apply_3d_mass_8(b2f_pa *, const double *, double *, const int *, double *);
 
+int pa_apply_generic(b2f_pa *pa, const double *x, double *y, const int *idx); // pa_apply_generic.cu
+
+// (D1D, Q1D) covered by the specialised kernels
+static bool in_tables(const b2f_pa *pa)
+{
+   const int D = pa->d1d, Q = pa->q1d;
+   return D >= 2 && D <= 9 && Q >= D && Q <= D + 2;
+}
+
 int pa_apply(b2f_pa *pa, const double *x, double *y, const int *idx, double *dot_acc)
 {
    if (pa->ne == 0) { return B2F_OK; }
-   if (!pa->symmetric)
+   if (!pa->symmetric || !in_tables(pa))
    {
-      set_error("non-symmetric matrix coefficients have no apply kernel yet");
-      return B2F_ERR_UNSUPPORTED;
+      // full-matrix coefficients and sizes outside the tables: run-time-sized kernel
+      if (dot_acc || pa->vd > 1 || pa->rb != 0 || pa->re >= 0)
+      {
+         set_error("pa_apply: this form needs the even-odd kernel (symmetric coefficient, D1D = 2..9, "
+                   "Q1D = D1D..D1D+2)");
+         return B2F_ERR_UNSUPPORTED;
+      }
+      return pa_apply_generic(pa, x, y, idx);
    }
    if (dot_acc && !pa_apply_has_fused_dot(pa))
    {

@@ -13,7 +13,7 @@ namespace b2f
 {
 
 __global__ void __launch_bounds__(128)
-diffusion_diag_3d_kernel(int D1D, int Q1D, const double *__restrict__ Bg,
+diffusion_diag_3d_kernel(int D1D, int Q1D, int ncomp, const double *__restrict__ Bg,
                          const double *__restrict__ Gg, const double *__restrict__ Dq,
                          double *__restrict__ Y)
 {
@@ -23,14 +23,16 @@ diffusion_diag_3d_kernel(int D1D, int Q1D, const double *__restrict__ Bg,
    double *QDD = QQD + Q1D * Q1D * D1D;   // [qx][dy][dz]
    const int64_t e = blockIdx.x;
    const int Q3 = Q1D * Q1D * Q1D, D3 = D1D * D1D * D1D;
-   const double *De = Dq + e * (int64_t)(6 * Q3);
+   const double *De = Dq + e * (int64_t)(ncomp * Q3);
    double *Ye = Y + e * (int64_t)D3;
    for (int i = threadIdx.x; i < Q1D * D1D; i += blockDim.x) { sB[i] = Bg[i]; sG[i] = Gg[i]; }
    __syncthreads();
    for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 3; ++j)
       {
-         const int k = j >= i ? 3 - (3 - i) * (2 - i) / 2 + j : 3 - (3 - j) * (2 - j) / 2 + i;
+         // symmetric: 6 components; full matrix: row-major i*3+j (kernels.hpp:300-318)
+         const int k = ncomp == 9 ? i * 3 + j
+                       : j >= i ? 3 - (3 - i) * (2 - i) / 2 + j : 3 - (3 - j) * (2 - j) / 2 + i;
          for (int t = threadIdx.x; t < Q1D * Q1D * D1D; t += blockDim.x)
          {
             const int dz = t % D1D, qy = (t / D1D) % Q1D, qx = t / (D1D * Q1D);
@@ -126,7 +128,7 @@ mass_diag_3d_kernel(int D1D, int Q1D, const double *__restrict__ Bg,
 }
 
 __global__ void __launch_bounds__(128)
-diag_2d_kernel(int kind, int D1D, int Q1D, const double *__restrict__ Bg,
+diag_2d_kernel(int kind, int D1D, int Q1D, int ncomp_in, const double *__restrict__ Bg,
                const double *__restrict__ Gg, const double *__restrict__ Dq,
                double *__restrict__ Y)
 {
@@ -135,7 +137,7 @@ diag_2d_kernel(int kind, int D1D, int Q1D, const double *__restrict__ Bg,
    double *QD0 = sG + Q1D * D1D, *QD1 = QD0 + Q1D * D1D, *QD2 = QD1 + Q1D * D1D; // [qx][dy]
    const int64_t e = blockIdx.x;
    const int Q2 = Q1D * Q1D, D2 = D1D * D1D;
-   const int ncomp = kind == B2F_KIND_MASS ? 1 : 3;
+   const int ncomp = kind == B2F_KIND_MASS ? 1 : ncomp_in;
    const double *De = Dq + e * (int64_t)(ncomp * Q2);
    double *Ye = Y + e * (int64_t)D2;
    for (int i = threadIdx.x; i < Q1D * D1D; i += blockDim.x) { sB[i] = Bg[i]; sG[i] = Gg[i]; }
@@ -151,9 +153,12 @@ diag_2d_kernel(int kind, int D1D, int Q1D, const double *__restrict__ Bg,
          if (kind == B2F_KIND_MASS) { s0 += b * b * De[q]; }
          else
          {
-            const double D00 = De[q], D10 = De[q + Q2], D11 = De[q + 2 * Q2];
+            // (11, 21, 12, 22) for a full matrix, (11, 21, 22) when symmetric (kernels.hpp:130-140)
+            const double D00 = De[q], D10 = De[q + Q2];
+            const double D01 = ncomp == 4 ? De[q + 2 * Q2] : D10;
+            const double D11 = ncomp == 4 ? De[q + 3 * Q2] : De[q + 2 * Q2];
             s0 += b * b * D00;
-            s1 += b * g * (D10 + D10);
+            s1 += b * g * (D01 + D10);
             s2 += g * g * D11;
          }
       }
@@ -183,11 +188,6 @@ int pa_diag(b2f_pa *pa, double *diag_e)
 {
    b2f_ctx *ctx = pa->ctx;
    if (pa->ne == 0) { return B2F_OK; }
-   if (!pa->symmetric)
-   {
-      set_error("non-symmetric matrix coefficients have no diagonal kernel yet");
-      return B2F_ERR_UNSUPPORTED;
-   }
    const int D = pa->d1d, Q = pa->q1d;
    const unsigned grid = (unsigned)pa->ne;
    if (pa->dim == 3)
@@ -195,7 +195,7 @@ int pa_diag(b2f_pa *pa, double *diag_e)
       const size_t smem = sizeof(double) * (2 * Q * D + Q * Q * D + Q * D * D);
       if (pa->kind == B2F_KIND_DIFFUSION)
       {
-         diffusion_diag_3d_kernel<<<grid, 128, smem, ctx->stream>>>(D, Q, pa->d_B, pa->d_G,
+         diffusion_diag_3d_kernel<<<grid, 128, smem, ctx->stream>>>(D, Q, pa->ncomp, pa->d_B, pa->d_G,
                                                                     pa->data, diag_e);
       }
       else
@@ -206,7 +206,7 @@ int pa_diag(b2f_pa *pa, double *diag_e)
    else
    {
       const size_t smem = sizeof(double) * (5 * Q * D);
-      diag_2d_kernel<<<grid, 128, smem, ctx->stream>>>(pa->kind, D, Q, pa->d_B, pa->d_G,
+      diag_2d_kernel<<<grid, 128, smem, ctx->stream>>>(pa->kind, D, Q, pa->ncomp, pa->d_B, pa->d_G,
                                                        pa->data, diag_e);
    }
    B2F_LAUNCH_CHECK(ctx);

@@ -62,6 +62,12 @@ CASES = {
     "vec_mass3d_p4_n2_byvdim": dict(dim=3, n=2, p=4, kind="mass", vdim=3, byvdim=1),
     "vec_bp6_3d_p3_n3_byvdim": dict(dim=3, n=3, p=3, kind="diffusion", quad="gll", vdim=3, byvdim=1),
     "vec_diff3d_p5_n2_curved": dict(dim=3, n=2, p=5, kind="diffusion", vdim=3, byvdim=1, curved=1),
+    # non-symmetric matrix coefficient (dim*dim quadrature-data components)
+    "nonsym_diff3d_p2_n2": dict(dim=3, n=2, p=2, kind="diffusion", nonsym=1),
+    "nonsym_diff3d_p4_n2_curved": dict(dim=3, n=2, p=4, kind="diffusion", nonsym=1, curved=1),
+    "nonsym_diff3d_p7_n2": dict(dim=3, n=2, p=7, kind="diffusion", nonsym=1),
+    "nonsym_diff2d_p3_n3_curved": dict(dim=2, n=3, p=3, kind="diffusion", nonsym=1, curved=1),
+    "nonsym_bp5_3d_p3_n2": dict(dim=3, n=2, p=3, kind="diffusion", quad="gll", nonsym=1),
 }
 
 
@@ -79,8 +85,9 @@ def main():
         np.savez_compressed(path, **d)
         sz = os.path.getsize(path)
         total += sz
+        its = int(d["pcg_iters"][0]) if "pcg_iters" in d else -1
         print(f"{name:28s} NE={int(d['NE'][0]):4d} ndofs={int(d['ndofs'][0]):6d} "
-              f"pcg_iters={int(d['pcg_iters'][0]):4d} {sz/1024:8.1f} KiB")
+              f"pcg_iters={its:4d} {sz/1024:8.1f} KiB")
     print(f"total {total/1e6:.2f} MB")
 
 

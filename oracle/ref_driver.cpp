@@ -437,6 +437,75 @@ static int do_dump_vector(const Args &A, const char *out)
    return 0;
 }
 
+// Non-symmetric matrix coefficient (DiffusionIntegrator(MatrixCoefficient&), symmetric = false:
+// dim*dim quadrature-data components, fem/integ/bilininteg_diffusion_pa.cpp:165).
+static void nonsym_coeff(const Vector &x, DenseMatrix &K)
+{
+   const int d = x.Size();
+   K.SetSize(d);
+   for (int i = 0; i < d; i++)
+      for (int j = 0; j < d; j++)
+      {
+         K(i, j) = (i == j ? 2.0 + 0.5 * x(i) : 0.0) + 0.3 * (i + 1) * x((i + j) % d) - 0.2 * (j + 1) * x(j);
+      }
+}
+
+static int do_dump_nonsym(const Args &A, const char *out)
+{
+   Problem P(A);
+   Dump D(out);
+   const int dim = P.dim;
+   MatrixFunctionCoefficient MQ(dim, nonsym_coeff);
+   BilinearForm a(P.fes);
+   a.SetAssemblyLevel(AssemblyLevel::PARTIAL);
+   auto *bfi = new DiffusionIntegrator(MQ, P.ir);
+   a.AddDomainIntegrator(bfi);
+   a.Assemble();
+   FiniteElementSpace &fes = *P.fes;
+   const FiniteElement &fe = *fes.GetTypicalFE();
+   const DofToQuad &maps = fe.GetDofToQuad(*P.ir, DofToQuad::TENSOR);
+   const int D1D = maps.ndof, Q1D = maps.nqpt, NE = fes.GetNE(), ndofs = fes.GetNDofs();
+   D.scalar("dim", dim); D.scalar("n", P.n); D.scalar("p", P.p);
+   D.scalar("D1D", D1D); D.scalar("Q1D", Q1D); D.scalar("NE", NE); D.scalar("ndofs", ndofs);
+   D.scalar("curved", (int)P.curved);
+   auto R = dynamic_cast<const ElementRestriction *>(
+               fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC));
+   D.ints("gather_map", R->GatherMap());
+   D.ints("offsets", R->Offsets());
+   D.ints("indices", R->Indices());
+   D.dbls("B", maps.B); D.dbls("G", maps.G);
+   D.dbls("W", P.ir->GetWeights());
+   const GeometricFactors *geom = P.mesh.GetGeometricFactors(*P.ir, GeometricFactors::JACOBIANS);
+   D.dbls("J", geom->J);
+   // the coefficient at the quadrature points, as AssemblePA evaluates it (dim*dim, NQ, NE)
+   QuadratureSpace qs(P.mesh, *P.ir);
+   CoefficientVector cv(qs, CoefficientStorage::FULL);
+   cv.ProjectTranspose(MQ); // what AssemblePA does (bilininteg_diffusion_pa.cpp:159): row-major entries
+   D.dbls("coeff_full", cv);
+   D.scalar("pa_symmetric", (int)bfi->symmetric);
+   D.dbls("pa_data", bfi->pa_data);
+   Vector x(ndofs); x.Randomize(1);
+   D.dbls("x", x);
+   Vector xE(R->Height()), yE(R->Height());
+   R->Mult(x, xE);
+   D.dbls("xE", xE);
+   yE = 0.0;
+   bfi->AddMultPA(xE, yE);
+   D.dbls("yE", yE);
+   Vector y(ndofs);
+   a.Mult(x, y);
+   D.dbls("y", y);
+   Vector diagE(R->Height()); diagE = 0.0;
+   bfi->AssembleDiagonalPA(diagE);
+   D.dbls("diagE", diagE);
+   Vector diag(ndofs);
+   a.AssembleDiagonal(diag);
+   D.dbls("diag", diag);
+   std::printf("dump %s: nonsymmetric coefficient dim=%d NE=%d p=%d symmetric=%d |y|=%.17g\n", out, dim, NE,
+               P.p, (int)bfi->symmetric, y.Norml2());
+   return 0;
+}
+
 // Timing of the reference CPU path.  Prints one JSON object.
 //   mode=mult : y = A x (BilinearForm::Mult, PA) repeated `reps` times
 //   mode=pcg  : bench_ceed.cpp BP style: CG (optionally Jacobi), fixed `iters` iterations
@@ -520,6 +589,7 @@ int main(int argc, char **argv)
    if (cmd == "dump")
    {
       Args A(argc, argv, 3);
+      if (A.geti("nonsym", 0)) { return do_dump_nonsym(A, argv[2]); }
       return A.geti("vdim", 1) > 1 ? do_dump_vector(A, argv[2]) : do_dump(A, argv[2]);
    }
    if (cmd == "bench") { Args A(argc, argv, 2); return do_bench(A); }

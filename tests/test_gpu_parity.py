@@ -9,7 +9,7 @@ PCG within +-1 iteration.
 import numpy as np
 import pytest
 
-from conftest import golden_names, load_golden, relerr
+from conftest import golden_names, load_golden, nonsym_golden_names, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -380,17 +380,20 @@ def test_empty_mesh_and_bad_arguments(dev):
     R0.Mult(e, e); it0.AddMultPA(e, e); it0.AssembleDiagonalPA(e)
     dev.sync()
     R0.close(); it0.close()
-    # (D1D, Q1D) outside the tables -> B2F_ERR_UNSUPPORTED, nothing launched, context still usable
+    # (D1D, Q1D) outside the specialised tables (Q1D = D1D + 4): the run-time-sized kernel takes over
+    from oracle import oracle as orc
     it = m.DiffusionIntegrator()
     nq = 7
     qp, qw = m.gauss_legendre(nq)
     B, G = m.h1_dof_to_quad(2, qp)
     J = np.ascontiguousarray(np.tile(np.repeat(np.eye(3).reshape(9), nq ** 3), 2))
-    it.assemble_from_factors(dev, 3, 3, nq, 2, B, G, m.tensor_weights(3, qw), J=J)
-    xe, ye = dev.zeros(2 * 27), dev.zeros(2 * 27)
-    with pytest.raises(B2FError) as ei:
-        it.AddMultPA(xe, ye)
-    assert ei.value.code == 3
+    W = m.tensor_weights(3, qw)
+    it.assemble_from_factors(dev, 3, 3, nq, 2, B, G, W, J=J)
+    xE = orc.randomize(2 * 27, 6)
+    xe, ye = dev.to_device(xE), dev.zeros(2 * 27)
+    it.AddMultPA(xe, ye)
+    Dq = orc.diffusion_setup(3, nq, 1, 2, W, J, [1.0])
+    assert relerr(host(ye), orc.diffusion_apply(3, 3, nq, 2, B, G, Dq, xE)) < TOL
     it.close()
     # aliasing x and y is refused, NULL handles are refused
     a, it2, R = make_form(dev, g)
@@ -488,4 +491,42 @@ def test_ragged_tiles(dev, ne):
     yE = orc.diffusion_apply(dim, D1D, Q1D, ne, g["B"], g["G"], D, xl[gmap])
     yref = orc.restriction_mult_transpose(nd, dof, off, ind, yE)
     assert relerr(host(y), yref) < TOL
+    a.close(); it.close(); R.close()
+
+
+@pytest.mark.parametrize("name", nonsym_golden_names())
+def test_nonsymmetric_matrix_coefficient(dev, name):
+    """DiffusionIntegrator(MatrixCoefficient) with a full (non-symmetric) matrix: dim*dim
+    quadrature-data components (bilininteg_diffusion_pa.cpp:165), against the reference."""
+    import mfem_b200 as m
+    g = load_golden(name)
+    dim, D1D, Q1D, NE, nd = (int(g[k][0]) for k in ("dim", "D1D", "Q1D", "NE", "ndofs"))
+    it = m.DiffusionIntegrator()
+    it.assemble_from_factors(dev, dim, D1D, Q1D, NE, g["B"], g["G"], g["W"], J=g["J"], coeff=g["coeff_full"],
+                             coeff_dim=dim * dim)
+    assert np.array_equal(it.pa_data(), g["pa_data"])           # setup: bit-exact
+    xe = dev.to_device(g["xE"])
+    ye = dev.zeros(xe.numel())
+    it.AddMultPA(xe, ye)
+    assert relerr(host(ye), g["yE"]) < TOL
+    de = dev.zeros(xe.numel())
+    it.AssembleDiagonalPA(de)
+    assert relerr(host(de), g["diagE"]) < TOL
+    R = m.ElementRestriction.from_tables(dev, NE, D1D ** dim, nd, g["gather_map"], g["offsets"], g["indices"])
+
+    class _Fes:
+        pass
+    fes = _Fes()
+    fes.ne, fes.dof, fes.ndofs = NE, D1D ** dim, nd
+    fes.GetElementRestriction = lambda d: R
+    a = m.BilinearForm(dev, fes)
+    a.AddDomainIntegrator(it)
+    a.Assemble()
+    y, y2, d = dev.empty(nd), dev.empty(nd), dev.empty(nd)
+    a.Mult(dev.to_device(g["x"]), y)
+    assert relerr(host(y), g["y"]) < TOL
+    a.MultUnfused(dev.to_device(g["x"]), y2)
+    assert relerr(host(y2), g["y"]) < TOL
+    a.AssembleDiagonal(d)
+    assert relerr(host(d), g["diag"]) < TOL
     a.close(); it.close(); R.close()
