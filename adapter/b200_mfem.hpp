@@ -320,12 +320,68 @@ public:
    }
 };
 
+/// OperatorChebyshevSmoother (linalg/solvers.hpp:392-505, solvers.cpp:453-658) over the
+/// constrained fused operator; both reference constructors (given eigenvalue estimate /
+/// power method with MFEM's own Vector::Randomize(power_seed) start vector).
+class OperatorChebyshevSmoother : public mfem::Solver
+{
+   const ConstrainedOperator &A;
+   b2f_chebyshev *h = nullptr;
+   double max_eig = 0.0;
+   mutable DeviceVector dx, dy;
+public:
+   OperatorChebyshevSmoother(const ConstrainedOperator &A_, const mfem::Vector &d, int order,
+                             double max_eig_estimate)
+      : mfem::Solver(d.Size()), A(A_), max_eig(max_eig_estimate)
+   {
+      DeviceVector dd;
+      dd.Upload(d);
+      B200_CHECK(b2f_chebyshev_create(A.Handle(), dd.Ptr(), order, max_eig, &h));
+      B200_CHECK(b2f_ctx_sync(Context::Get().get()));
+   }
+   OperatorChebyshevSmoother(const ConstrainedOperator &A_, const mfem::Vector &d,
+                             const mfem::Array<int> &ess_tdof_list, int order, int power_iterations = 10,
+                             double power_tolerance = 1e-8, int power_seed = 12345)
+      : mfem::Solver(d.Size()), A(A_)
+   {
+      MFEM_VERIFY(power_seed != 0, "invalid seed!");
+      b2f_ctx *ctx = Context::Get().get();
+      DeviceVector dd, dinv(d.Size()), ev;
+      dd.Upload(d);
+      int *d_ess = nullptr;
+      B200_CHECK(b2f_malloc(ctx, sizeof(int) * (ess_tdof_list.Size() + 1), (void **)&d_ess));
+      B200_CHECK(b2f_memcpy_h2d(ctx, d_ess, ess_tdof_list.HostRead(), sizeof(int) * ess_tdof_list.Size()));
+      B200_CHECK(b2f_jacobi_setup(ctx, d.Size(), dd.Ptr(), d_ess, ess_tdof_list.Size(), 1.0, dinv.Ptr()));
+      mfem::Vector v0(d.Size());
+      v0.Randomize(power_seed);
+      ev.Upload(v0);
+      B200_CHECK(b2f_power_method(A.Handle(), dinv.Ptr(), ev.Ptr(), power_iterations, power_tolerance,
+                                  &max_eig));
+      b2f_free(ctx, d_ess);
+      B200_CHECK(b2f_chebyshev_create(A.Handle(), dd.Ptr(), order, max_eig, &h));
+      B200_CHECK(b2f_ctx_sync(ctx));
+   }
+   ~OperatorChebyshevSmoother() override { b2f_chebyshev_destroy(h); }
+   void SetOperator(const mfem::Operator &) override { }
+   double MaxEigEstimate() const { return max_eig; }
+   b2f_chebyshev *Handle() const { return h; }
+   void Mult(const mfem::Vector &x, mfem::Vector &y) const override
+   {
+      MFEM_VERIFY(!iterative_mode, "Chebyshev smoother not implemented for iterative mode");
+      dx.Upload(x);
+      dy.Resize(height);
+      B200_CHECK(b2f_chebyshev_mult(h, dx.Ptr(), dy.Ptr()));
+      dy.Download(y);
+   }
+};
+
 /// CGSolver (linalg/solvers.cpp:869-1050) with an optional Jacobi preconditioner
 /// (OperatorJacobiSmoother, solvers.cpp:324-450), entirely on the device.
 class CGSolver : public mfem::IterativeSolver
 {
    const ConstrainedOperator *A = nullptr;
    bool jacobi = false;
+   const OperatorChebyshevSmoother *cheb = nullptr;
    DeviceVector dinv;
    mutable DeviceVector db, dxs;
 public:
@@ -351,6 +407,14 @@ public:
       B200_CHECK(b2f_ctx_sync(ctx));
       b2f_free(ctx, d_ess);
       jacobi = true;
+      cheb = nullptr;
+   }
+   /// Only the b200 Chebyshev smoother is accepted here (Jacobi: UseJacobi).
+   void SetPreconditioner(mfem::Solver &pr) override
+   {
+      cheb = dynamic_cast<const OperatorChebyshevSmoother *>(&pr);
+      MFEM_VERIFY(cheb, "b200::CGSolver: preconditioner must be a b200::OperatorChebyshevSmoother");
+      jacobi = false;
    }
    void Mult(const mfem::Vector &b, mfem::Vector &x) const override
    {
@@ -370,8 +434,15 @@ public:
       }
       b2f_pcg_options opt = {rel_tol, abs_tol, max_iter, 1};
       b2f_pcg_result res;
-      B200_CHECK(b2f_pcg(A->Handle(), jacobi ? dinv.Ptr() : nullptr, db.Ptr(), dxs.Ptr(), &opt, &res,
-                         nullptr, 0));
+      if (cheb)
+      {
+         B200_CHECK(b2f_pcg_chebyshev(A->Handle(), cheb->Handle(), db.Ptr(), dxs.Ptr(), &opt, &res, nullptr, 0));
+      }
+      else
+      {
+         B200_CHECK(b2f_pcg(A->Handle(), jacobi ? dinv.Ptr() : nullptr, db.Ptr(), dxs.Ptr(), &opt, &res,
+                            nullptr, 0));
+      }
       if (iterative_mode) { B200_CHECK(b2f_vector_add(ctx, height, x0.Ptr(), 1.0, dxs.Ptr(), dxs.Ptr())); }
       dxs.Download(x);
       final_iter = res.iterations;

@@ -137,6 +137,31 @@ int main(int argc, char *argv[])
    std::printf("  PCG iterations: MFEM %d, b200 %d\n", cg.GetNumIterations(), cg2.GetNumIterations());
    check("PCG iteration count |difference|", std::abs(cg.GetNumIterations() - cg2.GetNumIterations()), 1.0);
    check("PCG solution", relerr(X2, X), 1e-5);
+
+   // Chebyshev smoother (power-method constructor, MFEM's own start vector) as preconditioner
+   {
+      Vector dg(N);
+      a_ref->AssembleDiagonal(dg);
+      OperatorChebyshevSmoother S(*A, dg, ess, 3, 10, 1e-8, 12345);
+      b200::OperatorChebyshevSmoother S2(A_b2, dg, ess, 3, 10, 1e-8, 12345);
+      Vector t(N), s_ref(N), s2(N);
+      t.Randomize(11);
+      S.Mult(t, s_ref);
+      S2.Mult(t, s2);
+      check("OperatorChebyshevSmoother::Mult (order 3, power method)", relerr(s2, s_ref), 1e-10);
+      cg.SetPreconditioner(S);
+      X = 0.0;
+      cg.Mult(B, X);
+      b200::CGSolver cg3;
+      cg3.SetRelTol(1e-6); cg3.SetAbsTol(0.0); cg3.SetMaxIter(2000);
+      cg3.SetOperator(A_b2);
+      cg3.SetPreconditioner(S2);
+      Vector X3(N);
+      cg3.Mult(B2, X3);
+      std::printf("  Chebyshev-PCG iterations: MFEM %d, b200 %d\n", cg.GetNumIterations(), cg3.GetNumIterations());
+      check("Chebyshev-PCG iteration count |difference|", std::abs(cg.GetNumIterations() - cg3.GetNumIterations()), 1.0);
+      check("Chebyshev-PCG solution", relerr(X3, X), 1e-5);
+   }
    std::printf(fails ? "ex1_b200: %d check(s) FAILED\n" : "ex1_b200: all checks passed\n", fails);
    return fails ? 1 : 0;
 }

@@ -254,6 +254,33 @@ int b2f_pcg(b2f_operator *op, const double *dinv, const double *b, double *x,
             const b2f_pcg_options *opt, b2f_pcg_result *result_h, double *history_h,
             int history_capacity);
 
+/* ---- OperatorChebyshevSmoother (linalg/solvers.hpp:392-505, solvers.cpp:453-658) ------
+ * Polynomial smoother z = p(D^-1 A) D^-1 r of order 1..5 on the eigenvalue window
+ * [0.3, 1.2] max_eig_estimate; A is the constrained operator of `op`, D its diagonal with
+ * the essential entries replaced by 1 (Setup(), solvers.cpp:538-550). */
+typedef struct b2f_chebyshev b2f_chebyshev;
+/* The order coefficients of Setup() (solvers.cpp:553-618); host only, no device needed.
+ * Fails for order outside 1..5 like the reference's MFEM_ABORT. */
+int b2f_chebyshev_coefficients_h(int order, double max_eig_estimate, double *coeffs_h);
+/* PowerMethod::EstimateLargestEigenvalue (linalg/operator.cpp:886-945) on
+ * ProductOperator(OperatorJacobiSmoother(diag, ess, 1.0), A) as the smoother's second
+ * constructor runs it (solvers.cpp:496-513).  dinv = b2f_jacobi_setup(..., damping 1);
+ * v0 (device, true-dof size) holds the start vector on entry — the caller draws it
+ * (Vector::Randomize(seed), linalg/vector.cpp:955) — and the last iterate on return.
+ * Dot products are all-reduced when the operator has a halo. */
+int b2f_power_method(b2f_operator *op, const double *dinv, double *v0, int num_steps,
+                     double tolerance, double *eigenvalue_h);
+int b2f_chebyshev_create(b2f_operator *op, const double *diag, int order,
+                         double max_eig_estimate, b2f_chebyshev **out);
+void b2f_chebyshev_destroy(b2f_chebyshev *cheb);
+/* Mult (solvers.cpp:620-658; iterative_mode is not supported there either): order-1
+ * operator applications, each diagonal scaling fused with the accumulation into y. */
+int b2f_chebyshev_mult(b2f_chebyshev *cheb, const double *x, double *y);
+/* CGSolver with the Chebyshev smoother as preconditioner (same loop as b2f_pcg). */
+int b2f_pcg_chebyshev(b2f_operator *op, b2f_chebyshev *cheb, const double *b, double *x,
+                      const b2f_pcg_options *opt, b2f_pcg_result *result_h,
+                      double *history_h, int history_capacity);
+
 /* ---- rank-parallel prolongation: ConformingProlongationOperator ----------------------
  * (fem/pfespace.hpp:615-697, pfespace.cpp:5479-5927) with the shared-dof exchange as
  * NCCL send/recv over NVLink instead of MPI_Isend/Irecv. */

@@ -96,6 +96,13 @@ PROTOTYPES = {
     "b2f_vector_dot": (C.c_int, [vp, i64, vp, vp, c_double_p]),
     "b2f_vector_add": (C.c_int, [vp, i64, vp, C.c_double, vp, vp]),
     "b2f_pcg": (C.c_int, [vp, vp, vp, vp, C.POINTER(PcgOptions), C.POINTER(PcgResult), vp, C.c_int]),
+    "b2f_chebyshev_coefficients_h": (C.c_int, [C.c_int, C.c_double, c_double_p]),
+    "b2f_power_method": (C.c_int, [vp, vp, vp, C.c_int, C.c_double, c_double_p]),
+    "b2f_chebyshev_create": (C.c_int, [vp, vp, C.c_int, C.c_double, C.POINTER(vp)]),
+    "b2f_chebyshev_destroy": (None, [vp]),
+    "b2f_chebyshev_mult": (C.c_int, [vp, vp, vp]),
+    "b2f_pcg_chebyshev": (C.c_int, [vp, vp, vp, vp, C.POINTER(PcgOptions), C.POINTER(PcgResult), vp,
+                                    C.c_int]),
     "b2f_nccl_unique_id_h": (C.c_int, [vp]),
     "b2f_halo_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp,
                                   vp, vp, C.POINTER(vp)]),

@@ -40,6 +40,9 @@ int pcg_update(b2f_ctx *ctx, void *state, int64_t n, double *x, const double *d,
                const double *q, const double *dinv, double *z);
 int pcg_after_betanom(b2f_ctx *ctx, void *state, double *history, int history_cap);
 int pcg_direction(b2f_ctx *ctx, void *state, int64_t n, const double *z, double *d);
+int cheb_step(b2f_ctx *ctx, int64_t n, const double *src, const double *dinv, double c, double *res,
+              double *y, bool first);
+int normalize_by(b2f_ctx *ctx, int64_t n, const double *d_normsq, double *v);
 int pcg_after_den(b2f_ctx *ctx, void *state);
 double *pcg_dot_slot(void *state);
 void pcg_read_state(const void *host_copy, int *iter, int *done, int *converged, int *final_iter,
@@ -952,10 +955,182 @@ int b2f_vector_add(b2f_ctx *ctx, int64_t n, const double *x, double a, const dou
    return vector_add(ctx, n, x, a, y, z);
 }
 
+// ---- OperatorChebyshevSmoother (linalg/solvers.cpp:453-658) ------------------------------
+} // extern "C"
+
+struct b2f_chebyshev
+{
+   b2f_operator *op;
+   int order;
+   double coeffs[5];
+   double *dinv = nullptr;
+   double *res = nullptr, *help = nullptr; // "residual" and "helperVector", L-vector capacity
+   double *vin = nullptr;                  // staging copy when the caller's input cannot be used in place
+};
+
+// z = p(D^-1 A) D^-1 r
+static int chebyshev_apply(b2f_chebyshev *c, const double *x, double *y)
+{
+   b2f_operator *op = c->op;
+   b2f_ctx *ctx = op->ctx;
+   const int64_t n = b2f_operator_height(op);
+   B2F_TRY(cheb_step(ctx, n, x, c->dinv, c->coeffs[0], c->res, y, true));
+   for (int k = 1; k < c->order; k++)
+   {
+      B2F_TRY(mult_constrained(op, c->res, c->help, true));
+      B2F_TRY(cheb_step(ctx, n, c->help, c->dinv, c->coeffs[k], c->res, y, false));
+   }
+   return B2F_OK;
+}
+
+extern "C" {
+
+int b2f_chebyshev_coefficients_h(int order, double max_eig_estimate, double *coeffs_h)
+{
+   B2F_REQUIRE(coeffs_h, "b2f_chebyshev_coefficients_h: NULL argument");
+   B2F_REQUIRE(order >= 1 && order <= 5, "Chebyshev smoother not implemented for order = %d", order);
+   // Eigenvalue window [0.3, 1.2] lambda_max of D^-1 A (solvers.cpp:553-560); the coefficients
+   // are those of the polynomial q with 1 - t q(t) = T_k((theta - t)/delta) / T_k(theta/delta),
+   // written in the monomial basis of t; closed forms as in solvers.cpp:562-618.
+   const double ub = 1.2 * max_eig_estimate, lb = 0.3 * max_eig_estimate;
+   const double th = 0.5 * (ub + lb), de = 0.5 * (ub - lb);
+   const double th2 = pow(th, 2), de2 = pow(de, 2);
+   double *c = coeffs_h;
+   switch (order)
+   {
+      case 1:
+         c[0] = 1.0 / th;
+         break;
+      case 2:
+      {
+         const double w = 1.0 / (de2 - 2 * th2);
+         c[0] = -4 * th * w;
+         c[1] = 2 * w;
+         break;
+      }
+      case 3:
+      {
+         const double a = 3 * de2;
+         const double w = 1.0 / (-4 * pow(th, 3) + th * a);
+         c[0] = w * (a - 12 * th2);
+         c[1] = 12 / (a - 4 * th2);
+         c[2] = -4 * w;
+         break;
+      }
+      case 4:
+      {
+         const double a = 8 * de2;
+         const double w = 1.0 / (pow(de, 4) + 8 * pow(th, 4) - th2 * a);
+         c[0] = w * (32 * pow(th, 3) - 16 * th * de2);
+         c[1] = w * (-48 * th2 + a);
+         c[2] = 32 * th * w;
+         c[3] = -8 * w;
+         break;
+      }
+      case 5:
+      {
+         const double a = 5 * pow(de, 4), th4 = pow(th, 4);
+         const double b60 = 60 * de2, b20 = 20 * de2;
+         const double w = 1.0 / (16 * pow(th, 5) - pow(th, 3) * b20 + th * a);
+         const double t160 = 160 * th2;
+         const double v = 1.0 / (a + 16 * th4 - th2 * b20);
+         c[0] = w * (a + 80 * th4 - th2 * b60);
+         c[1] = v * (b60 - t160);
+         c[2] = w * (-b20 + t160);
+         c[3] = -80 * v;
+         c[4] = 16 * w;
+         break;
+      }
+   }
+   return B2F_OK;
+}
+
+int b2f_power_method(b2f_operator *op, const double *dinv, double *v0, int num_steps, double tolerance,
+                     double *eigenvalue_h)
+{
+   B2F_REQUIRE(op && dinv && v0 && eigenvalue_h, "b2f_power_method: NULL argument");
+   b2f_ctx *ctx = op->ctx;
+   b2f_halo *halo = op->halo;
+   const int64_t n = b2f_operator_height(op);
+   const int64_t ncap = halo ? (int64_t)op->r->ndofs : n;
+   // the iteration vector and its image live in the PCG scratch (L-vector capacity)
+   for (int k = 0; k < 3; k++) { B2F_TRY(ensure(&op->pcg_vec[k], ncap)); }
+   double *va = op->pcg_vec[0], *vb = op->pcg_vec[1], *q = op->pcg_vec[2];
+   double *slot = ctx->d_scalars + 62;
+   B2F_CUDA(cudaMemcpyAsync(va, v0, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+   double eig = 1.0;
+   for (int it = 0; it < num_steps; it++)
+   {
+      B2F_TRY(dot_to_device(ctx, n, va, va, slot));
+      if (halo) { B2F_TRY(halo_allreduce_sum(halo, slot, 1)); }
+      B2F_TRY(normalize_by(ctx, n, slot, va));                 // v0 /= sqrt(normV0)
+      B2F_TRY(mult_constrained(op, va, q, true));              // ProductOperator: A first,
+      B2F_TRY(vector_mul(ctx, n, dinv, q, vb));                // then the Jacobi smoother
+      B2F_TRY(dot_to_device(ctx, n, va, vb, slot));
+      if (halo) { B2F_TRY(halo_allreduce_sum(halo, slot, 1)); }
+      B2F_CUDA(cudaMemcpyAsync(ctx->h_scalars + 62, slot, sizeof(double), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+      B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+      const double eig_new = ctx->h_scalars[62];
+      const double diff = fabs((eig_new - eig) / eig);
+      eig = eig_new;
+      std::swap(va, vb);
+      if (diff < tolerance) { break; }
+   }
+   B2F_CUDA(cudaMemcpyAsync(v0, va, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+   B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+   *eigenvalue_h = eig;
+   return B2F_OK;
+}
+
+int b2f_chebyshev_create(b2f_operator *op, const double *diag, int order, double max_eig_estimate,
+                         b2f_chebyshev **out)
+{
+   B2F_REQUIRE(op && diag && out, "b2f_chebyshev_create: NULL argument");
+   *out = nullptr;
+   double coeffs[5] = {0, 0, 0, 0, 0};
+   B2F_TRY(b2f_chebyshev_coefficients_h(order, max_eig_estimate, coeffs));
+   b2f_chebyshev *c = new b2f_chebyshev;
+   c->op = op;
+   c->order = order;
+   memcpy(c->coeffs, coeffs, sizeof(coeffs));
+   const int64_t n = b2f_operator_height(op);
+   const int64_t ncap = op->halo ? (int64_t)op->r->ndofs : n;
+   cudaError_t e1 = cudaMalloc((void **)&c->dinv, sizeof(double) * (n ? n : 1));
+   cudaError_t e2 = cudaMalloc((void **)&c->res, sizeof(double) * (ncap ? ncap : 1));
+   cudaError_t e3 = cudaMalloc((void **)&c->help, sizeof(double) * (ncap ? ncap : 1));
+   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+   {
+      b2f_chebyshev_destroy(c);
+      B2F_REQUIRE(false, "b2f_chebyshev_create: out of device memory");
+   }
+   // Setup(): dinv = 1/diag, dinv[ess] = 1 (solvers.cpp:538-550)
+   int rc = jacobi_setup(op->ctx, (int)n, diag, op->ess, op->n_ess, 1.0, c->dinv);
+   if (rc != B2F_OK) { b2f_chebyshev_destroy(c); return rc; }
+   *out = c;
+   return B2F_OK;
+}
+
+void b2f_chebyshev_destroy(b2f_chebyshev *c)
+{
+   if (!c) { return; }
+   cudaFree(c->dinv); cudaFree(c->res); cudaFree(c->help); cudaFree(c->vin);
+   delete c;
+}
+
+int b2f_chebyshev_mult(b2f_chebyshev *c, const double *x, double *y)
+{
+   B2F_REQUIRE(c && x && y, "b2f_chebyshev_mult: NULL argument");
+   B2F_REQUIRE(x != y, "b2f_chebyshev_mult: x and y alias");
+   return chebyshev_apply(c, x, y);
+}
+
 // ---- PCG --------------------------------------------------------------------------------
-int b2f_pcg(b2f_operator *op, const double *dinv, const double *b, double *x,
-            const b2f_pcg_options *opt, b2f_pcg_result *result_h, double *history_h,
-            int history_capacity)
+} // extern "C"
+
+static int pcg_impl(b2f_operator *op, const double *dinv, b2f_chebyshev *cheb, const double *b, double *x,
+                    const b2f_pcg_options *opt, b2f_pcg_result *result_h, double *history_h,
+                    int history_capacity)
 {
    B2F_REQUIRE(op && b && x && opt && result_h, "b2f_pcg: NULL argument");
    B2F_REQUIRE(opt->max_iter >= 0, "b2f_pcg: max_iter < 0");
@@ -1006,7 +1181,12 @@ int b2f_pcg(b2f_operator *op, const double *dinv, const double *b, double *x,
    B2F_CUDA(cudaMemcpyAsync(r, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
    B2F_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * n, ctx->stream));
    const double *zz = r; // "z" of the unpreconditioned iteration is r itself
-   if (dinv)
+   if (cheb)
+   {
+      B2F_TRY(chebyshev_apply(cheb, r, z));
+      zz = z;
+   }
+   else if (dinv)
    {
       B2F_TRY(vector_mul(ctx, n, dinv, r, z)); // z = B r
       zz = z;
@@ -1037,6 +1217,12 @@ int b2f_pcg(b2f_operator *op, const double *dinv, const double *b, double *x,
    while (!done)
    {
       B2F_TRY(pcg_update(ctx, st, n, x, d, r, q, dinv, z));
+      if (cheb)
+      {
+         // general preconditioner: z = B r, betanom = (r, z) replace the fused Jacobi step
+         B2F_TRY(chebyshev_apply(cheb, r, z));
+         B2F_TRY(dot_to_device(ctx, n, r, z, pcg_dot_slot(st)));
+      }
       B2F_TRY(reduce());
       B2F_TRY(pcg_after_betanom(ctx, st, hist, hist ? history_capacity : 0));
       B2F_TRY(pcg_direction(ctx, st, n, zz, d));
@@ -1056,6 +1242,23 @@ int b2f_pcg(b2f_operator *op, const double *dinv, const double *b, double *x,
       B2F_CUDA(cudaStreamSynchronize(ctx->stream));
    }
    return B2F_OK;
+}
+
+extern "C" {
+
+int b2f_pcg(b2f_operator *op, const double *dinv, const double *b, double *x,
+            const b2f_pcg_options *opt, b2f_pcg_result *result_h, double *history_h,
+            int history_capacity)
+{
+   return pcg_impl(op, dinv, nullptr, b, x, opt, result_h, history_h, history_capacity);
+}
+
+int b2f_pcg_chebyshev(b2f_operator *op, b2f_chebyshev *cheb, const double *b, double *x,
+                      const b2f_pcg_options *opt, b2f_pcg_result *result_h, double *history_h,
+                      int history_capacity)
+{
+   B2F_REQUIRE(cheb && cheb->op == op, "b2f_pcg_chebyshev: smoother was built for another operator");
+   return pcg_impl(op, nullptr, cheb, b, x, opt, result_h, history_h, history_capacity);
 }
 
 } // extern "C"

@@ -89,6 +89,32 @@ mul_kernel(int64_t n, const double *__restrict__ a, const double *__restrict__ x
    }
 }
 
+// One term of OperatorChebyshevSmoother::Mult (linalg/solvers.cpp:637-657):
+// R = dinv .* src; y (+)= c R.   FIRST: y starts from 0 (the reference's y = 0.0).
+template <bool FIRST>
+__global__ void __launch_bounds__(VT)
+cheb_step_kernel(int64_t n, const double *__restrict__ src, const double *__restrict__ dinv,
+                 double c, double *__restrict__ res, double *__restrict__ y)
+{
+   for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
+   {
+      const double r = src[i] * dinv[i];
+      res[i] = r;
+      y[i] = (FIRST ? 0.0 : y[i]) + c * r;
+   }
+}
+
+// v *= s, s = 1 / sqrt(*d_normsq)   (PowerMethod, linalg/operator.cpp:913)
+__global__ void __launch_bounds__(VT)
+normalize_kernel(int64_t n, const double *__restrict__ d_normsq, double *v)
+{
+   const double s = sqrt(*d_normsq);
+   for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n; i += (int64_t)gridDim.x * VT)
+   {
+      v[i] /= s;
+   }
+}
+
 __global__ void jacobi_setup_kernel(int n, const double *__restrict__ diag, double damping,
                                     double *dinv)
 {
@@ -422,6 +448,24 @@ int jacobi_setup(b2f_ctx *ctx, int n, const double *diag, const int *ess, int n_
    jacobi_setup_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(n, diag, damping, dinv);
    B2F_LAUNCH_CHECK(ctx);
    return set_entries(ctx, dinv, ess, n_ess, damping);
+}
+
+int cheb_step(b2f_ctx *ctx, int64_t n, const double *src, const double *dinv, double c, double *res,
+              double *y, bool first)
+{
+   if (n == 0) { return B2F_OK; }
+   if (first) { cheb_step_kernel<true><<<stream_grid(ctx, n, 4), VT, 0, ctx->stream>>>(n, src, dinv, c, res, y); }
+   else { cheb_step_kernel<false><<<stream_grid(ctx, n, 4), VT, 0, ctx->stream>>>(n, src, dinv, c, res, y); }
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+int normalize_by(b2f_ctx *ctx, int64_t n, const double *d_normsq, double *v)
+{
+   if (n == 0) { return B2F_OK; }
+   normalize_kernel<<<stream_grid(ctx, n, 4), VT, 0, ctx->stream>>>(n, d_normsq, v);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
 }
 
 // pieces of the PCG loop, called from capi.cu

@@ -567,6 +567,16 @@ class BilinearForm:
     def Height(self):
         return int(capi.lib().b2f_operator_height(self.op))
 
+    def constrained_tdofs(self, ess_dofs=None):
+        """The operator's own constrained list: true dofs when a halo is attached."""
+        ess = self.ess if ess_dofs is None else ess_dofs
+        if self.halo is None:
+            return _i32(ess)
+        l2t = np.full(self.fes.ndofs, -1, np.int64)
+        l2t[self.halo.tables["ltdof_ldof"]] = np.arange(self.halo.n_tdofs)
+        e = l2t[np.asarray(ess, np.int64)]
+        return _i32(e[e >= 0])
+
     def Mult(self, x, y):
         call("b2f_operator_mult", self.op, _dp(x), _dp(y))
 
@@ -616,15 +626,7 @@ class OperatorJacobiSmoother:
         diag = dev.empty(n)
         form.AssembleDiagonal(diag)
         self.dinv = dev.empty(n)
-        # the operator's own constrained list (true dofs when a halo is attached)
-        import torch
-        if form.halo is not None:
-            l2t = np.full(form.fes.ndofs, -1, np.int64)
-            l2t[form.halo.tables["ltdof_ldof"]] = np.arange(form.halo.n_tdofs)
-            e = l2t[np.asarray(form.ess if ess_dofs is None else ess_dofs, np.int64)]
-            ess = _i32(e[e >= 0])
-        else:
-            ess = _i32(form.ess if ess_dofs is None else ess_dofs)
+        ess = form.constrained_tdofs(ess_dofs)
         ess_d = dev.to_device(ess) if len(ess) else None
         call("b2f_jacobi_setup", dev.ctx, n, _dp(diag), _dp(ess_d), len(ess), float(damping),
              _dp(self.dinv))
@@ -632,6 +634,59 @@ class OperatorJacobiSmoother:
 
     def Mult(self, x, y):
         call("b2f_jacobi_mult", self.dev.ctx, self.n, _dp(self.dinv), _dp(x), _dp(y))
+
+
+class OperatorChebyshevSmoother:
+    """linalg/solvers.hpp:392-505, solvers.cpp:453-658.  `oper` is the ConstrainedOperator of a
+    BilinearForm; `diag` its assembled diagonal (device vector).  Either give
+    `max_eig_estimate`, or leave it None to run the power method from `start` (a host vector
+    the caller draws: Vector::Randomize(power_seed) in the reference)."""
+
+    def __init__(self, oper, diag, order, max_eig_estimate=None, power_iterations=10,
+                 power_tolerance=1e-8, start=None):
+        form = oper.form if hasattr(oper, "form") else oper
+        dev = form.dev
+        self.dev, self.form, self.order = dev, form, order
+        self.n = form.Height()
+        if max_eig_estimate is None:
+            if start is None:
+                raise ValueError("OperatorChebyshevSmoother: the power method needs a start vector")
+            jac = OperatorJacobiSmoother.__new__(OperatorJacobiSmoother)
+            jac.dev, jac.n = dev, self.n
+            jac.dinv = dev.empty(self.n)
+            ess = form.constrained_tdofs()
+            ess_d = dev.to_device(ess) if len(ess) else None
+            call("b2f_jacobi_setup", dev.ctx, self.n, _dp(diag), _dp(ess_d), len(ess), 1.0, _dp(jac.dinv))
+            v0 = dev.to_device(np.ascontiguousarray(start, dtype=np.float64))
+            lam = C.c_double()
+            call("b2f_power_method", form.op, _dp(jac.dinv), _dp(v0), int(power_iterations),
+                 float(power_tolerance), C.byref(lam))
+            max_eig_estimate = lam.value
+        self.max_eig_estimate = float(max_eig_estimate)
+        h = C.c_void_p()
+        call("b2f_chebyshev_create", form.op, _dp(diag), int(order), self.max_eig_estimate, C.byref(h))
+        self.handle = h
+        dev.sync()
+
+    @staticmethod
+    def coefficients(order, max_eig_estimate):
+        c = np.zeros(5)
+        call("b2f_chebyshev_coefficients_h", int(order), float(max_eig_estimate), _np_ptr(c))
+        return c[:order]
+
+    def Mult(self, x, y):
+        call("b2f_chebyshev_mult", self.handle, _dp(x), _dp(y))
+
+    def close(self):
+        if self.handle:
+            capi.lib().b2f_chebyshev_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class CGSolver:
@@ -663,9 +718,12 @@ class CGSolver:
         res = capi.PcgResult()
         form = self.oper.form
         hist = np.zeros(self.max_iter + 2) if record_history else None
-        call("b2f_pcg", form.op, _dp(self.prec.dinv) if self.prec else None, _dp(b), _dp(x),
-             C.byref(opt), C.byref(res), _np_ptr(hist) if hist is not None else None,
-             len(hist) if hist is not None else 0)
+        tail = (_dp(b), _dp(x), C.byref(opt), C.byref(res), _np_ptr(hist) if hist is not None else None,
+                len(hist) if hist is not None else 0)
+        if isinstance(self.prec, OperatorChebyshevSmoother):
+            call("b2f_pcg_chebyshev", form.op, self.prec.handle, *tail)
+        else:
+            call("b2f_pcg", form.op, _dp(self.prec.dinv) if self.prec else None, *tail)
         self.final_iter, self.converged = res.iterations, bool(res.converged)
         self.initial_norm, self.final_norm = res.initial_norm, res.final_norm
         self.history = hist[:res.iterations + 1] if hist is not None else None

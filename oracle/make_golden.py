@@ -68,6 +68,12 @@ CASES = {
     "nonsym_diff3d_p7_n2": dict(dim=3, n=2, p=7, kind="diffusion", nonsym=1),
     "nonsym_diff2d_p3_n3_curved": dict(dim=2, n=3, p=3, kind="diffusion", nonsym=1, curved=1),
     "nonsym_bp5_3d_p3_n2": dict(dim=3, n=2, p=3, kind="diffusion", quad="gll", nonsym=1),
+    # OperatorChebyshevSmoother: coefficients/action for orders 1..5, power method, CG + Chebyshev
+    "cheb_diff3d_p2_n3": dict(dim=3, n=3, p=2, kind="diffusion", cheb=1, order=3),
+    "cheb_diff3d_p4_n2_curved": dict(dim=3, n=2, p=4, kind="diffusion", cheb=1, curved=1, order=2),
+    "cheb_diff2d_p3_n4": dict(dim=2, n=4, p=3, kind="diffusion", cheb=1, order=4),
+    "cheb_mass3d_p3_n2": dict(dim=3, n=2, p=3, kind="mass", cheb=1, order=5),
+    "cheb_bp5_3d_p5_n2": dict(dim=3, n=2, p=5, kind="diffusion", quad="gll", cheb=1, order=3),
 }
 
 

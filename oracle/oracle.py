@@ -229,6 +229,39 @@ class Operator:
                 C.byref(fn), _p(hist), len(hist))
         return x, its, bool(conv.value), fn.value, hist[:its + 1]
 
+    # OperatorChebyshevSmoother (linalg/solvers.cpp:453-658)
+    def chebyshev_mult(self, dinv, order, max_eig, x):
+        c = chebyshev_coeffs(order, max_eig)
+        y = np.empty(self.ndofs)
+        lib().orc_chebyshev_mult(C.byref(self.op), _p(_f64(dinv)), order, _p(c), _p(_f64(x)), _p(y))
+        return y
+
+    def power_method(self, dinv, start, steps=10, tol=1e-8):
+        v = _f64(start).copy()
+        f = lib().orc_power_method
+        f.restype = C.c_double
+        lam = f(C.byref(self.op), _p(_f64(dinv)), _p(v), steps, C.c_double(tol))
+        return lam, v
+
+    def pcg_chebyshev(self, b, dinv, order, max_eig, rel_tol=1e-8, abs_tol=0.0, max_iter=2000):
+        c = chebyshev_coeffs(order, max_eig)
+        x = np.zeros(self.ndofs)
+        hist = np.zeros(max_iter + 2)
+        conv = C.c_int(0)
+        fn = C.c_double(0)
+        f = lib().orc_pcg_chebyshev
+        f.restype = C.c_int
+        its = f(C.byref(self.op), _p(_f64(dinv)), order, _p(c), _p(_f64(b)), _p(x), C.c_double(rel_tol),
+                C.c_double(abs_tol), max_iter, C.byref(conv), C.byref(fn), _p(hist), len(hist))
+        return x, its, bool(conv.value), fn.value, hist[:its + 1]
+
+
+def chebyshev_coeffs(order, max_eig):
+    c = np.zeros(max(order, 1))
+    if lib().orc_chebyshev_coeffs(order, C.c_double(max_eig), _p(c)) != 0:
+        raise ValueError("Chebyshev smoother not implemented for order = %d" % order)
+    return c
+
 
 class VectorOperator:
     """Vector (vdim > 1) PA operator: CEED BP2/BP4/BP6.

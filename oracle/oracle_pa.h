@@ -108,6 +108,14 @@ int orc_pcg(const orc_operator *op, const double *dinv, const double *b, double 
             double *final_norm, double *history, int history_cap);
 
 /* linalg/vector.cpp:955-966: srand(seed); v[i] = rand()/(RAND_MAX+1.0) */
+/* OperatorChebyshevSmoother (linalg/solvers.cpp:453-658), PowerMethod (linalg/operator.cpp:886) */
+int orc_chebyshev_coeffs(int order, double max_eig, double *coeffs);
+void orc_chebyshev_mult(const orc_operator *op, const double *dinv, int order, const double *coeffs,
+                        const double *x, double *y);
+double orc_power_method(const orc_operator *op, const double *dinv, double *v0, int steps, double tol);
+int orc_pcg_chebyshev(const orc_operator *op, const double *dinv, int order, const double *coeffs,
+                      const double *b, double *x, double rel_tol, double abs_tol, int max_iter,
+                      int *converged, double *final_norm, double *history, int history_cap);
 void orc_randomize(int n, int seed, double *v);
 
 #ifdef __cplusplus

@@ -506,6 +506,115 @@ static int do_dump_nonsym(const Args &A, const char *out)
    return 0;
 }
 
+// OperatorChebyshevSmoother (linalg/solvers.cpp:453-658) on the constrained PA operator:
+// coefficients and action for every order, the power-method eigenvalue estimate, and CG
+// preconditioned with it.
+static int do_dump_cheb(const Args &A, const char *out)
+{
+   Problem P(A);
+   Dump D(out);
+   const int dim = P.dim;
+   P.a->Assemble();
+   FiniteElementSpace &fes = *P.fes;
+   const FiniteElement &fe = *fes.GetTypicalFE();
+   const DofToQuad &maps = fe.GetDofToQuad(*P.ir, DofToQuad::TENSOR);
+   const int D1D = maps.ndof, Q1D = maps.nqpt, NE = fes.GetNE(), ndofs = fes.GetNDofs();
+   D.scalar("dim", dim); D.scalar("n", P.n); D.scalar("p", P.p);
+   D.scalar("D1D", D1D); D.scalar("Q1D", Q1D); D.scalar("NE", NE); D.scalar("ndofs", ndofs);
+   D.scalar("is_mass", (int)P.mass);
+   auto R = dynamic_cast<const ElementRestriction *>(
+               fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC));
+   D.ints("gather_map", R->GatherMap());
+   D.ints("offsets", R->Offsets());
+   D.ints("indices", R->Indices());
+   D.dbls("B", maps.B); D.dbls("G", maps.G);
+   Vector pa_data;
+   if (P.mass) { pa_data = static_cast<MassIntegrator *>(P.bfi)->pa_data; }
+   else { pa_data = static_cast<DiffusionIntegrator *>(P.bfi)->pa_data; }
+   D.dbls("pa_data", pa_data);
+   D.dbls("W", P.ir->GetWeights());
+   {
+      const GeometricFactors *geom = P.mesh.GetGeometricFactors(
+                                        *P.ir, GeometricFactors::JACOBIANS | GeometricFactors::DETERMINANTS);
+      D.dbls("J", geom->J); D.dbls("detJ", geom->detJ);
+   }
+   Array<int> ess_bdr(P.mesh.bdr_attributes.Max()); ess_bdr = 1;
+   Array<int> ess;
+   fes.GetEssentialTrueDofs(ess_bdr, ess);
+   D.ints("ess_tdof_list", ess);
+   LinearForm b(&fes);
+   b.AddDomainIntegrator(new DomainLFIntegrator(P.one));
+   b.Assemble();
+   D.dbls("b", b);
+   GridFunction u(&fes); u = 0.0;
+   OperatorPtr Aop; Vector B, X;
+   P.a->FormLinearSystem(ess, u, b, Aop, X, B);
+   D.dbls("B_rhs", B);
+   Vector diag(ndofs);
+   P.a->AssembleDiagonal(diag);
+   D.dbls("diag", diag);
+   // power method, as the smoother's second constructor runs it (solvers.cpp:496-513)
+   const int seed = A.geti("power_seed", 12345), pit = A.geti("power_iterations", 10);
+   const double ptol = A.getd("power_tolerance", 1e-8);
+   double lam;
+   {
+      OperatorJacobiSmoother invDiag(diag, ess, 1.0);
+      ProductOperator dp(&invDiag, Aop.Ptr(), false, false);
+      PowerMethod pm;
+      Vector ev(ndofs);
+      ev.Randomize(seed);
+      D.dbls("power_start", ev);
+      lam = pm.EstimateLargestEigenvalue(dp, ev, pit, ptol, seed);
+      D.dbls("power_vector", ev);
+   }
+   D.scalar("power_seed", seed); D.scalar("power_iterations", pit); D.scalar("power_tolerance", ptol);
+   D.scalar("max_eig_estimate", lam);
+   Vector t(ndofs); t.Randomize(11);
+   D.dbls("cheb_in_seed11", t);
+   for (int order = 1; order <= 5; order++)
+   {
+      OperatorChebyshevSmoother S(*Aop, diag, ess, order, lam);
+      Vector y(ndofs);
+      S.Mult(t, y);
+      char nm[64];
+      std::snprintf(nm, sizeof nm, "cheb_out_order%d", order);
+      D.dbls(nm, y);
+   }
+   // CG preconditioned with the order-`order` smoother built by the power-method constructor
+   const int order = A.geti("order", 3);
+   const double rtol = A.getd("rtol", 1e-8);
+   OperatorChebyshevSmoother S(*Aop, diag, ess, order, pit, ptol, seed);
+   CGSolver cg;
+   cg.SetRelTol(rtol); cg.SetAbsTol(0.0); cg.SetMaxIter(A.geti("maxit", 2000));
+   cg.SetOperator(*Aop);
+   cg.SetPreconditioner(S);
+   std::stringstream hist;
+   std::streambuf *old = mfem::out.rdbuf(hist.rdbuf());
+   cg.SetPrintLevel(1);
+   X = 0.0;
+   cg.Mult(B, X);
+   mfem::out.rdbuf(old);
+   std::vector<double> h;
+   {
+      string line;
+      while (std::getline(hist, line))
+      {
+         size_t pos = line.find("(B r, r) =");
+         if (pos != string::npos) { h.push_back(atof(line.c_str() + pos + 10)); }
+      }
+   }
+   D.dbls("pcg_history", h.data(), h.size());
+   D.scalar("pcg_order", order);
+   D.scalar("pcg_iters", cg.GetNumIterations());
+   D.scalar("pcg_converged", (int)cg.GetConverged());
+   D.scalar("pcg_final_norm", (double)cg.GetFinalNorm());
+   D.scalar("pcg_rtol", rtol);
+   D.dbls("X_sol", X);
+   std::printf("dump %s: chebyshev dim=%d NE=%d p=%d lambda=%.17g pcg_iters=%d\n", out, dim, NE, P.p, lam,
+               cg.GetNumIterations());
+   return 0;
+}
+
 // Timing of the reference CPU path.  Prints one JSON object.
 //   mode=mult : y = A x (BilinearForm::Mult, PA) repeated `reps` times
 //   mode=pcg  : bench_ceed.cpp BP style: CG (optionally Jacobi), fixed `iters` iterations
@@ -590,6 +699,7 @@ int main(int argc, char **argv)
    {
       Args A(argc, argv, 3);
       if (A.geti("nonsym", 0)) { return do_dump_nonsym(A, argv[2]); }
+      if (A.geti("cheb", 0)) { return do_dump_cheb(A, argv[2]); }
       return A.geti("vdim", 1) > 1 ? do_dump_vector(A, argv[2]) : do_dump(A, argv[2]);
    }
    if (cmd == "bench") { Args A(argc, argv, 2); return do_bench(A); }

@@ -17,12 +17,17 @@ def pytest_configure(config):
 def golden_names():
     """scalar fixtures (every table of the path); vector ones are in vector_golden_names()"""
     return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
-                  if not n.startswith(("vec_", "nonsym_")))
+                  if not n.startswith(("vec_", "nonsym_", "cheb_")))
 
 
 def nonsym_golden_names():
     return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
                   if n.startswith("nonsym_"))
+
+
+def chebyshev_golden_names():
+    return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+                  if n.startswith("cheb_"))
 
 
 def vector_golden_names():

@@ -9,7 +9,7 @@ PCG within +-1 iteration.
 import numpy as np
 import pytest
 
-from conftest import golden_names, load_golden, nonsym_golden_names, relerr
+from conftest import chebyshev_golden_names, golden_names, load_golden, nonsym_golden_names, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -530,3 +530,52 @@ def test_nonsymmetric_matrix_coefficient(dev, name):
     a.AssembleDiagonal(d)
     assert relerr(host(d), g["diag"]) < TOL
     a.close(); it.close(); R.close()
+
+
+@pytest.mark.parametrize("name", chebyshev_golden_names())
+def test_chebyshev_smoother_power_method_and_pcg(dev, name):
+    """OperatorChebyshevSmoother (linalg/solvers.cpp:453-658) + PowerMethod
+    (linalg/operator.cpp:886-945) against the reference dump, and CG preconditioned with it."""
+    import mfem_b200 as m
+    from oracle import oracle as orc
+    g = load_golden(name)
+    a, it, R = make_form(dev, g, ess=True)
+    nd = R.ndofs
+    ess = g["ess_tdof_list"]
+    u, b = dev.zeros(nd), dev.to_device(g["b"])
+    A, X, B = a.FormLinearSystem(ess, u, b)
+    assert relerr(host(B), g["B_rhs"]) < TOL
+    diag = dev.empty(nd)
+    a.AssembleDiagonal(diag)
+    assert relerr(host(diag), g["diag"]) < TOL
+    lam_ref = float(g["max_eig_estimate"][0])
+    x = dev.to_device(g["cheb_in_seed11"])
+    y = dev.empty(nd)
+    for order in range(1, 6):
+        S = m.OperatorChebyshevSmoother(A, diag, order, lam_ref)
+        S.Mult(x, y)
+        assert relerr(host(y), g["cheb_out_order%d" % order]) < TOL, order
+        S.close()
+    with pytest.raises(RuntimeError):
+        m.OperatorChebyshevSmoother(A, diag, 6, lam_ref)
+    # the power-method constructor: the caller draws the start vector (Vector::Randomize(seed))
+    order = int(g["pcg_order"][0])
+    start = orc.randomize(nd, int(g["power_seed"][0]))
+    S = m.OperatorChebyshevSmoother(A, diag, order, None, int(g["power_iterations"][0]),
+                                    float(g["power_tolerance"][0]), start=start)
+    assert abs(S.max_eig_estimate - lam_ref) < 1e-11 * lam_ref
+    cg = m.CGSolver()
+    cg.SetRelTol(float(g["pcg_rtol"][0])); cg.SetAbsTol(0.0); cg.SetMaxIter(2000)
+    cg.SetOperator(A); cg.SetPreconditioner(S)
+    X = dev.zeros(nd)
+    cg.Mult(B, X, record_history=True)
+    assert abs(cg.GetNumIterations() - int(g["pcg_iters"][0])) <= 1
+    assert cg.GetConverged() == bool(g["pcg_converged"][0])
+    assert relerr(host(X), g["X_sol"]) < 1e-6
+    n = min(len(cg.history), len(g["pcg_history"]), 5)
+    assert np.allclose(cg.history[:n], g["pcg_history"][:n], rtol=2e-5)
+    cg.check_every = 4   # device-resident scalars: same answer when polled every 4 iterations
+    X2 = dev.zeros(nd)
+    cg.Mult(B, X2)
+    assert relerr(host(X2), host(X)) < 1e-9
+    S.close(); a.close(); it.close(); R.close()
