@@ -273,6 +273,14 @@ public:
       }
       B200_CHECK(b2f_operator_create(Context::Get().get(), restr, integ.data(), (int)integ.size(),
                                      ess_tdof_list.HostRead(), ess_tdof_list.Size(), &op));
+      // AddDomainIntegrator(bfi, elem_marker): hand over MFEM's own marker and attribute arrays
+      Array<Array<int>*> &markers = *a.GetDBFI_Marker();
+      for (int i = 0; i < markers.Size(); i++)
+      {
+         if (!markers[i]) { continue; }
+         const Array<int> &attr = fes.GetMesh()->GetElementAttributes();
+         B200_CHECK(b2f_operator_set_markers(op, i, attr.HostRead(), markers[i]->HostRead(), markers[i]->Size()));
+      }
    }
    ~PAOperator() override
    {

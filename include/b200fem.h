@@ -175,6 +175,10 @@ int b2f_pa_data(const b2f_pa *pa, const double **data, int64_t *size);
  * Replaces (Smem)PADiffusionApply2D/3D (bilininteg_diffusion_kernels.hpp:514-1215) and
  * (Smem)PAMassApply2D/3D (bilininteg_mass_kernels.hpp:440-1165). */
 int b2f_pa_add_mult(b2f_pa *pa, const double *x_e, double *y_e);
+/* BilinearFormIntegrator::AddMultTransposePA (bilininteg.hpp:88): the same kernel for the
+ * symmetric operators; like the reference (bilininteg_diffusion_pa.cpp:95-106) it fails for a
+ * diffusion integrator with a non-symmetric matrix coefficient. */
+int b2f_pa_add_mult_transpose(b2f_pa *pa, const double *x_e, double *y_e);
 /* VectorDiffusionIntegrator / VectorMassIntegrator::AddMultPA (fem/integ/
  * bilininteg_vecdiffusion_pa.cpp, bilininteg_vecmass_pa.cpp; CEED BP2/4/6): the same operator on
  * every component of an E-vector laid out (dofs, vdim, NE); one quadrature-data load serves
@@ -183,6 +187,19 @@ int b2f_pa_add_mult_vec(b2f_pa *pa, int vdim, const double *x_e, double *y_e);
 /* BilinearFormIntegrator::AssembleDiagonalPA (bilininteg.hpp:68): diag_e += diag(A_e).
  * Replaces (Smem)PADiffusionDiagonal2D/3D, (Smem)PAMassAssembleDiagonal2D/3D. */
 int b2f_pa_assemble_diagonal(b2f_pa *pa, double *diag_e);
+
+/* ---- DomainLFIntegrator fast assembly (LinearForm::UseFastAssembly) ------------------- */
+/* DomainLFIntegrator / VectorDomainLFIntegrator::AssembleDevice (fem/integ/
+ * lininteg_domain.cpp:21-72) -> DLFEvalAssemble2D/3D (lininteg_domain_kernels.hpp:76-297):
+ * y_e(d, c, e) += sum_q B(q,d) W(q) f_c(q,e) detJ(q,e) on E-vectors (D1D^dim, vdim, NE).
+ * markers (device, [NE], 0 = skip the element) may be NULL; detJ (device, (Q^dim, NE)) as
+ * GeometricFactors::detJ; coeff (device) is the CoefficientVector: vdim constants
+ * (coeff_size == vdim) or (vdim, Q^dim, NE).  LinearFormExtension::Assemble
+ * (fem/linearform_ext.cpp:20-66) then applies b2f_restriction_mult_transpose. */
+int b2f_domain_lf_assemble(b2f_ctx *ctx, int dim, int d1d, int q1d, int vdim, int64_t ne,
+                           const int *markers, const double *B_h, const double *W_h,
+                           const double *detJ, const double *coeff, int64_t coeff_size,
+                           double *y_e);
 
 /* ---- PABilinearFormExtension + ConstrainedOperator ---------------------------------- */
 /* PABilinearFormExtension (fem/bilinearform_ext.cpp:256-564) over one restriction and
@@ -211,6 +228,15 @@ int b2f_operator_eliminate_rhs(b2f_operator *op, const double *x_l, double *b_l)
  * RAPOperator(P, A, P) (linalg/operator.hpp:981-1033) on true-dof vectors. */
 int b2f_operator_set_halo(b2f_operator *op, b2f_halo *halo);
 int b2f_operator_height(const b2f_operator *op); /* true-dof size if a halo is set */
+/* BilinearForm::AddDomainIntegrator(bfi, elem_marker) (fem/bilinearform.hpp; applied by
+ * PABilinearFormExtension::AddMultWithMarkers / AssembleDiagonal, bilinearform_ext.cpp:
+ * 374-399, 753-847): integrator `integrator` acts only on elements e with
+ * markers_h[elem_attributes_h[e] - 1] != 0 (attributes are 1-based as in Mesh::GetAttribute).
+ * markers_h = NULL removes the restriction.  The enabled elements are compacted at this call,
+ * so the fused operator streams only them; the diagonal follows the reference literally
+ * (the E-diagonal accumulated so far is reset on the integrator's unmarked elements). */
+int b2f_operator_set_markers(b2f_operator *op, int integrator, const int *elem_attributes_h,
+                             const int *markers_h, int n_markers);
 /* Declare that elements [0, n_interior) touch no dof owned by another rank (the partition
  * generator orders elements that way).  With a peer-memory halo the operator then overlaps
  * the shared-dof exchange with interior-element work (the reference overlaps its local copy

@@ -79,8 +79,11 @@ PROTOTYPES = {
     "b2f_pa_destroy": (None, [vp]),
     "b2f_pa_data": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
     "b2f_pa_add_mult": (C.c_int, [vp, vp, vp]),
+    "b2f_pa_add_mult_transpose": (C.c_int, [vp, vp, vp]),
     "b2f_pa_add_mult_vec": (C.c_int, [vp, C.c_int, vp, vp]),
     "b2f_pa_assemble_diagonal": (C.c_int, [vp, vp]),
+    "b2f_domain_lf_assemble": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, i64, vp, vp, vp, vp, vp, i64,
+                                         vp]),
     "b2f_operator_create": (C.c_int, [vp, vp, C.POINTER(vp), C.c_int, vp, C.c_int, C.POINTER(vp)]),
     "b2f_operator_destroy": (None, [vp]),
     "b2f_operator_mult": (C.c_int, [vp, vp, vp]),
@@ -91,6 +94,7 @@ PROTOTYPES = {
     "b2f_operator_set_halo": (C.c_int, [vp, vp]),
     "b2f_operator_height": (C.c_int, [vp]),
     "b2f_operator_set_interior": (C.c_int, [vp, i64]),
+    "b2f_operator_set_markers": (C.c_int, [vp, C.c_int, vp, vp, C.c_int]),
     "b2f_jacobi_setup": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, C.c_double, vp]),
     "b2f_jacobi_mult": (C.c_int, [vp, C.c_int, vp, vp, vp]),
     "b2f_vector_dot": (C.c_int, [vp, i64, vp, vp, c_double_p]),

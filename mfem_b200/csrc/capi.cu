@@ -40,6 +40,9 @@ int pcg_update(b2f_ctx *ctx, void *state, int64_t n, double *x, const double *d,
                const double *q, const double *dinv, double *z);
 int pcg_after_betanom(b2f_ctx *ctx, void *state, double *history, int history_cap);
 int pcg_direction(b2f_ctx *ctx, void *state, int64_t n, const double *z, double *d);
+int lf_domain(b2f_ctx *ctx, int dim, int d, int q, int vdim, int64_t ne, const int *markers,
+              const double *B_d, const double *W_d, const double *detJ, const double *coeff, int cst,
+              double *y_e);
 int cheb_step(b2f_ctx *ctx, int64_t n, const double *src, const double *dinv, double c, double *res,
               double *y, bool first);
 int normalize_by(b2f_ctx *ctx, int64_t n, const double *d_normsq, double *v);
@@ -461,6 +464,15 @@ int b2f_pa_add_mult(b2f_pa *pa, const double *x_e, double *y_e)
    return pa_apply(pa, x_e, y_e, nullptr);
 }
 
+int b2f_pa_add_mult_transpose(b2f_pa *pa, const double *x_e, double *y_e)
+{
+   B2F_REQUIRE(pa && (pa->ne == 0 || (x_e && y_e)), "b2f_pa_add_mult_transpose: NULL argument");
+   // bilininteg_diffusion_pa.cpp:95-106, bilininteg_mass_pa.cpp (AddMultTransposePA = AddMultPA)
+   B2F_REQUIRE(pa->kind == B2F_KIND_MASS || pa->symmetric,
+               "DiffusionIntegrator::AddMultTransposePA only implemented in the symmetric case.");
+   return pa_apply(pa, x_e, y_e, nullptr);
+}
+
 int b2f_pa_add_mult_vec(b2f_pa *pa, int vdim, const double *x_e, double *y_e)
 {
    B2F_REQUIRE(pa && vdim >= 1 && (pa->ne == 0 || (x_e && y_e)), "b2f_pa_add_mult_vec: bad argument");
@@ -469,6 +481,28 @@ int b2f_pa_add_mult_vec(b2f_pa *pa, int vdim, const double *x_e, double *y_e)
    pa->vd = vdim;
    const int rc = pa_apply(pa, x_e, y_e, nullptr);
    pa->vd = 1;
+   return rc;
+}
+
+int b2f_domain_lf_assemble(b2f_ctx *ctx, int dim, int d1d, int q1d, int vdim, int64_t ne,
+                           const int *markers, const double *B_h, const double *W_h, const double *detJ,
+                           const double *coeff, int64_t coeff_size, double *y_e)
+{
+   B2F_REQUIRE(ctx && B_h && W_h && coeff && (ne == 0 || (detJ && y_e)), "b2f_domain_lf_assemble: NULL argument");
+   B2F_REQUIRE(dim == 2 || dim == 3, "b2f_domain_lf_assemble: dim = %d", dim);
+   B2F_REQUIRE(d1d >= 1 && d1d <= 16 && q1d >= 1 && q1d <= 16 && vdim >= 1,
+               "b2f_domain_lf_assemble: D1D = %d, Q1D = %d, vdim = %d", d1d, q1d, vdim);
+   int nq = 1;
+   for (int i = 0; i < dim; i++) { nq *= q1d; }
+   const int cst = coeff_size == vdim;
+   B2F_REQUIRE(cst || coeff_size == (int64_t)vdim * nq * ne, "b2f_domain_lf_assemble: coeff_size = %lld",
+               (long long)coeff_size);
+   double *B_d = nullptr, *W_d = nullptr;
+   B2F_TRY(upload(B_h, (size_t)d1d * q1d, &B_d));
+   int rc = upload(W_h, (size_t)nq, &W_d);
+   if (rc == B2F_OK) { rc = lf_domain(ctx, dim, d1d, q1d, vdim, ne, markers, B_d, W_d, detJ, coeff, cst, y_e); }
+   if (rc == B2F_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = B2F_ERR_CUDA; }
+   cudaFree(B_d); cudaFree(W_d);
    return rc;
 }
 
@@ -503,10 +537,103 @@ __global__ void mark_kernel(int n, const int *__restrict__ idx, unsigned char *f
    const int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i < n) { flags[idx[i]] = 1; }
 }
+} // extern "C"
+// dst row j = src row rows[j]   (row_len entries each)
+template <typename T>
+__global__ void compact_rows_kernel(int64_t n_rows, int64_t row_len, const int *__restrict__ rows,
+                                    const T *__restrict__ src, T *__restrict__ dst)
+{
+   const int64_t total = n_rows * row_len;
+   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+        i += (int64_t)gridDim.x * blockDim.x)
+   {
+      const int64_t j = i / row_len, k = i - j * row_len;
+      dst[i] = src[(int64_t)rows[j] * row_len + k];
+   }
+}
+extern "C" {
+// AddWithMarkers_ (bilinearform_ext.cpp:753-774): y_e += t_e on the marked elements
+__global__ void add_marked_kernel(int64_t n, int64_t nd, const unsigned char *__restrict__ on,
+                                  const double *__restrict__ t, double *y)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n && on[i / nd]) { y[i] += t[i]; }
+}
+// assemble_diagonal_with_markers (bilinearform_ext.cpp:374-399): the accumulated E-diagonal
+// of the unmarked elements is reset to 0
+__global__ void zero_unmarked_kernel(int64_t n, int64_t nd, const unsigned char *__restrict__ on, double *d)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n && !on[i / nd]) { d[i] = 0.0; }
+}
 __global__ void any_negative_kernel(int64_t n, const int *__restrict__ v, int *flag)
 {
    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (i < n && v[i] < 0) { *flag = 1; }
+}
+
+static void marked_free_device(b2f_marked *m)
+{
+   if (!m) { return; }
+   if (m->cpa) { cudaFree(m->cpa->data); delete m->cpa; m->cpa = nullptr; }
+   cudaFree(m->idx_c); m->idx_c = nullptr;
+   cudaFree(m->fidx_c); m->fidx_c = nullptr;
+   cudaFree(m->on); m->on = nullptr;
+}
+
+// compact the enabled elements of integrator i (data slabs, gather rows, masked gather rows)
+static int marked_rebuild(b2f_operator *op, size_t i)
+{
+   b2f_marked *m = op->marked[i];
+   if (!m) { return B2F_OK; }
+   b2f_ctx *ctx = op->ctx;
+   const b2f_restriction *r = op->r;
+   const b2f_pa *pa = op->integ[i];
+   marked_free_device(m);
+   std::vector<int> rows;
+   for (int e = 0; e < r->ne; e++) { if (m->on_h[e]) { rows.push_back(e); } }
+   m->ne_c = (int64_t)rows.size();
+   B2F_TRY(upload(m->on_h.data(), m->on_h.size(), &m->on));
+   int *d_rows = nullptr;
+   B2F_TRY(upload(rows.data(), rows.size(), &d_rows));
+   const int64_t slab = pa->ne ? pa->data_size / pa->ne : 0;
+   m->cpa = new b2f_pa(*pa);
+   m->cpa->data = nullptr;
+   m->cpa->ne = m->ne_c;
+   m->cpa->data_size = slab * m->ne_c;
+   const int64_t nidx = m->ne_c * r->dof;
+   int rc = B2F_OK;
+   auto run = [&]() -> int
+   {
+      B2F_CUDA(cudaMalloc((void **)&m->cpa->data, sizeof(double) * (size_t)(m->cpa->data_size + 2)));
+      B2F_CUDA(cudaMalloc((void **)&m->idx_c, sizeof(int) * (size_t)(nidx + 4)));
+      if (m->ne_c)
+      {
+         compact_rows_kernel<double><<<(unsigned)std::min<int64_t>(cdiv(m->cpa->data_size, 256), 65535 * 16), 256,
+                                       0, ctx->stream>>>(m->ne_c, slab, d_rows, pa->data, m->cpa->data);
+         B2F_LAUNCH_CHECK(ctx);
+         compact_rows_kernel<int><<<(unsigned)std::min<int64_t>(cdiv(nidx, 256), 65535 * 16), 256, 0,
+                                    ctx->stream>>>(m->ne_c, r->dof, d_rows, r->gather_map, m->idx_c);
+         B2F_LAUNCH_CHECK(ctx);
+      }
+      if (op->fused_idx)
+      {
+         B2F_CUDA(cudaMalloc((void **)&m->fidx_c, sizeof(int) * (size_t)(nidx * r->vdim + 4)));
+         for (int c = 0; c < r->vdim && m->ne_c; c++)
+         {
+            compact_rows_kernel<int><<<(unsigned)std::min<int64_t>(cdiv(nidx, 256), 65535 * 16), 256, 0,
+                                       ctx->stream>>>(m->ne_c, r->dof, d_rows,
+                                                      op->fused_idx + (int64_t)c * r->ne * r->dof,
+                                                      m->fidx_c + c * nidx);
+            B2F_LAUNCH_CHECK(ctx);
+         }
+      }
+      B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+      return B2F_OK;
+   };
+   rc = run();
+   cudaFree(d_rows);
+   return rc;
 }
 
 // (re)build the essential-dof tables: ess_l = constrained LOCAL dofs (mask of the fused
@@ -553,6 +680,7 @@ static int operator_build_masks(b2f_operator *op, const int *ess_ldofs_h, int n_
       cudaFree(flags);
       cudaFree(d_ess_l);
    }
+   for (size_t i = 0; i < op->marked.size(); i++) { B2F_TRY(marked_rebuild(op, i)); }
    return B2F_OK;
 }
 
@@ -594,6 +722,7 @@ int b2f_operator_create(b2f_ctx *ctx, b2f_restriction *r, b2f_pa *const *integra
    op->ctx = ctx;
    op->r = r;
    op->integ.assign(integrators, integrators + n_integrators);
+   op->marked.assign((size_t)n_integrators, nullptr);
    op->ess_l_h.assign(ess_dofs_h, ess_dofs_h + n_ess);
    // signed gather maps (non-H1 spaces) cannot use the fused kernel's "-1 = skip" encoding
    {
@@ -628,6 +757,8 @@ void b2f_operator_destroy(b2f_operator *op)
    for (double *p : op->pcg_vec) { cudaFree(p); }
    cudaFree(op->pcg_hist);
    cudaFree(op->dot_acc);
+   cudaFree(op->te);
+   for (b2f_marked *m : op->marked) { marked_free_device(m); delete m; }
    delete op;
 }
 
@@ -650,8 +781,19 @@ static int local_mult_fused(b2f_operator *op, const double *x_l, double *y_l, co
    b2f_ctx *ctx = op->ctx;
    const b2f_restriction *r = op->r;
    B2F_CUDA(cudaMemsetAsync(y_l, 0, sizeof(double) * (size_t)r->ndofs * r->vdim, ctx->stream));
-   for (b2f_pa *pa : op->integ)
+   for (size_t i = 0; i < op->integ.size(); i++)
    {
+      b2f_pa *pa = op->integ[i];
+      const int *ix = idx;
+      int64_t ne_i = r->ne;
+      if (const b2f_marked *m = op->marked[i])
+      {
+         // marked integrator: its compacted elements with their own rows of the same index
+         if (m->ne_c == 0) { continue; }
+         pa = m->cpa;
+         ix = (idx == r->gather_map || !m->fidx_c) ? m->idx_c : m->fidx_c;
+         ne_i = m->ne_c;
+      }
       if (r->vdim > 1)
       {
          // Vector{Mass,Diffusion}Integrator: the scalar kernel per component, one quadrature-data
@@ -659,9 +801,9 @@ static int local_mult_fused(b2f_operator *op, const double *x_l, double *y_l, co
          pa->vd = r->vdim;
          pa->vxs = r->byvdim ? r->vdim : 1;
          pa->vxo = r->byvdim ? 1 : r->ndofs;
-         pa->vics = idx == r->gather_map ? 0 : (int64_t)r->ne * r->dof;
+         pa->vics = idx == r->gather_map ? 0 : ne_i * r->dof;
       }
-      const int rc = pa_apply(pa, x_l, y_l, idx, dot_acc);
+      const int rc = pa_apply(pa, x_l, y_l, ix, dot_acc);
       pa->vd = 1; pa->vxs = 1; pa->vxo = 0; pa->vics = 0;
       if (rc) { return rc; }
    }
@@ -672,10 +814,20 @@ static int local_mult_fused(b2f_operator *op, const double *x_l, double *y_l, co
 static int local_mult_range(b2f_operator *op, const double *x_l, double *y_l, const int *idx,
                             int64_t eb, int64_t ee, double *dot_acc)
 {
-   for (b2f_pa *pa : op->integ)
+   for (size_t i = 0; i < op->integ.size(); i++)
    {
-      pa->rb = eb; pa->re = ee;
-      const int rc = pa_apply(pa, x_l, y_l, idx, dot_acc);
+      b2f_pa *pa = op->integ[i];
+      const int *ix = idx;
+      int64_t b = eb, e = ee;
+      if (const b2f_marked *m = op->marked[i])
+      {
+         pa = m->cpa;
+         ix = (idx == op->r->gather_map || !m->fidx_c) ? m->idx_c : m->fidx_c;
+         b = m->prefix[eb]; e = m->prefix[ee]; // compaction keeps the element order
+         if (b == e) { continue; }
+      }
+      pa->rb = b; pa->re = e;
+      const int rc = pa_apply(pa, x_l, y_l, ix, dot_acc);
       pa->rb = 0; pa->re = -1;
       if (rc) { return rc; }
    }
@@ -709,12 +861,27 @@ static int local_mult_unfused(b2f_operator *op, const double *x_l, double *y_l)
    B2F_TRY(ensure(&op->ye, ne_dof));
    B2F_TRY(restriction_gather(r, x_l, op->xe, false));                 // bilinearform_ext.cpp:543
    B2F_CUDA(cudaMemsetAsync(op->ye, 0, sizeof(double) * ne_dof, ctx->stream)); // :545
-   for (b2f_pa *pa : op->integ)                                        // :548
+   for (size_t i = 0; i < op->integ.size(); i++)                       // :548
    {
+      b2f_pa *pa = op->integ[i];
+      double *out = op->ye;
+      if (op->marked[i])
+      {
+         // AddMultWithMarkers (:807-833): into a zeroed temporary, then the masked add
+         B2F_TRY(ensure(&op->te, ne_dof));
+         B2F_CUDA(cudaMemsetAsync(op->te, 0, sizeof(double) * ne_dof, ctx->stream));
+         out = op->te;
+      }
       pa->vd = r->vdim;
-      const int rc = pa_apply(pa, op->xe, op->ye, nullptr);
+      const int rc = pa_apply(pa, op->xe, out, nullptr);
       pa->vd = 1;
       if (rc) { return rc; }
+      if (op->marked[i] && ne_dof)
+      {
+         add_marked_kernel<<<(unsigned)cdiv(ne_dof, 256), 256, 0, ctx->stream>>>(
+            ne_dof, (int64_t)r->dof * r->vdim, op->marked[i]->on, op->te, op->ye);
+         B2F_LAUNCH_CHECK(ctx);
+      }
    }
    return restriction_scatter(r, op->ye, y_l, 0);                      // :557
 }
@@ -786,6 +953,42 @@ static int rap_mult(b2f_operator *op, const double *x, double *y, bool constrain
    B2F_TRY(halo_mult(op->halo, x, op->xl));
    B2F_TRY(local_mult(op, op->xl, op->yl, constrained_mask, dot_acc));
    return halo_mult_transpose(op->halo, op->yl, y);
+}
+
+int b2f_operator_set_markers(b2f_operator *op, int integrator, const int *elem_attributes_h,
+                             const int *markers_h, int n_markers)
+{
+   B2F_REQUIRE(op, "b2f_operator_set_markers: NULL handle");
+   B2F_REQUIRE(integrator >= 0 && integrator < (int)op->integ.size(),
+               "b2f_operator_set_markers: integrator %d of %d", integrator, (int)op->integ.size());
+   if (b2f_marked *old = op->marked[integrator])
+   {
+      B2F_CUDA(cudaStreamSynchronize(op->ctx->stream));
+      marked_free_device(old);
+      delete old;
+      op->marked[integrator] = nullptr;
+   }
+   if (!markers_h) { return B2F_OK; } // acts on every element again
+   const int ne = op->r->ne;
+   B2F_REQUIRE(elem_attributes_h || ne == 0, "b2f_operator_set_markers: elem_attributes_h is NULL");
+   b2f_marked *m = new b2f_marked;
+   m->on_h.resize((size_t)ne);
+   m->prefix.resize((size_t)ne + 1);
+   m->prefix[0] = 0;
+   for (int e = 0; e < ne; e++)
+   {
+      const int attr = elem_attributes_h[e];
+      if (attr > n_markers)
+      {
+         delete m;
+         B2F_REQUIRE(false, "b2f_operator_set_markers: element %d has attribute %d, the marker array %d entries",
+                     e, attr, n_markers);
+      }
+      m->on_h[e] = !(attr <= 0 || markers_h[attr - 1] == 0); // bilinearform_ext.cpp:768
+      m->prefix[e + 1] = m->prefix[e] + m->on_h[e];
+   }
+   op->marked[integrator] = m;
+   return marked_rebuild(op, (size_t)integrator);
 }
 
 int b2f_operator_set_interior(b2f_operator *op, int64_t n_interior)
@@ -866,7 +1069,17 @@ int b2f_operator_assemble_diagonal(b2f_operator *op, double *diag)
    const int64_t ne_dof = (int64_t)r->ne * r->dof;
    B2F_TRY(ensure(&op->ye, ne_dof));
    B2F_CUDA(cudaMemsetAsync(op->ye, 0, sizeof(double) * ne_dof, ctx->stream)); // bilinearform_ext.cpp:385
-   for (b2f_pa *pa : op->integ) { B2F_TRY(pa_diag(pa, op->ye)); }
+   for (size_t i = 0; i < op->integ.size(); i++)
+   {
+      B2F_TRY(pa_diag(op->integ[i], op->ye));
+      if (op->marked[i] && ne_dof)
+      {
+         // the reference resets what has been accumulated so far on the unmarked elements
+         zero_unmarked_kernel<<<(unsigned)cdiv(ne_dof, 256), 256, 0, ctx->stream>>>(ne_dof, r->dof,
+                                                                                   op->marked[i]->on, op->ye);
+         B2F_LAUNCH_CHECK(ctx);
+      }
+   }
    if (r->vdim > 1)
    {
       // vector integrators: the scalar diagonal for every component

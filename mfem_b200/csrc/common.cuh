@@ -118,11 +118,28 @@ struct b2f_pa
    int64_t vxs = 1, vxo = 0, vics = 0;
 };
 
+// A domain integrator restricted to the elements whose attribute is marked
+// (BilinearForm::AddDomainIntegrator(bfi, elem_marker), bilinearform_ext.cpp:753-847).
+// The enabled elements' quadrature data and gather-index rows are compacted at setup, so
+// the fused kernels stream only those elements.
+struct b2f_marked
+{
+   std::vector<unsigned char> on_h;  // [NE] element enabled
+   std::vector<int64_t> prefix;      // [NE+1] enabled elements before e
+   unsigned char *on = nullptr;      // device copy of on_h
+   b2f_pa *cpa = nullptr;            // shallow copy of the integrator over the compacted data
+   int *idx_c = nullptr;             // compacted gather_map rows
+   int *fidx_c = nullptr;            // compacted fused_idx rows (vdim copies), if any
+   int64_t ne_c = 0;
+};
+
 struct b2f_operator
 {
    b2f_ctx *ctx;
    b2f_restriction *r;
    std::vector<b2f_pa *> integ;
+   std::vector<b2f_marked *> marked;    // per integrator, nullptr = acts on every element
+   double *te = nullptr;                // E-vector scratch of the marked unfused path
    int n_ess = 0;
    int *ess = nullptr;          // device list of essential ldofs / tdofs
    int *fused_idx = nullptr;    // gather_map with ess dofs marked -1 (constrained fused path);

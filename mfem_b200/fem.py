@@ -435,6 +435,9 @@ class _PAIntegrator:
         else:
             call("b2f_pa_add_mult_vec", self.h, vdim, _dp(x_e), _dp(y_e))
 
+    def AddMultTransposePA(self, x_e, y_e):
+        call("b2f_pa_add_mult_transpose", self.h, _dp(x_e), _dp(y_e))
+
     def AssembleDiagonalPA(self, diag_e):
         call("b2f_pa_assemble_diagonal", self.h, _dp(diag_e))
 
@@ -520,6 +523,8 @@ class BilinearForm:
     def __init__(self, device, fes):
         self.dev, self.fes = device, fes
         self.integrators = []
+        self.markers = []          # per integrator: None or the 0/1 array indexed by attribute - 1
+        self.elem_attributes = None
         self.op = None
         self.ess = np.zeros(0, np.int32)
         self.halo = None
@@ -528,8 +533,15 @@ class BilinearForm:
         if level != "PARTIAL":
             raise ValueError("only AssemblyLevel::PARTIAL exists on this path")
 
-    def AddDomainIntegrator(self, integ):
+    def AddDomainIntegrator(self, integ, elem_marker=None):
+        """elem_marker: BilinearForm::AddDomainIntegrator(bfi, elem_marker) -- the integrator acts
+        on the elements whose attribute a has elem_marker[a-1] != 0; the element attributes
+        come from SetElementAttributes (Mesh::GetElementAttributes, mesh/mesh.cpp:1040)."""
         self.integrators.append(integ)
+        self.markers.append(None if elem_marker is None else _i32(elem_marker))
+
+    def SetElementAttributes(self, attributes):
+        self.elem_attributes = _i32(attributes)
 
     def Assemble(self):
         self.restr = self.fes.GetElementRestriction(self.dev)
@@ -548,6 +560,11 @@ class BilinearForm:
         call("b2f_operator_create", self.dev.ctx, self.restr.h, arr, len(self.integrators),
              _np_ptr(ess) if len(ess) else None, len(ess), C.byref(h))
         self.op, self.ess = h, ess
+        for i, mk in enumerate(self.markers):
+            if mk is not None:
+                if self.elem_attributes is None:
+                    raise ValueError("AddDomainIntegrator(elem_marker): call SetElementAttributes first")
+                call("b2f_operator_set_markers", self.op, i, _np_ptr(self.elem_attributes), _np_ptr(mk), len(mk))
         if self.halo is not None:
             call("b2f_operator_set_halo", self.op, self.halo.h)
             self._set_interior()
@@ -742,6 +759,14 @@ def vector_dot(device, x, y):
     r = C.c_double()
     call("b2f_vector_dot", device.ctx, x.numel(), _dp(x), _dp(y), C.byref(r))
     return r.value
+
+
+def domain_lf_assemble(device, dim, d1d, q1d, vdim, ne, B, W, detJ_d, coeff_d, y_e, markers_d=None):
+    """DomainLFIntegrator / VectorDomainLFIntegrator::AssembleDevice (fem/integ/lininteg_domain.cpp:
+    21-72) on device E-vectors: y_e += B^T (W f detJ)."""
+    B, W = _f64(B), _f64(W)
+    call("b2f_domain_lf_assemble", device.ctx, dim, d1d, q1d, vdim, ne, _dp(markers_d), _np_ptr(B), _np_ptr(W),
+         _dp(detJ_d), _dp(coeff_d), coeff_d.numel(), _dp(y_e))
 
 
 class LinearForm:

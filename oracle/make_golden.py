@@ -74,6 +74,19 @@ CASES = {
     "cheb_diff2d_p3_n4": dict(dim=2, n=4, p=3, kind="diffusion", cheb=1, order=4),
     "cheb_mass3d_p3_n2": dict(dim=3, n=2, p=3, kind="mass", cheb=1, order=5),
     "cheb_bp5_3d_p5_n2": dict(dim=3, n=2, p=5, kind="diffusion", quad="gll", cheb=1, order=3),
+    # integrators restricted by element attribute (AddDomainIntegrator(bfi, elem_marker))
+    "mark_3d_p2_n3": dict(dim=3, n=3, p=2, kind="diffusion", markers=1, nattr=3, maxit=25),
+    "mark_3d_p4_n2_curved": dict(dim=3, n=2, p=4, kind="diffusion", markers=1, nattr=3, curved=1, maxit=25),
+    "mark_3d_p3_n3_plain_first": dict(dim=3, n=3, p=3, kind="diffusion", markers=1, nattr=2, marker_order=1,
+                                      jacobi=0, maxit=25),
+    "mark_2d_p3_n5": dict(dim=2, n=5, p=3, kind="diffusion", markers=1, nattr=3, maxit=25),
+    # DomainLFIntegrator / VectorDomainLFIntegrator device assembly (LinearForm::UseFastAssembly)
+    "lf_3d_p2_n3": dict(dim=3, n=3, p=2, kind="mass", lf=1, nattr=2),
+    "lf_3d_p4_n2_curved": dict(dim=3, n=2, p=4, kind="mass", lf=1, nattr=3, curved=1),
+    "lf_3d_p7_n2_gll": dict(dim=3, n=2, p=7, kind="mass", quad="gll", lf=1, nattr=2),
+    "lf_2d_p3_n4_curved": dict(dim=2, n=4, p=3, kind="mass", lf=1, nattr=2, curved=1),
+    "lf_3d_p3_n2_vec_byvdim": dict(dim=3, n=2, p=3, kind="mass", lf=1, nattr=2, vdim=3, byvdim=1),
+    "lf_3d_p2_n2_vec_bynodes": dict(dim=3, n=2, p=2, kind="mass", lf=1, nattr=2, vdim=3, byvdim=0, curved=1),
 }
 
 

@@ -164,6 +164,16 @@ def mass_diag(dim, d1d, q1d, ne, B, D):
     return Y
 
 
+def domain_lf(dim, d1d, q1d, vdim, ne, B, W, detJ, coeff, markers=None):
+    """DomainLFIntegrator::AssembleDevice on a zeroed E-vector (D1D^dim, vdim, NE)."""
+    coeff = _f64(coeff)
+    y = np.zeros(ne * vdim * d1d ** dim)
+    mk = _i32(markers) if markers is not None else None
+    lib().orc_domain_lf(dim, d1d, q1d, vdim, ne, _p(mk) if mk is not None else None, _p(_f64(B)),
+                        _p(_f64(W)), _p(_f64(detJ)), _p(coeff), int(coeff.size == vdim), _p(y))
+    return y
+
+
 def randomize(n, seed):
     v = np.empty(n)
     lib().orc_randomize(n, seed, _p(v))
@@ -254,6 +264,62 @@ class Operator:
         its = f(C.byref(self.op), _p(_f64(dinv)), order, _p(c), _p(_f64(b)), _p(x), C.c_double(rel_tol),
                 C.c_double(abs_tol), max_iter, C.byref(conv), C.byref(fn), _p(hist), len(hist))
         return x, its, bool(conv.value), fn.value, hist[:its + 1]
+
+
+class MarkedForm:
+    """BilinearForm with PA domain integrators restricted by element attribute
+    (PABilinearFormExtension::MultInternal / AddMultWithMarkers / AssembleDiagonal,
+    fem/bilinearform_ext.cpp:370-454,487-564,753-847), on top of the oracle's element kernels.
+    integrators: list of (kind, D, marker-or-None), kind in {"diffusion", "mass"}."""
+
+    def __init__(self, dim, d1d, q1d, ne, ndofs, gather_map, offsets, indices, B, G, attributes, integrators):
+        self.dim, self.d1d, self.q1d, self.ne, self.ndofs = dim, d1d, q1d, ne, ndofs
+        self.g, self.o, self.i = _i32(gather_map), _i32(offsets), _i32(indices)
+        self.B, self.G = _f64(B), _f64(G)
+        self.attr = _i32(attributes)
+        self.integ = integrators
+        self.dof = d1d ** dim
+
+    def _on(self, marker):
+        a = self.attr
+        m = _i32(marker)
+        return (a > 0) & (m[np.maximum(a, 1) - 1] != 0)        # bilinearform_ext.cpp:768
+
+    def _apply(self, kind, D, xe):
+        if kind == "mass":
+            return mass_apply(self.dim, self.d1d, self.q1d, self.ne, self.B, D, xe)
+        return diffusion_apply(self.dim, self.d1d, self.q1d, self.ne, self.B, self.G, D, xe)
+
+    def mult(self, x):
+        xe = restriction_mult(self.ne, self.dof, self.g, x)
+        ye = np.zeros_like(xe)
+        for kind, D, marker in self.integ:
+            t = self._apply(kind, D, xe)                        # into a zeroed temporary (:818-829)
+            if marker is None:
+                ye += t
+            else:
+                on = np.repeat(self._on(marker), self.dof)
+                ye[on] += t[on]                                  # AddWithMarkers_ (:753-774)
+        return restriction_mult_transpose(self.ndofs, self.dof, self.o, self.i, ye)
+
+    def diag(self):
+        de = np.zeros(self.ne * self.dof)
+        for kind, D, marker in self.integ:
+            if kind == "mass":
+                de += mass_diag(self.dim, self.d1d, self.q1d, self.ne, self.B, D)
+            else:
+                de += diffusion_diag(self.dim, self.d1d, self.q1d, self.ne, self.B, self.G, D)
+            if marker is not None:
+                # the reference zeroes the ACCUMULATED E-diagonal on unmarked elements (:374-399)
+                de[np.repeat(~self._on(marker), self.dof)] = 0.0
+        return restriction_abs_mult_transpose(self.ndofs, self.dof, self.o, self.i, de)
+
+    def mult_constrained(self, x, ess):
+        z = _f64(x).copy()
+        z[ess] = 0.0
+        y = self.mult(z)
+        y[ess] = x[ess]
+        return y
 
 
 def chebyshev_coeffs(order, max_eig):

@@ -108,6 +108,9 @@ int orc_pcg(const orc_operator *op, const double *dinv, const double *b, double 
             double *final_norm, double *history, int history_cap);
 
 /* linalg/vector.cpp:955-966: srand(seed); v[i] = rand()/(RAND_MAX+1.0) */
+/* DomainLFIntegrator device assembly (fem/integ/lininteg_domain_kernels.hpp:76-297) */
+void orc_domain_lf(int dim, int d, int q, int vdim, int ne, const int *markers, const double *B,
+                   const double *W, const double *detJ, const double *coeff, int cst, double *y);
 /* OperatorChebyshevSmoother (linalg/solvers.cpp:453-658), PowerMethod (linalg/operator.cpp:886) */
 int orc_chebyshev_coeffs(int order, double max_eig, double *coeffs);
 void orc_chebyshev_mult(const orc_operator *op, const double *dinv, int order, const double *coeffs,

@@ -147,6 +147,12 @@ struct Problem
          mesh = Mesh::MakeCartesian2D(n, ny, Element::QUADRILATERAL, false, 1.0, 1.0, sfc);
       }
       if (curved) { mesh.SetCurvature(A.geti("node_order", 3)); mesh.Transform(curve_map); }
+      if (const int nattr = A.geti("nattr", 0))
+      {
+         // element attributes 1..nattr in short runs (for the marked-integrator dump)
+         for (int e = 0; e < mesh.GetNE(); e++) { mesh.SetAttribute(e, 1 + (e / 3 + e / 7) % nattr); }
+         mesh.SetAttributes();
+      }
       fec = new H1_FECollection(p, dim);
       fes = vdim == 1 ? new FiniteElementSpace(&mesh, fec)
             : new FiniteElementSpace(&mesh, fec, vdim, byvdim ? Ordering::byVDIM : Ordering::byNODES);
@@ -506,6 +512,195 @@ static int do_dump_nonsym(const Args &A, const char *out)
    return 0;
 }
 
+// DomainLFIntegrator / VectorDomainLFIntegrator fast assembly (LinearForm::UseFastAssembly,
+// fem/linearform_ext.cpp:20-66; fem/integ/lininteg_domain.cpp, lininteg_domain_kernels.hpp)
+static double lf_coeff(const Vector &x)
+{
+   double s = 1.0 + x(0) + 2.0 * x(1) * x(1);
+   if (x.Size() > 2) { s += std::sin(3.0 * x(2)); }
+   return s;
+}
+static void lf_vcoeff(const Vector &x, Vector &v)
+{
+   for (int c = 0; c < v.Size(); c++) { v(c) = lf_coeff(x) * (c + 1) + 0.25 * c * x(c % x.Size()); }
+}
+static int do_dump_lf(const Args &A, const char *out)
+{
+   Problem P(A);
+   Dump D(out);
+   const int dim = P.dim, vdim = P.vdim;
+   FiniteElementSpace &fes = *P.fes;
+   const FiniteElement &fe = *fes.GetTypicalFE();
+   const DofToQuad &maps = fe.GetDofToQuad(*P.ir, DofToQuad::TENSOR);
+   const int D1D = maps.ndof, Q1D = maps.nqpt, NE = fes.GetNE(), ndofs = fes.GetNDofs();
+   D.scalar("dim", dim); D.scalar("n", P.n); D.scalar("p", P.p); D.scalar("vdim", vdim);
+   D.scalar("byvdim", P.byvdim);
+   D.scalar("D1D", D1D); D.scalar("Q1D", Q1D); D.scalar("NE", NE); D.scalar("ndofs", ndofs);
+   auto R = dynamic_cast<const ElementRestriction *>(
+               fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC));
+   D.ints("gather_map", R->GatherMap());
+   D.ints("offsets", R->Offsets());
+   D.ints("indices", R->Indices());
+   D.dbls("B", maps.B);
+   D.dbls("W", P.ir->GetWeights());
+   const GeometricFactors *geom = P.mesh.GetGeometricFactors(*P.ir, GeometricFactors::DETERMINANTS);
+   D.dbls("detJ", geom->detJ);
+   FunctionCoefficient f(lf_coeff);
+   VectorFunctionCoefficient vf(vdim, lf_vcoeff);
+   QuadratureSpace qs(P.mesh, *P.ir);
+   std::unique_ptr<LinearFormIntegrator> integ, integ2;
+   if (vdim == 1)
+   {
+      CoefficientVector cv(f, qs, CoefficientStorage::COMPRESSED);
+      D.dbls("coeff", cv);
+      integ.reset(new DomainLFIntegrator(f, P.ir));
+      integ2.reset(new DomainLFIntegrator(f, P.ir));
+   }
+   else
+   {
+      CoefficientVector cv(vf, qs, CoefficientStorage::COMPRESSED);
+      D.dbls("coeff", cv);
+      integ.reset(new VectorDomainLFIntegrator(vf, P.ir));
+      integ2.reset(new VectorDomainLFIntegrator(vf, P.ir));
+   }
+   // the integrator's device kernel on an E-vector, with element markers
+   const Array<int> &attr = P.mesh.GetElementAttributes();
+   D.ints("elem_attributes", attr);
+   Array<int> markers(NE);
+   for (int e = 0; e < NE; e++) { markers[e] = (attr[e] % 2 == 1); }
+   D.ints("markers", markers);
+   Vector be(R->Height());
+   be = 0.0;
+   integ->AssembleDevice(fes, markers, be);
+   D.dbls("b_e_marked", be);
+   markers = 1;
+   be = 0.0;
+   integ->AssembleDevice(fes, markers, be);
+   D.dbls("b_e", be);
+   // constant coefficient (CoefficientVector of size vdim)
+   {
+      ConstantCoefficient c3(3.0);
+      Vector cvec(vdim);
+      for (int c = 0; c < vdim; c++) { cvec(c) = 1.5 + c; }
+      VectorConstantCoefficient vc3(cvec);
+      std::unique_ptr<LinearFormIntegrator> ic;
+      if (vdim == 1) { ic.reset(new DomainLFIntegrator(c3, P.ir)); }
+      else { ic.reset(new VectorDomainLFIntegrator(vc3, P.ir)); }
+      be = 0.0;
+      ic->AssembleDevice(fes, markers, be);
+      D.dbls("b_e_const", be);
+   }
+   // the whole LinearForm: fast assembly and the legacy element loop
+   LinearForm lf(&fes);
+   lf.AddDomainIntegrator(integ.release());
+   lf.UseFastAssembly(true);
+   lf.Assemble();
+   D.dbls("b_fast", lf);
+   LinearForm lf2(&fes);
+   lf2.AddDomainIntegrator(integ2.release());
+   lf2.Assemble();
+   D.dbls("b_legacy", lf2);
+   Vector diff(lf); diff -= lf2;
+   std::printf("dump %s: linear form dim=%d vdim=%d NE=%d p=%d |b|=%.17g fast-legacy=%.3e\n", out, dim, vdim, NE,
+               P.p, lf.Norml2(), diff.Norml2() / lf2.Norml2());
+   return 0;
+}
+
+// BilinearForm::AddDomainIntegrator(bfi, elem_marker): integrators restricted by element
+// attribute (PABilinearFormExtension::AddMultWithMarkers / AssembleDiagonal,
+// fem/bilinearform_ext.cpp:370-454,753-847).  Three integrators on a mesh with 3 attributes:
+// diffusion on attributes {1,3}, mass on {2}, mass (coefficient 0.5) unrestricted.
+static int do_dump_markers(const Args &A, const char *out)
+{
+   Problem P(A);
+   Dump D(out);
+   const int dim = P.dim;
+   FiniteElementSpace &fes = *P.fes;
+   const FiniteElement &fe = *fes.GetTypicalFE();
+   const DofToQuad &maps = fe.GetDofToQuad(*P.ir, DofToQuad::TENSOR);
+   const int D1D = maps.ndof, Q1D = maps.nqpt, NE = fes.GetNE(), ndofs = fes.GetNDofs();
+   const int nattr = P.mesh.attributes.Max();
+   Array<int> m_diff(nattr), m_mass(nattr);
+   for (int k = 0; k < nattr; k++) { m_diff[k] = (k % 2 == 0); m_mass[k] = (k % 2 == 1); }
+   ConstantCoefficient half(0.5);
+   BilinearForm a(&fes);
+   a.SetAssemblyLevel(AssemblyLevel::PARTIAL);
+   auto *bd = new DiffusionIntegrator(P.one, P.ir);
+   auto *bm = new MassIntegrator(P.one, P.ir);
+   auto *bh = new MassIntegrator(half, P.ir);
+   const int order = A.geti("marker_order", 0); // 0: marked, marked, plain; 1: plain first
+   if (order == 1) { a.AddDomainIntegrator(bh); }
+   a.AddDomainIntegrator(bd, m_diff);
+   a.AddDomainIntegrator(bm, m_mass);
+   if (order == 0) { a.AddDomainIntegrator(bh); }
+   a.Assemble();
+   D.scalar("dim", dim); D.scalar("n", P.n); D.scalar("p", P.p);
+   D.scalar("D1D", D1D); D.scalar("Q1D", Q1D); D.scalar("NE", NE); D.scalar("ndofs", ndofs);
+   D.scalar("marker_order", order);
+   auto R = dynamic_cast<const ElementRestriction *>(
+               fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC));
+   D.ints("gather_map", R->GatherMap());
+   D.ints("offsets", R->Offsets());
+   D.ints("indices", R->Indices());
+   D.dbls("B", maps.B); D.dbls("G", maps.G);
+   D.dbls("W", P.ir->GetWeights());
+   {
+      const GeometricFactors *geom = P.mesh.GetGeometricFactors(
+                                        *P.ir, GeometricFactors::JACOBIANS | GeometricFactors::DETERMINANTS);
+      D.dbls("J", geom->J); D.dbls("detJ", geom->detJ);
+   }
+   D.ints("elem_attributes", P.mesh.GetElementAttributes());
+   D.ints("marker_diffusion", m_diff); D.ints("marker_mass", m_mass);
+   D.dbls("pa_data_diffusion", bd->pa_data);
+   D.dbls("pa_data_mass", bm->pa_data);
+   D.dbls("pa_data_mass_half", bh->pa_data);
+   Vector x(ndofs); x.Randomize(1);
+   D.dbls("x", x);
+   Vector y(ndofs);
+   a.Mult(x, y);
+   D.dbls("y", y);
+   Vector diag(ndofs);
+   a.AssembleDiagonal(diag);
+   D.dbls("diag", diag);
+   Array<int> ess_bdr(P.mesh.bdr_attributes.Max()); ess_bdr = 1;
+   Array<int> ess;
+   fes.GetEssentialTrueDofs(ess_bdr, ess);
+   D.ints("ess_tdof_list", ess);
+   LinearForm b(&fes);
+   b.AddDomainIntegrator(new DomainLFIntegrator(P.one));
+   b.Assemble();
+   D.dbls("b", b);
+   GridFunction u(&fes); u = 0.0;
+   OperatorPtr Aop; Vector B, X;
+   a.FormLinearSystem(ess, u, b, Aop, X, B);
+   D.dbls("B_rhs", B);
+   Vector cy(ndofs);
+   Aop->Mult(x, cy);
+   D.dbls("y_constrained", cy);
+   // (with the plain integrator first the reference's marked diagonal has zero entries -- the
+   // later integrators reset what was accumulated on their unmarked elements -- and
+   // OperatorJacobiSmoother aborts; that case is solved without a preconditioner)
+   const int use_prec = A.geti("jacobi", 1);
+   std::unique_ptr<OperatorJacobiSmoother> M;
+   if (use_prec) { M.reset(new OperatorJacobiSmoother(a, ess)); }
+   const double rtol = A.getd("rtol", 1e-8);
+   CGSolver cg;
+   cg.SetRelTol(rtol); cg.SetAbsTol(0.0); cg.SetMaxIter(A.geti("maxit", 2000));
+   cg.SetOperator(*Aop);
+   if (use_prec) { cg.SetPreconditioner(*M); }
+   cg.SetPrintLevel(-1);
+   X = 0.0;
+   cg.Mult(B, X);
+   D.scalar("pcg_iters", cg.GetNumIterations());
+   D.scalar("pcg_converged", (int)cg.GetConverged());
+   D.scalar("pcg_rtol", rtol);
+   D.scalar("pcg_jacobi", use_prec);
+   D.dbls("X_sol", X);
+   std::printf("dump %s: markers dim=%d NE=%d p=%d nattr=%d |y|=%.17g pcg_iters=%d\n", out, dim, NE, P.p, nattr,
+               y.Norml2(), cg.GetNumIterations());
+   return 0;
+}
+
 // OperatorChebyshevSmoother (linalg/solvers.cpp:453-658) on the constrained PA operator:
 // coefficients and action for every order, the power-method eigenvalue estimate, and CG
 // preconditioned with it.
@@ -700,6 +895,8 @@ int main(int argc, char **argv)
       Args A(argc, argv, 3);
       if (A.geti("nonsym", 0)) { return do_dump_nonsym(A, argv[2]); }
       if (A.geti("cheb", 0)) { return do_dump_cheb(A, argv[2]); }
+      if (A.geti("markers", 0)) { return do_dump_markers(A, argv[2]); }
+      if (A.geti("lf", 0)) { return do_dump_lf(A, argv[2]); }
       return A.geti("vdim", 1) > 1 ? do_dump_vector(A, argv[2]) : do_dump(A, argv[2]);
    }
    if (cmd == "bench") { Args A(argc, argv, 2); return do_bench(A); }

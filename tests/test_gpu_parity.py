@@ -9,7 +9,8 @@ PCG within +-1 iteration.
 import numpy as np
 import pytest
 
-from conftest import chebyshev_golden_names, golden_names, load_golden, nonsym_golden_names, relerr
+from conftest import (chebyshev_golden_names, golden_names, lf_golden_names, load_golden, marker_golden_names,
+                      nonsym_golden_names, relerr)
 
 pytestmark = pytest.mark.gpu
 
@@ -145,6 +146,8 @@ def test_element_apply_and_diagonal(dev, golden):
     assert relerr(host(ye), golden["yE"]) < TOL
     it.AddMultPA(xe, ye)  # accumulates (bilininteg.hpp:78)
     assert relerr(host(ye), 2 * golden["yE"]) < TOL
+    it.AddMultTransposePA(xe, ye)  # symmetric operators: the same kernel (bilininteg.hpp:88)
+    assert relerr(host(ye), 3 * golden["yE"]) < TOL
     de = dev.zeros(xe.numel())
     it.AssembleDiagonalPA(de)
     assert relerr(host(de), golden["diagE"]) < TOL
@@ -512,6 +515,8 @@ def test_nonsymmetric_matrix_coefficient(dev, name):
     de = dev.zeros(xe.numel())
     it.AssembleDiagonalPA(de)
     assert relerr(host(de), g["diagE"]) < TOL
+    with pytest.raises(RuntimeError, match="only implemented in the symmetric case"):
+        it.AddMultTransposePA(xe, ye)     # bilininteg_diffusion_pa.cpp:95-106
     R = m.ElementRestriction.from_tables(dev, NE, D1D ** dim, nd, g["gather_map"], g["offsets"], g["indices"])
 
     class _Fes:
@@ -579,3 +584,112 @@ def test_chebyshev_smoother_power_method_and_pcg(dev, name):
     cg.Mult(B, X2)
     assert relerr(host(X2), host(X)) < 1e-9
     S.close(); a.close(); it.close(); R.close()
+
+
+@pytest.mark.parametrize("name", marker_golden_names())
+def test_attribute_restricted_integrators(dev, name):
+    """BilinearForm::AddDomainIntegrator(bfi, elem_marker) (fem/bilinearform_ext.cpp:370-454,
+    753-847): fused (compacted elements), unfused (masked add), diagonal, constrained solve."""
+    import mfem_b200 as m
+    g = load_golden(name)
+    dim, D1D, Q1D, NE, nd = (int(g[k][0]) for k in ("dim", "D1D", "Q1D", "NE", "ndofs"))
+
+    def integ(cls, coeff, J=None, detJ=None):
+        it = cls(coeff)
+        it.assemble_from_factors(dev, dim, D1D, Q1D, NE, g["B"], g["G"], g["W"], J=J, detJ=detJ)
+        return it
+    itd = integ(m.DiffusionIntegrator, 1.0, J=g["J"])
+    itm = integ(m.MassIntegrator, 1.0, detJ=g["detJ"])
+    ith = integ(m.MassIntegrator, 0.5, detJ=g["detJ"])
+    assert np.array_equal(itd.pa_data(), g["pa_data_diffusion"])
+    assert np.array_equal(ith.pa_data(), g["pa_data_mass_half"])
+    R = m.ElementRestriction.from_tables(dev, NE, D1D ** dim, nd, g["gather_map"], g["offsets"], g["indices"])
+
+    class _Fes:
+        pass
+    fes = _Fes()
+    fes.ne, fes.dof, fes.ndofs = NE, D1D ** dim, nd
+    fes.GetElementRestriction = lambda d: R
+    a = m.BilinearForm(dev, fes)
+    a.SetElementAttributes(g["elem_attributes"])
+    if int(g["marker_order"][0]) == 1:
+        a.AddDomainIntegrator(ith)
+    a.AddDomainIntegrator(itd, g["marker_diffusion"])
+    a.AddDomainIntegrator(itm, g["marker_mass"])
+    if int(g["marker_order"][0]) == 0:
+        a.AddDomainIntegrator(ith)
+    a.Assemble()
+    x = dev.to_device(g["x"])
+    y, y2, d = dev.empty(nd), dev.empty(nd), dev.empty(nd)
+    a.Mult(x, y)
+    assert relerr(host(y), g["y"]) < TOL
+    a.MultUnfused(x, y2)
+    assert relerr(host(y2), g["y"]) < TOL
+    a.AssembleDiagonal(d)
+    assert relerr(host(d), g["diag"]) < TOL
+    assert np.array_equal(host(d) == 0.0, g["diag"] == 0.0)
+    ess = g["ess_tdof_list"]
+    u, b = dev.zeros(nd), dev.to_device(g["b"])
+    A, X, B = a.FormLinearSystem(ess, u, b)
+    assert relerr(host(B), g["B_rhs"]) < TOL
+    A.Mult(x, y)
+    assert relerr(host(y), g["y_constrained"]) < TOL
+    cg = m.CGSolver()
+    # 25 fixed iterations (the reference's marked diagonal makes a poor preconditioner -- see
+    # test_oracle_markers.py -- so a converged count would sit in the round-off regime)
+    cg.SetRelTol(float(g["pcg_rtol"][0])); cg.SetAbsTol(0.0); cg.SetMaxIter(25)
+    cg.SetOperator(A)
+    if int(g["pcg_jacobi"][0]):
+        cg.SetPreconditioner(m.OperatorJacobiSmoother(a, ess))
+    X = dev.zeros(nd)
+    cg.Mult(B, X)
+    assert cg.GetNumIterations() == int(g["pcg_iters"][0]) == 25
+    assert cg.GetConverged() == bool(g["pcg_converged"][0])
+    assert relerr(host(X), g["X_sol"]) < 1e-9
+    # removing the restriction gives the plain sum of the three operators
+    import ctypes as C
+    from mfem_b200.capi import call
+    for i in range(3):
+        call("b2f_operator_set_markers", a.op, i, None, None, 0)
+    a.Mult(x, y)
+    plain = m.BilinearForm(dev, fes)
+    for it in (itd, itm, ith):
+        plain.AddDomainIntegrator(it)
+    plain.Assemble()
+    plain.Mult(x, y2)
+    assert relerr(host(y), host(y2)) < TOL
+    plain.close(); a.close(); itd.close(); itm.close(); ith.close(); R.close()
+
+
+@pytest.mark.parametrize("name", lf_golden_names())
+def test_domain_linear_form_device_assembly(dev, name):
+    """DomainLFIntegrator / VectorDomainLFIntegrator::AssembleDevice + LinearFormExtension::Assemble
+    (fem/integ/lininteg_domain_kernels.hpp:76-297, fem/linearform_ext.cpp:20-66)."""
+    import mfem_b200 as m
+    g = load_golden(name)
+    dim, D1D, Q1D, NE, nd, vdim = (int(g[k][0]) for k in ("dim", "D1D", "Q1D", "NE", "ndofs", "vdim"))
+    detJ, coeff = dev.to_device(g["detJ"]), dev.to_device(g["coeff"])
+    n_e = NE * vdim * D1D ** dim
+    be = dev.zeros(n_e)
+    m.domain_lf_assemble(dev, dim, D1D, Q1D, vdim, NE, g["B"], g["W"], detJ, coeff, be)
+    assert relerr(host(be), g["b_e"]) < TOL
+    m.domain_lf_assemble(dev, dim, D1D, Q1D, vdim, NE, g["B"], g["W"], detJ, coeff, be)   # accumulates
+    assert relerr(host(be), 2 * g["b_e"]) < TOL
+    bm = dev.zeros(n_e)
+    import torch
+    mk = torch.from_numpy(np.ascontiguousarray(g["markers"], dtype=np.int32)).to(dev.tdev)
+    m.domain_lf_assemble(dev, dim, D1D, Q1D, vdim, NE, g["B"], g["W"], detJ, coeff, bm, markers_d=mk)
+    assert relerr(host(bm), g["b_e_marked"]) < TOL
+    bc = dev.zeros(n_e)
+    cst = dev.to_device(1.5 + np.arange(vdim) if vdim > 1 else np.array([3.0]))
+    m.domain_lf_assemble(dev, dim, D1D, Q1D, vdim, NE, g["B"], g["W"], detJ, cst, bc)
+    assert relerr(host(bc), g["b_e_const"]) < TOL
+    # lf = R^T b_e (linearform_ext.cpp:64)
+    R = m.ElementRestriction.from_tables(dev, NE, D1D ** dim, nd, g["gather_map"], g["offsets"], g["indices"],
+                                         vdim=vdim, byvdim=bool(int(g["byvdim"][0])))
+    be.zero_()
+    m.domain_lf_assemble(dev, dim, D1D, Q1D, vdim, NE, g["B"], g["W"], detJ, coeff, be)
+    b = dev.empty(nd * vdim)
+    R.MultTranspose(be, b)
+    assert relerr(host(b), g["b_fast"]) < TOL
+    R.close()

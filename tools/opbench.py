@@ -33,6 +33,8 @@ ap.add_argument("--vdim", type=int, default=1, help="3: vector problem (BP2/4/6)
 ap.add_argument("--sweep", default="", help="comma list of BPs: sweep p=1..8")
 ap.add_argument("--dofs", type=float, default=20e6)
 ap.add_argument("--maxn", type=int, default=100)
+ap.add_argument("--numbering", default="h1", help="h1 | dg: probe with a private, contiguous dof range per "
+                "element (perfectly coalesced gather/scatter, no sharing) -- an upper bound for index layouts")
 a = ap.parse_args()
 
 dev = m.Device("cuda")
@@ -55,6 +57,12 @@ def run_case(bp, p, n, variants, reps):
         R.close()
         Rv = m.ElementRestriction.from_tables(dev, fes.ne, fes.dof, fes.ndofs, gm, off, ind, vdim=vd, byvdim=True)
         fes.GetElementRestriction = lambda d: Rv
+    if a.numbering == "dg":
+        ntot = fes.ne * fes.dof
+        gm = np.arange(ntot, dtype=np.int32)
+        Rd = m.ElementRestriction.from_tables(dev, fes.ne, fes.dof, ntot, gm, np.arange(ntot + 1, dtype=np.int32), gm)
+        fes.GetElementRestriction = lambda d: Rd
+        fes.ndofs = ntot
     form = m.BilinearForm(dev, fes)
     form.AddDomainIntegrator(it)
     form.Assemble()
