@@ -486,39 +486,6 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
    const int64_t e0 = e_first + (int64_t)blockIdx.x * NEB; // elements [e_first, ne) of this launch
    const int nev = (int)((ne - e0) < NEB ? (ne - e0) : NEB);
 
-   // quadrature-data stream: TMA per element + L2 prefetch for the CTA `pf` blocks on
-   const double *qslab = qdata + e0 * (int64_t)(C::NQD * Q3);
-   if constexpr (C::TMA_OK)
-   {
-      if (t == 0)
-      {
-         mbar_init(bar, 1);
-         mbar_expect_tx(bar, (uint32_t)(nev * C::NQD * Q3) * 8u);
-         for (int e = 0; e < nev; e++)
-         {
-            bulk_g2s(qd + e * C::DS, qslab + (int64_t)e * (C::NQD * Q3), (uint32_t)(C::NQD * Q3) * 8u, bar);
-         }
-      }
-   }
-   else
-   {
-      for (int i = t; i < nev * C::NQD * Q3; i += C::NT) { cp_async8(qd + i, qslab + i); }
-   }
-   if (pf > 0 && t == 32 % C::NT)
-   {
-      const int64_t ep = e0 + (int64_t)pf * NEB;
-      if (ep + NEB <= ne)
-      {
-         const uintptr_t q = reinterpret_cast<uintptr_t>(qdata + ep * (int64_t)(C::NQD * Q3)) & ~(uintptr_t)15;
-         l2_prefetch_bulk(reinterpret_cast<const void *>(q), ((uint32_t)(NEB * C::NQD * Q3) * 8u) & ~15u);
-         if (FUSED)
-         {
-            const uintptr_t a = reinterpret_cast<uintptr_t>(idx + ep * D3) & ~(uintptr_t)15;
-            l2_prefetch_bulk(reinterpret_cast<const void *>(a), ((uint32_t)(NEB * D3) * 4u) & ~15u);
-         }
-      }
-   }
-
    int e1, dx1, dz1;
    eo_line_coords<D, NEB, C::L.order>(t, e1, dx1, dz1);
    const bool has1 = t < C::T1;
@@ -534,13 +501,56 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
          double u[D];
 #pragma unroll
          for (int dy = 0; dy < D; dy++) { gi[dy] = -1; u[dy] = 0.0; }
-         if (act1)
+         if constexpr (FUSED)
          {
-            if constexpr (FUSED)
+            // the gather indices head the longest dependent chain (index -> x -> stage 1): their
+            // loads are issued before anything else, the copy set-up below runs in their shadow
+            if (act1)
             {
                const int *ip = idx + (VEC ? c * va.ics : 0) + (e0 + e1) * D3 + loc1;
 #pragma unroll
                for (int dy = 0; dy < D; dy++) { gi[dy] = __ldg(ip + D * dy); }
+            }
+         }
+         if (c == 0)
+         {
+         // quadrature-data stream: TMA per element + L2 prefetch for the CTA `pf` blocks on
+         const double *qslab = qdata + e0 * (int64_t)(C::NQD * Q3);
+         if constexpr (C::TMA_OK)
+         {
+            if (t == 0)
+            {
+               mbar_init(bar, 1);
+               mbar_expect_tx(bar, (uint32_t)(nev * C::NQD * Q3) * 8u);
+               for (int e = 0; e < nev; e++)
+               {
+                  bulk_g2s(qd + e * C::DS, qslab + (int64_t)e * (C::NQD * Q3), (uint32_t)(C::NQD * Q3) * 8u, bar);
+               }
+            }
+         }
+         else
+         {
+            for (int i = t; i < nev * C::NQD * Q3; i += C::NT) { cp_async8(qd + i, qslab + i); }
+         }
+         if (pf > 0 && t == 32 % C::NT)
+         {
+            const int64_t ep = e0 + (int64_t)pf * NEB;
+            if (ep + NEB <= ne)
+            {
+               const uintptr_t q = reinterpret_cast<uintptr_t>(qdata + ep * (int64_t)(C::NQD * Q3)) & ~(uintptr_t)15;
+               l2_prefetch_bulk(reinterpret_cast<const void *>(q), ((uint32_t)(NEB * C::NQD * Q3) * 8u) & ~15u);
+               if (FUSED)
+               {
+                  const uintptr_t a = reinterpret_cast<uintptr_t>(idx + ep * D3) & ~(uintptr_t)15;
+                  l2_prefetch_bulk(reinterpret_cast<const void *>(a), ((uint32_t)(NEB * D3) * 4u) & ~15u);
+               }
+            }
+         }
+         }
+         if (act1)
+         {
+            if constexpr (FUSED)
+            {
 #pragma unroll
                for (int dy = 0; dy < D; dy++)
                {
