@@ -328,6 +328,47 @@ public:
    }
 };
 
+/// DomainLFIntegrator whose device assembly (LinearForm::UseFastAssembly(true),
+/// fem/linearform_ext.cpp:20-66 -> fem/integ/lininteg_domain.cpp:21-59) runs on the B200:
+/// the E-vector b_e += B^T (W f detJ) comes from b2f_domain_lf_assemble; MFEM's
+/// LinearFormExtension keeps doing the R^T scatter.
+class DomainLFIntegrator : public mfem::DomainLFIntegrator
+{
+   mfem::Coefficient &Qf;
+   int qa, qb;
+   const mfem::IntegrationRule *ir_given;
+public:
+   DomainLFIntegrator(mfem::Coefficient &QF, int a = 2, int b = 0)
+      : mfem::DomainLFIntegrator(QF, a, b), Qf(QF), qa(a), qb(b), ir_given(nullptr) { }
+   DomainLFIntegrator(mfem::Coefficient &QF, const mfem::IntegrationRule *ir)
+      : mfem::DomainLFIntegrator(QF, ir), Qf(QF), qa(2), qb(0), ir_given(ir) { }
+   void AssembleDevice(const mfem::FiniteElementSpace &fes, const mfem::Array<int> &markers,
+                       mfem::Vector &b) override
+   {
+      using namespace mfem;
+      const FiniteElement &fe = *fes.GetTypicalFE();
+      const IntegrationRule *ir = ir_given ? ir_given : &IntRules.Get(fe.GetGeomType(), qa * fe.GetOrder() + qb);
+      const DofToQuad &maps = fe.GetDofToQuad(*ir, DofToQuad::TENSOR);
+      Mesh *mesh = fes.GetMesh();
+      const GeometricFactors *geom = mesh->GetGeometricFactors(*ir, GeometricFactors::DETERMINANTS);
+      QuadratureSpace qs(*mesh, *ir);
+      CoefficientVector coeff(Qf, qs, CoefficientStorage::COMPRESSED);
+      b2f_ctx *ctx = Context::Get().get();
+      DeviceVector d_detj, d_coeff, d_b;
+      d_detj.Upload(geom->detJ);
+      d_coeff.Upload(coeff);
+      d_b.Upload(b);
+      int *d_mk = nullptr;
+      B200_CHECK(b2f_malloc(ctx, sizeof(int) * (markers.Size() + 1), (void **)&d_mk));
+      B200_CHECK(b2f_memcpy_h2d(ctx, d_mk, markers.HostRead(), sizeof(int) * markers.Size()));
+      B200_CHECK(b2f_domain_lf_assemble(ctx, mesh->Dimension(), maps.ndof, maps.nqpt, fes.GetVDim(), fes.GetNE(),
+                                        d_mk, maps.B.HostRead(), ir->GetWeights().HostRead(), d_detj.Ptr(),
+                                        d_coeff.Ptr(), coeff.Size(), d_b.Ptr()));
+      d_b.Download(b);
+      b2f_free(ctx, d_mk);
+   }
+};
+
 /// OperatorChebyshevSmoother (linalg/solvers.hpp:392-505, solvers.cpp:453-658) over the
 /// constrained fused operator; both reference constructors (given eigenvalue estimate /
 /// power method with MFEM's own Vector::Randomize(power_seed) start vector).

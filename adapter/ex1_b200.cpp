@@ -138,6 +138,20 @@ int main(int argc, char *argv[])
    check("PCG iteration count |difference|", std::abs(cg.GetNumIterations() - cg2.GetNumIterations()), 1.0);
    check("PCG solution", relerr(X2, X), 1e-5);
 
+   // right-hand side with a spatially varying coefficient, fast (device) assembly
+   if (vdim == 1)
+   {
+      FunctionCoefficient f([](const Vector &xx) { return 1.0 + xx(0) + 2.0 * xx(1) * xx(1) + (xx.Size() > 2 ? sin(3.0 * xx(2)) : 0.0); });
+      LinearForm l_ref(&fes), l_b2(&fes);
+      l_ref.AddDomainIntegrator(new DomainLFIntegrator(f));
+      l_ref.UseFastAssembly(true);
+      l_ref.Assemble();
+      l_b2.AddDomainIntegrator(new b200::DomainLFIntegrator(f));
+      l_b2.UseFastAssembly(true);
+      l_b2.Assemble();
+      check("LinearForm fast assembly with b200::DomainLFIntegrator", relerr(l_b2, l_ref), 1e-12);
+   }
+
    // Chebyshev smoother (power-method constructor, MFEM's own start vector) as preconditioner
    {
       Vector dg(N);

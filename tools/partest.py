@@ -122,6 +122,29 @@ def check(mode):
     assert conv_p and conv_s and abs(it_p - it_s) <= 1, (it_p, it_s)
     e4 = rel(X_p, X_s[t2s])
     assert e4 < 1e-6, f"PCG solution {e4}"
+    # Chebyshev smoother: power method (all-reduced dots), action, and CG preconditioned with it
+    start = np.random.default_rng(3).random(nlat)
+    Ss = m.OperatorChebyshevSmoother(As, dgs, 3, None, 10, 1e-8, start=start)
+    Sp = m.OperatorChebyshevSmoother(A, dg, 3, None, 10, 1e-8, start=start[t2s.cpu().numpy()])
+    assert abs(Sp.max_eig_estimate - Ss.max_eig_estimate) < 1e-10 * Ss.max_eig_estimate, \
+        (Sp.max_eig_estimate, Ss.max_eig_estimate)
+    z_t, zs = dev.empty(fes.ntdofs), dev.empty(nlat)
+    Sp.Mult(x_t, z_t)
+    Ss.Mult(xs, zs)
+    dev.sync()
+    e5 = rel(z_t, zs[t2s])
+    assert e5 < 1e-10, f"Chebyshev action {e5}"
+    res = []
+    for (AA, MM, BB, n) in ((A, Sp, B, fes.ntdofs), (As, Ss, Bs, nlat)):
+        cg = m.CGSolver()
+        cg.SetRelTol(1e-8); cg.SetMaxIter(1000); cg.SetOperator(AA); cg.SetPreconditioner(MM)
+        X = dev.zeros(n)
+        cg.Mult(BB, X)
+        res.append((cg.GetNumIterations(), cg.GetConverged(), X))
+    (ic_p, cc_p, Xc_p), (ic_s, cc_s, Xc_s) = res
+    assert cc_p and cc_s and abs(ic_p - ic_s) <= 1, (ic_p, ic_s)
+    assert rel(Xc_p, Xc_s[t2s]) < 1e-6
+    Sp.close(); Ss.close()
     return e1, e2, e3, it_p, it_s, e4
 
 
