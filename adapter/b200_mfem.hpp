@@ -125,6 +125,42 @@ public:
                                          ir.GetWeights().HostRead(), nmaps.ndof, nmaps.B.HostRead(),
                                          nmaps.G.HostRead(), d_nodes.Ptr(), coeff, &pa));
    }
+   /** AssemblePA with a general coefficient, exactly the reference seam
+       (bilininteg_diffusion_pa.cpp:108-171, bilininteg_mass_pa.cpp:25-91): the
+       CoefficientVector MFEM projects at the quadrature points (scalar, vector, symmetric or
+       full matrix) and GeometricFactors J / detJ go to b2f_diffusion_setup / b2f_mass_setup. */
+   void AssembleGeneral(int kind, const mfem::FiniteElementSpace &fes, const mfem::IntegrationRule &ir,
+                        const mfem::CoefficientVector &coeff)
+   {
+      using namespace mfem;
+      Mesh &mesh = *fes.GetMesh();
+      const FiniteElement &fe = *fes.GetTypicalFE();
+      const DofToQuad &maps = fe.GetDofToQuad(ir, DofToQuad::TENSOR);
+      ne = fes.GetNE();
+      dof = fe.GetDof();
+      vdim = fes.GetVDim();
+      b2f_pa_destroy(pa);
+      pa = nullptr;
+      DeviceVector d_geo, d_c;
+      d_c.Upload(coeff);
+      b2f_ctx *ctx = Context::Get().get();
+      if (kind == 0)
+      {
+         const GeometricFactors *geom = mesh.GetGeometricFactors(ir, GeometricFactors::JACOBIANS);
+         d_geo.Upload(geom->J);
+         B200_CHECK(b2f_diffusion_setup(ctx, mesh.Dimension(), maps.ndof, maps.nqpt, ne, maps.B.HostRead(),
+                                        maps.G.HostRead(), ir.GetWeights().HostRead(), d_geo.Ptr(), d_c.Ptr(),
+                                        coeff.GetVDim(), coeff.Size(), &pa));
+      }
+      else
+      {
+         const GeometricFactors *geom = mesh.GetGeometricFactors(ir, GeometricFactors::DETERMINANTS);
+         d_geo.Upload(geom->detJ);
+         B200_CHECK(b2f_mass_setup(ctx, mesh.Dimension(), maps.ndof, maps.nqpt, ne, maps.B.HostRead(),
+                                   ir.GetWeights().HostRead(), d_geo.Ptr(), d_c.Ptr(), coeff.Size(), &pa));
+      }
+      B200_CHECK(b2f_ctx_sync(ctx));
+   }
    void AddMult(const mfem::Vector &x, mfem::Vector &y) const
    {
       xe.Upload(x);
@@ -157,9 +193,10 @@ inline double ConstantOf(mfem::Coefficient *Q)
 {
    if (!Q) { return 1.0; }
    auto c = dynamic_cast<mfem::ConstantCoefficient *>(Q);
-   MFEM_VERIFY(c, "b200 integrators take a ConstantCoefficient (or none)");
+   MFEM_VERIFY(c, "b200 vector integrators take a ConstantCoefficient (or none)");
    return c->constant;
 }
+inline bool IsConstant(mfem::Coefficient *Q) { return !Q || dynamic_cast<mfem::ConstantCoefficient *>(Q); }
 
 /// seam 3: drop-in for mfem::DiffusionIntegrator on the PA path.
 class DiffusionIntegrator : public mfem::DiffusionIntegrator
@@ -173,7 +210,15 @@ public:
       const mfem::FiniteElement &fe = *fes.GetTypicalFE();
       const mfem::IntegrationRule *ir = GetIntegrationRule();
       if (!ir) { ir = &GetRule(fe, fe); }
-      data.Assemble(0, fes, *ir, ConstantOf(Q));
+      if (!VQ && !MQ && IsConstant(Q)) { data.Assemble(0, fes, *ir, ConstantOf(Q)); return; }
+      // spatially varying scalar, vector (diagonal) or matrix coefficient: the reference's own
+      // projection at the quadrature points (bilininteg_diffusion_pa.cpp:155-163)
+      mfem::QuadratureSpace qs(*fes.GetMesh(), *ir);
+      mfem::CoefficientVector coeff(qs, mfem::CoefficientStorage::COMPRESSED);
+      if (MQ) { coeff.ProjectTranspose(*MQ); }
+      else if (VQ) { coeff.Project(*VQ); }
+      else { coeff.Project(*Q); }
+      data.AssembleGeneral(0, fes, *ir, coeff);
    }
    void AddMultPA(const mfem::Vector &x, mfem::Vector &y) const override { data.AddMult(x, y); }
    void AssembleDiagonalPA(mfem::Vector &diag) override { data.AddDiagonal(diag); }
@@ -192,7 +237,10 @@ public:
       const mfem::FiniteElement &fe = *fes.GetTypicalFE();
       const mfem::IntegrationRule *ir = GetIntegrationRule();
       if (!ir) { ir = &GetRule(fe, fe, *fes.GetMesh()->GetTypicalElementTransformation()); }
-      data.Assemble(1, fes, *ir, ConstantOf(Q));
+      if (IsConstant(Q)) { data.Assemble(1, fes, *ir, ConstantOf(Q)); return; }
+      mfem::QuadratureSpace qs(*fes.GetMesh(), *ir);
+      mfem::CoefficientVector coeff(Q, qs, mfem::CoefficientStorage::COMPRESSED); // bilininteg_mass_pa.cpp:46
+      data.AssembleGeneral(1, fes, *ir, coeff);
    }
    void AddMultPA(const mfem::Vector &x, mfem::Vector &y) const override { data.AddMult(x, y); }
    void AssembleDiagonalPA(mfem::Vector &diag) override { data.AddDiagonal(diag); }

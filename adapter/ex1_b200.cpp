@@ -138,6 +138,46 @@ int main(int argc, char *argv[])
    check("PCG iteration count |difference|", std::abs(cg.GetNumIterations() - cg2.GetNumIterations()), 1.0);
    check("PCG solution", relerr(X2, X), 1e-5);
 
+   // spatially varying scalar and full-matrix coefficients through the reference's own
+   // CoefficientVector projection (seam 3 + the fused operator)
+   if (vdim == 1 && dim == 3)
+   {
+      FunctionCoefficient kf([](const Vector &xx) { return 1.0 + 0.5 * xx(0) * xx(1) + xx(2) * xx(2); });
+      MatrixFunctionCoefficient mf(3, [](const Vector &xx, DenseMatrix &K)
+      {
+         K.SetSize(3);
+         K = 0.0;
+         for (int i = 0; i < 3; i++) { K(i, i) = 2.0 + xx(i); }
+         K(0, 1) = 0.3 * xx(2); K(1, 0) = -0.1; K(1, 2) = 0.2 * xx(0); K(2, 0) = 0.15;
+      });
+      for (int variant = 0; variant < 3; variant++)
+      {
+         BilinearForm ar(&fes), ab(&fes);
+         ar.SetAssemblyLevel(AssemblyLevel::PARTIAL);
+         ab.SetAssemblyLevel(AssemblyLevel::PARTIAL);
+         if (variant == 0) { ar.AddDomainIntegrator(new DiffusionIntegrator(kf)); ab.AddDomainIntegrator(new b200::DiffusionIntegrator(kf)); }
+         if (variant == 1) { ar.AddDomainIntegrator(new DiffusionIntegrator(mf)); ab.AddDomainIntegrator(new b200::DiffusionIntegrator(mf)); }
+         if (variant == 2) { ar.AddDomainIntegrator(new MassIntegrator(kf)); ab.AddDomainIntegrator(new b200::MassIntegrator(kf)); }
+         ar.Assemble();
+         ab.Assemble();
+         const char *nm[3] = {"function-coefficient diffusion", "full-matrix-coefficient diffusion",
+                              "function-coefficient mass"};
+         char msg[128];
+         ar.Mult(x, y_ref);
+         ab.Mult(x, y);
+         std::snprintf(msg, sizeof msg, "seam 3: %s, Mult", nm[variant]);
+         check(msg, relerr(y, y_ref), 1e-12);
+         b200::PAOperator Af(ab, none);
+         Af.Mult(x, y);
+         std::snprintf(msg, sizeof msg, "seam 1: %s, fused Mult", nm[variant]);
+         check(msg, relerr(y, y_ref), 1e-12);
+         ar.AssembleDiagonal(d_ref);
+         Af.AssembleDiagonal(d);
+         std::snprintf(msg, sizeof msg, "seam 1: %s, diagonal", nm[variant]);
+         check(msg, relerr(d, d_ref), 1e-12);
+      }
+   }
+
    // right-hand side with a spatially varying coefficient, fast (device) assembly
    if (vdim == 1)
    {
