@@ -67,13 +67,11 @@ def workload(a):
              3: 133 if (p == 4 and vdim == 1) else round((150e6 / vdim) ** (1 / 3) / p),
              5: round((99e6 / vdim) ** (1 / 3) / p)}[sbp]
     else:
-        n = round((100e6) ** (1 / 3) / p)
+        n = round((100e6 / vdim) ** (1 / 3) / p)
     grid = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[a.gpus]
     kind = {1: "mass", 3: "diffusion", 5: "diffusion"}[sbp]
     q = p + 1 if sbp == 5 else p + 2
     curved = bool(a.curved) if a.curved is not None else sbp == 5
-    if vdim > 1 and a.gpus > 1:
-        raise SystemExit("the vector BPs are single-GPU for now")
     return dict(bp=a.bp, p=p, n=n, grid=grid, kind=kind, q1d=q, d1d=p + 1, gll=(sbp == 5), curved=curved,
                 vdim=vdim)
 
@@ -258,14 +256,14 @@ def main():
     if world > 1:
         ids = [m.Halo.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
-        halo = m.Halo(dev, rank, world, fes.ndofs, fes.halo_tables, ids[0])
+        halo = m.Halo(dev, rank, world, fes.ndofs, fes.halo_tables, ids[0], vdim=w["vdim"])
         if os.environ.get("B2F_HALO", "p2p") != "nccl":
             halo.connect_p2p(dist)  # shared dofs: peer-memory stores over NVLink, no NCCL send/recv
         form.SetHalo(halo)
     ess = fes.GetEssentialTrueDofs()
     b_l = m.LinearForm(dev, fes).Assemble()
     if halo:
-        b = dev.empty(fes.ntdofs)
+        b = dev.empty(fes.GetTrueVSize())
         halo.MultTranspose(b_l, b)
     else:
         b = b_l

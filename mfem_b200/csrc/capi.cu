@@ -908,7 +908,7 @@ static int rap_mult(b2f_operator *op, const double *x, double *y, bool constrain
 {
    if (!op->halo) { return local_mult(op, x, y, constrained_mask, dot_acc); }
    b2f_ctx *ctx = op->ctx;
-   const int nl = op->r->ndofs;
+   const int nl = op->r->ndofs * op->r->vdim; // local (v)dofs; the halo tables are per vdof
    if (halo_is_prefix(op->halo))
    {
       int nl2 = 0, nt = 0;
@@ -1084,15 +1084,21 @@ int b2f_operator_assemble_diagonal(b2f_operator *op, double *diag)
    {
       // vector integrators: the scalar diagonal for every component
       // (bilininteg_vecdiffusion_pa.cpp / bilininteg_vecmass_pa.cpp AssembleDiagonalPA)
-      B2F_REQUIRE(!op->halo, "b2f_operator_assemble_diagonal: vector spaces are single-rank for now");
       B2F_TRY(ensure(&op->z, (int64_t)r->ndofs * r->vdim)); // (z is also the vdof-sized scratch elsewhere)
       b2f_restriction scalar = *r;
       scalar.vdim = 1; scalar.byvdim = 0;
       B2F_TRY(restriction_scatter(&scalar, op->ye, op->z, 2));
+      double *dl = diag;
+      if (op->halo)
+      {
+         // ParBilinearForm::AssembleDiagonal (fem/pbilinearform.cpp:293): P^T of the local diagonal
+         B2F_TRY(ensure(&op->yl, (int64_t)r->ndofs * r->vdim));
+         dl = op->yl;
+      }
       replicate_components_kernel<<<(unsigned)cdiv(r->ndofs, 256), 256, 0, ctx->stream>>>(
-         r->ndofs, r->vdim, r->byvdim ? r->vdim : 1, r->byvdim ? 1 : r->ndofs, op->z, diag);
+         r->ndofs, r->vdim, r->byvdim ? r->vdim : 1, r->byvdim ? 1 : r->ndofs, op->z, dl);
       B2F_LAUNCH_CHECK(ctx);
-      return B2F_OK;
+      return op->halo ? halo_mult_transpose(op->halo, op->yl, diag) : B2F_OK;
    }
    if (!op->halo) { return restriction_scatter(r, op->ye, diag, 2); } // AbsMultTranspose :426
    // ParBilinearForm::AssembleDiagonal (fem/pbilinearform.cpp:293): P^T of the local diagonal
@@ -1124,9 +1130,13 @@ int b2f_operator_set_halo(b2f_operator *op, b2f_halo *halo)
    {
       int nl = 0, nt = 0;
       halo_sizes(halo, &nl, &nt);
-      B2F_REQUIRE(op->r->vdim == 1, "b2f_operator_set_halo: vector spaces are single-rank for now");
-      B2F_REQUIRE(nl == op->r->ndofs, "b2f_operator_set_halo: halo has %d ldofs, the space %d", nl,
-                  op->r->ndofs);
+      // vector spaces: the halo is built on vdofs (every table entry expanded per component by
+      // the caller, as ParFiniteElementSpace's group communicator does for vdim > 1); with
+      // Ordering::byVDIM the owned-first numbering keeps true vdofs the head of the local vector
+      B2F_REQUIRE(op->r->vdim == 1 || op->r->byvdim,
+                  "b2f_operator_set_halo: rank-parallel vector spaces need Ordering::byVDIM");
+      B2F_REQUIRE(nl == op->r->ndofs * op->r->vdim, "b2f_operator_set_halo: halo has %d ldofs, the space %d",
+                  nl, op->r->ndofs * op->r->vdim);
    }
    op->halo = halo;
    cudaFree(op->z); op->z = nullptr;
@@ -1265,7 +1275,7 @@ int b2f_power_method(b2f_operator *op, const double *dinv, double *v0, int num_s
    b2f_ctx *ctx = op->ctx;
    b2f_halo *halo = op->halo;
    const int64_t n = b2f_operator_height(op);
-   const int64_t ncap = halo ? (int64_t)op->r->ndofs : n;
+   const int64_t ncap = halo ? (int64_t)op->r->ndofs * op->r->vdim : n;
    // the iteration vector and its image live in the PCG scratch (L-vector capacity)
    for (int k = 0; k < 3; k++) { B2F_TRY(ensure(&op->pcg_vec[k], ncap)); }
    double *va = op->pcg_vec[0], *vb = op->pcg_vec[1], *q = op->pcg_vec[2];
@@ -1308,7 +1318,7 @@ int b2f_chebyshev_create(b2f_operator *op, const double *diag, int order, double
    c->order = order;
    memcpy(c->coeffs, coeffs, sizeof(coeffs));
    const int64_t n = b2f_operator_height(op);
-   const int64_t ncap = op->halo ? (int64_t)op->r->ndofs : n;
+   const int64_t ncap = op->halo ? (int64_t)op->r->ndofs * op->r->vdim : n;
    cudaError_t e1 = cudaMalloc((void **)&c->dinv, sizeof(double) * (n ? n : 1));
    cudaError_t e2 = cudaMalloc((void **)&c->res, sizeof(double) * (ncap ? ncap : 1));
    cudaError_t e3 = cudaMalloc((void **)&c->help, sizeof(double) * (ncap ? ncap : 1));
@@ -1355,7 +1365,7 @@ static int pcg_impl(b2f_operator *op, const double *dinv, b2f_chebyshev *cheb, c
    void *st = ctx->d_scalars; // PcgState lives in the context's device scalars
    // d and q (the operator's input and output) get room for a local-dof vector so that the
    // halo can run in place on them
-   const int64_t ncap = halo ? (int64_t)op->r->ndofs : n;
+   const int64_t ncap = halo ? (int64_t)op->r->ndofs * op->r->vdim : n;
    for (int k = 0; k < 4; k++) { B2F_TRY(ensure(&op->pcg_vec[k], ncap)); }
    double *r = op->pcg_vec[0], *d = op->pcg_vec[1], *z = op->pcg_vec[2], *q = op->pcg_vec[3];
    double *hist = nullptr;

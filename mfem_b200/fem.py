@@ -231,8 +231,8 @@ class FiniteElementSpace:
         bench_ceed.cpp:131 uses Ordering::byVDIM for the vector BPs."""
         self.mesh, self.fec = mesh, fec
         self.vdim, self.byvdim = int(vdim), ordering == "byVDIM"
-        if vdim > 1 and mesh.part is not None:
-            raise ValueError("vector spaces are single-rank for now")
+        if vdim > 1 and mesh.part is not None and not self.byvdim:
+            raise ValueError("rank-parallel vector spaces need Ordering::byVDIM")
         p, dim = fec.order, mesh.dim
         self.p, self.dim = p, dim
         self.d1d = p + 1
@@ -468,8 +468,29 @@ VectorMassIntegrator = MassIntegrator
 class Halo:
     """ConformingProlongationOperator (fem/pfespace.hpp:615) over NCCL."""
 
-    def __init__(self, device, rank, nranks, n_ldofs, tables, nccl_id=None):
-        t = tables
+    @staticmethod
+    def expand_vdim(tables, vdim):
+        """Scalar shared-dof tables -> the vdof tables of a vdim-component space ordered byVDIM
+        (vdof = ldof*vdim + c), which is what ParFiniteElementSpace's communicator holds for
+        vdim > 1.  Owned-first numbering is preserved: true vdofs stay the head of the vector."""
+        c = np.arange(vdim, dtype=np.int64)
+
+        def ex(a):
+            return _i32((np.asarray(a, np.int64)[:, None] * vdim + c[None, :]).ravel())
+        t = dict(tables)
+        t["ltdof_ldof"] = ex(tables["ltdof_ldof"])
+        t["shr_ltdof"] = ex(tables["shr_ltdof"])
+        t["ext_ldof"] = ex(tables["ext_ldof"])
+        t["shr_offsets"] = _i32(np.asarray(tables["shr_offsets"], np.int64) * vdim)
+        t["ext_offsets"] = _i32(np.asarray(tables["ext_offsets"], np.int64) * vdim)
+        return t
+
+    def __init__(self, device, rank, nranks, n_ldofs, tables, nccl_id=None, vdim=1):
+        """vdim > 1: n_ldofs and tables are the SCALAR ones of the space; the halo is built on
+        its vdofs (Ordering::byVDIM)."""
+        t = tables if vdim == 1 else Halo.expand_vdim(tables, vdim)
+        n_ldofs = n_ldofs * vdim
+        self.vdim = vdim
         self.dev, self.tables = device, t
         self.n_ldofs, self.n_tdofs = n_ldofs, len(t["ltdof_ldof"])
         h = vp()
@@ -589,7 +610,7 @@ class BilinearForm:
         ess = self.ess if ess_dofs is None else ess_dofs
         if self.halo is None:
             return _i32(ess)
-        l2t = np.full(self.fes.ndofs, -1, np.int64)
+        l2t = np.full(self.halo.n_ldofs, -1, np.int64)
         l2t[self.halo.tables["ltdof_ldof"]] = np.arange(self.halo.n_tdofs)
         e = l2t[np.asarray(ess, np.int64)]
         return _i32(e[e >= 0])

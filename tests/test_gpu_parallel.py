@@ -47,16 +47,18 @@ def test_single_rank_halo_is_transparent():
     form.close(); it.close(); halo.close(); dev.close()
 
 
-@pytest.mark.parametrize("world,kind,p", [(2, "diffusion", 3), (2, "mass", 2), (4, "diffusion", 2),
-                                          (8, "diffusion", 4)])
-def test_nccl_halo_matches_serial(world, kind, p):
+@pytest.mark.parametrize("world,kind,p,vdim", [(2, "diffusion", 3, 1), (2, "mass", 2, 1), (4, "diffusion", 2, 1),
+                                               (8, "diffusion", 4, 1), (2, "diffusion", 3, 3), (2, "mass", 2, 3)])
+def test_nccl_halo_matches_serial(world, kind, p, vdim):
+    """vdim = 3: vector space (CEED BP2/BP4), vdof-level halo tables, Ordering::byVDIM"""
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    port = 29500 + world * 7 + p
+    port = 29500 + world * 7 + p + 20 * vdim
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
-           os.path.join(ROOT, "tools", "partest.py"), "--order", str(p), "--elems", "5", "--integrator", kind]
+           os.path.join(ROOT, "tools", "partest.py"), "--order", str(p), "--elems", "5", "--integrator", kind,
+           "--vdim", str(vdim)]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
     out = r.stdout.decode(errors="replace")
     assert r.returncode == 0 and "PARTEST OK" in out, out[-3000:]

@@ -213,3 +213,57 @@ def test_rap_operator_and_pcg_match_serial(grid, n, p, kind):
     xs = np.empty(nlat)
     xs[slat] = X
     assert np.linalg.norm(x_par - xs) <= 1e-6 * np.linalg.norm(xs)
+
+
+@pytest.mark.parametrize("grid,n,p,vdim", [((2, 1, 1), (4, 3, 2), 2, 3), ((2, 2, 1), (4, 4, 2), 3, 2)])
+def test_vdof_halo_tables_for_vector_spaces(grid, n, p, vdim):
+    """Halo.expand_vdim: the vdof-level tables of a byVDIM vector space (what
+    ParFiniteElementSpace's communicator holds for vdim > 1).  Emulates P and P^T for all ranks
+    in one process: P reproduces a global vector field on every rank's local vdofs, true vdofs
+    stay the head of the local vector, and P^T of the local "ones" counts every global vdof's
+    sharers exactly once per owner."""
+    import mfem_b200 as m
+    world = grid[0] * grid[1] * grid[2]
+    spaces = [m.FiniteElementSpace(m.Mesh(3, n[0], n[1], n[2], True, part=grid, rank=r), m.H1_FECollection(p, 3))
+              for r in range(world)]
+    tabs = [m.Halo.expand_vdim(f.halo_tables, vdim) for f in spaces]
+    nlat = (p * n[0] + 1) * (p * n[1] + 1) * (p * n[2] + 1)
+    rng = np.random.default_rng(5)
+    field = rng.random(nlat * vdim)                     # global field, byVDIM
+
+    def vd(ids):
+        return (np.asarray(ids, np.int64)[:, None] * vdim + np.arange(vdim)[None, :]).ravel()
+    x_t = []
+    for f, t in zip(spaces, tabs):
+        nt = f.ntdofs * vdim
+        assert np.array_equal(t["ltdof_ldof"], np.arange(nt))          # owned-first prefix survives
+        x_t.append(field[vd(f.halo_tables["ldof_lattice"][f.halo_tables["ltdof_ldof"]])])
+    # P: owners' shared values travel to the sharers' ext slots (neighbour-pair order must agree)
+    counts = np.zeros(nlat * vdim)
+    for r, (f, t) in enumerate(zip(spaces, tabs)):
+        y = np.full(f.ndofs * vdim, np.nan)
+        y[t["ltdof_ldof"]] = x_t[r]
+        for k, nb in enumerate(t["nbr_rank"]):
+            tn = tabs[nb]
+            kk = list(tn["nbr_rank"]).index(r)
+            sent = x_t[nb][tn["shr_ltdof"][tn["shr_offsets"][kk]:tn["shr_offsets"][kk + 1]]]
+            seg = t["ext_ldof"][t["ext_offsets"][k]:t["ext_offsets"][k + 1]]
+            assert len(sent) == len(seg)
+            y[seg] = sent
+        assert np.array_equal(y, field[vd(f.halo_tables["ldof_lattice"])])
+    # P^T of ones: every owner collects one contribution per sharing rank
+    for r, (f, t) in enumerate(zip(spaces, tabs)):
+        acc = np.ones(f.ntdofs * vdim)
+        for k, nb in enumerate(t["nbr_rank"]):
+            tn = tabs[nb]
+            kk = list(tn["nbr_rank"]).index(r)
+            n_in = tn["ext_offsets"][kk + 1] - tn["ext_offsets"][kk]
+            seg = t["shr_ltdof"][t["shr_offsets"][k]:t["shr_offsets"][k + 1]]
+            assert n_in == len(seg)
+            np.add.at(acc, seg, 1.0)
+        counts[vd(f.halo_tables["ldof_lattice"][f.halo_tables["ltdof_ldof"]])] += acc
+    # each global vdof is owned by exactly one rank; its count = number of ranks holding it
+    holders = np.zeros(nlat * vdim)
+    for f in spaces:
+        holders[vd(f.halo_tables["ldof_lattice"])] += 1
+    assert np.array_equal(counts, holders)

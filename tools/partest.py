@@ -24,7 +24,9 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--order", dest="p", type=int, default=3)
 ap.add_argument("--elems", dest="n", type=int, default=6, help="elements per side per rank")
 ap.add_argument("--integrator", dest="kind", default="diffusion")
+ap.add_argument("--vdim", type=int, default=1, help="3: vector space (CEED BP2/BP4), Ordering::byVDIM")
 a = ap.parse_args()
+vd = a.vdim
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 lr = int(os.environ.get("LOCAL_RANK", rank))
@@ -37,7 +39,7 @@ p = a.p
 
 
 def build(mesh):
-    fes = m.FiniteElementSpace(mesh, m.H1_FECollection(p, 3))
+    fes = m.FiniteElementSpace(mesh, m.H1_FECollection(p, 3), vd, "byVDIM" if vd > 1 else "byNODES")
     it = (m.MassIntegrator if a.kind == "mass" else m.DiffusionIntegrator)(1.0, m.IntRules.Get(3, 2 * p + 3))
     form = m.BilinearForm(dev, fes)
     form.AddDomainIntegrator(it)
@@ -49,7 +51,7 @@ def build(mesh):
 fes, form = build(m.Mesh(3, N[0], N[1], N[2], True, part=grid, rank=rank))
 ids = [m.Halo.unique_id() if rank == 0 else None]
 dist.broadcast_object_list(ids, src=0)
-halo = m.Halo(dev, rank, world, fes.ndofs, fes.halo_tables, ids[0])
+halo = m.Halo(dev, rank, world, fes.ndofs, fes.halo_tables, ids[0], vdim=vd)
 form.SetHalo(halo)
 # serial problem on the union mesh (every rank solves it on its own GPU as the reference)
 sfes, sform = build(m.Mesh(3, N[0], N[1], N[2], True, part=(1, 1, 1), rank=0))
@@ -59,8 +61,15 @@ own = fes.halo_tables["ltdof_ldof"]
 nlat = len(slat)
 s_of_lat = np.empty(nlat, np.int64)
 s_of_lat[slat] = np.arange(nlat)
-t2s = torch.from_numpy(s_of_lat[lat[own]]).to(dev.tdev)   # my true dofs -> serial dof ids
-l2s = torch.from_numpy(s_of_lat[lat]).to(dev.tdev)
+def vdofs(ids):
+    """scalar dof ids -> vdof ids (byVDIM)"""
+    return (ids[:, None] * vd + np.arange(vd)[None, :]).ravel()
+
+
+t2s = torch.from_numpy(vdofs(s_of_lat[lat[own]])).to(dev.tdev)   # my true (v)dofs -> serial (v)dof ids
+l2s = torch.from_numpy(vdofs(s_of_lat[lat])).to(dev.tdev)
+nlat *= vd
+NT, NL = fes.ntdofs * vd, fes.ndofs * vd
 
 
 def rel(u, v):
@@ -71,14 +80,14 @@ gen = torch.Generator(device="cpu").manual_seed(7)
 xs = torch.rand(nlat, dtype=torch.float64, generator=gen).to(dev.tdev)  # same on every rank
 x_t = xs[t2s].contiguous()
 # P
-x_l = dev.empty(fes.ndofs)
+x_l = dev.empty(NL)
 halo.Mult(x_t, x_l)
 dev.sync()
 assert torch.equal(x_l, xs[l2s]), "P does not reproduce the global field"
 def check(mode):
     global form
     # y = P^T A P x
-    y_t, ys = dev.empty(fes.ntdofs), dev.empty(nlat)
+    y_t, ys = dev.empty(NT), dev.empty(nlat)
     form.Mult(x_t, y_t)
     sform.Mult(xs, ys)
     dev.sync()
@@ -87,19 +96,19 @@ def check(mode):
     # constrained operator + diagonal
     ess, sess = fes.GetEssentialTrueDofs(), sfes.GetEssentialTrueDofs()
     b_l = m.LinearForm(dev, fes).Assemble()
-    b_t = dev.empty(fes.ntdofs)
+    b_t = dev.empty(NT)
     halo.MultTranspose(b_l, b_t)
     bs = m.LinearForm(dev, sfes).Assemble()
     dev.sync()
     assert rel(b_t, bs[t2s]) < 1e-12
-    A, _, B = form.FormLinearSystem(ess, dev.zeros(fes.ntdofs), b_t)
+    A, _, B = form.FormLinearSystem(ess, dev.zeros(NT), b_t)
     As, _, Bs = sform.FormLinearSystem(sess, dev.zeros(nlat), bs)
     A.Mult(x_t, y_t)
     As.Mult(xs, ys)
     dev.sync()
     e2 = rel(y_t, ys[t2s])
     assert e2 < 1e-12, f"constrained operator parity {e2}"
-    dg, dgs = dev.empty(fes.ntdofs), dev.empty(nlat)
+    dg, dgs = dev.empty(NT), dev.empty(nlat)
     form.AssembleDiagonal(dg)
     sform.AssembleDiagonal(dgs)
     dev.sync()
@@ -112,7 +121,7 @@ def check(mode):
     # PCG
     M, Ms = m.OperatorJacobiSmoother(form, ess), m.OperatorJacobiSmoother(sform, sess)
     res = []
-    for (AA, MM, BB, n) in ((A, M, B, fes.ntdofs), (As, Ms, Bs, nlat)):
+    for (AA, MM, BB, n) in ((A, M, B, NT), (As, Ms, Bs, nlat)):
         cg = m.CGSolver()
         cg.SetRelTol(1e-8); cg.SetMaxIter(1000); cg.SetOperator(AA); cg.SetPreconditioner(MM)
         X = dev.zeros(n)
@@ -128,14 +137,14 @@ def check(mode):
     Sp = m.OperatorChebyshevSmoother(A, dg, 3, None, 10, 1e-8, start=start[t2s.cpu().numpy()])
     assert abs(Sp.max_eig_estimate - Ss.max_eig_estimate) < 1e-10 * Ss.max_eig_estimate, \
         (Sp.max_eig_estimate, Ss.max_eig_estimate)
-    z_t, zs = dev.empty(fes.ntdofs), dev.empty(nlat)
+    z_t, zs = dev.empty(NT), dev.empty(nlat)
     Sp.Mult(x_t, z_t)
     Ss.Mult(xs, zs)
     dev.sync()
     e5 = rel(z_t, zs[t2s])
     assert e5 < 1e-10, f"Chebyshev action {e5}"
     res = []
-    for (AA, MM, BB, n) in ((A, Sp, B, fes.ntdofs), (As, Ss, Bs, nlat)):
+    for (AA, MM, BB, n) in ((A, Sp, B, NT), (As, Ss, Bs, nlat)):
         cg = m.CGSolver()
         cg.SetRelTol(1e-8); cg.SetMaxIter(1000); cg.SetOperator(AA); cg.SetPreconditioner(MM)
         X = dev.zeros(n)
@@ -155,7 +164,7 @@ out["p2p"] = check("p2p")
 e1, e2, e3, it_p, it_s, e4 = out["p2p"]
 dist.barrier()
 if rank == 0:
-    print(f"PARTEST OK (nccl and p2p halo) world={world} grid={grid} p={p} n/rank={a.n} kind={a.kind}: RAP {e1:.1e} constrained {e2:.1e} "
+    print(f"PARTEST OK (nccl and p2p halo) world={world} grid={grid} p={p} n/rank={a.n} kind={a.kind} vdim={vd}: RAP {e1:.1e} constrained {e2:.1e} "
           f"diag {e3:.1e} pcg its {it_p} vs serial {it_s}, sol {e4:.1e}")
 halo.close()
 dist.destroy_process_group()
