@@ -2,7 +2,7 @@
 """bench.py -- CEED BP GDOF/s (DOFs x CG iterations / s) of the B200 partial-assembly path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--bp 1|3|5] [--p P] [--n ELEMS_PER_SIDE_PER_GPU] [--iters I]
+                    [--bp 1..6] [--p P] [--n ELEMS_PER_SIDE_PER_GPU] [--iters I]
 
 One "step" = one BP solve: Jacobi-preconditioned CG with a FIXED number of iterations
 (rel_tol = 0, the protocol of tests/benchmarks/bench_ceed.cpp:222-243) on a synthetic
@@ -10,8 +10,9 @@ structured hex mesh of the unit cube, all-boundary Dirichlet, RHS (1, phi_i), x0
 Default workload (BASELINE.json configs[2], the config the metric is quoted on at one
 GPU): BP3 diffusion, p = 4, Q = 6, 133^3 elements = 151.4 M dofs.  With --gpus N > 1
 (configs[3]) each rank owns a 116^3-element block (100.5 M dofs / GPU, weak scaling) of a
-2x1x1 / 2x2x1 / 2x2x2 Cartesian partition; shared dofs go over NCCL send/recv and the PCG
-dot products over ncclAllReduce.
+2x1x1 / 2x2x1 / 2x2x2 Cartesian partition; shared dofs go over peer-memory stores (CUDA IPC
+over NVLink; B2F_HALO=nccl selects ncclSend/Recv) and the PCG dot products over
+ncclAllReduce.  --bp 2/4/6 are the vector (vdim = 3, byVDIM) forms.
 
 Prints ONE JSON line (rank 0).  `value`: device-resident solves, CUDA-event timed, max
 over ranks.  `e2e`: the same solves through the public API with HOST buffers -- the RHS

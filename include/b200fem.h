@@ -312,6 +312,9 @@ int b2f_pcg_chebyshev(b2f_operator *op, b2f_chebyshev *cheb, const double *b, do
  * NCCL send/recv over NVLink instead of MPI_Isend/Irecv. */
 /* rank 0 creates the id and distributes it out of band (e.g. torch.distributed) */
 int b2f_nccl_unique_id_h(void *id128_h);
+/* For a vector space (vdim > 1, Ordering::byVDIM) every table is on vdofs (vdof = ldof*vdim
+ * + c), as the communicator of a ParFiniteElementSpace with vdim > 1 holds them; n_ldofs and
+ * n_tdofs then count vdofs. */
 int b2f_halo_create(b2f_ctx *ctx, const void *nccl_id128_h, int rank, int nranks,
                     int n_ldofs, int n_tdofs,
                     const int *ltdof_ldof_h,         /* [n_tdofs] owned ldofs, ascending   */
