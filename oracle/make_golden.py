@@ -20,6 +20,7 @@ import refio  # noqa: E402
 OUT = os.path.join(os.path.dirname(refio.HERE), "tests", "golden")
 
 # name -> ref_driver arguments.  Sizes are kept tiny: every array on the path is stored.
+DATA = "/root/reference/data/"
 CASES = {
     # BP3-style diffusion, Gauss-Legendre Q = p+2 (bench_ceed.cpp:121)
     "diff3d_p1_n3": dict(dim=3, n=3, p=1, kind="diffusion"),
@@ -80,6 +81,15 @@ CASES = {
     "mark_3d_p3_n3_plain_first": dict(dim=3, n=3, p=3, kind="diffusion", markers=1, nattr=2, marker_order=1,
                                       jacobi=0, maxit=25),
     "mark_2d_p3_n5": dict(dim=2, n=5, p=3, kind="diffusion", markers=1, nattr=3, maxit=25),
+    # meshes from the reference's data directory (unstructured numbering, twisted orientations,
+    # curved Q2/Q3 nodes); inline-hex -o 3 is BASELINE config C1 (here refined once, not 3 times)
+    "mesh_inline_hex_r1_p3": dict(mesh=DATA + "inline-hex.mesh", refine=1, p=3, kind="diffusion", lean=1),
+    "mesh_toroid_hex_r1_p2": dict(mesh=DATA + "toroid-hex.mesh", refine=1, p=2, kind="diffusion", lean=1),
+    "mesh_toroid_hex_r0_p5_mass": dict(mesh=DATA + "toroid-hex.mesh", refine=0, p=5, kind="mass", lean=1),
+    "mesh_fichera_q2_r1_p4": dict(mesh=DATA + "fichera-q2.mesh", refine=1, p=4, kind="diffusion", lean=1),
+    "mesh_star_q3_r1_p3": dict(mesh=DATA + "star-q3.mesh", refine=1, p=3, kind="diffusion", lean=1),
+    "mesh_fichera_q3_r0_p7_bp5": dict(mesh=DATA + "fichera-q3.mesh", refine=0, p=7, kind="diffusion", quad="gll",
+                                      lean=1),
     # DomainLFIntegrator / VectorDomainLFIntegrator device assembly (LinearForm::UseFastAssembly)
     "lf_3d_p2_n3": dict(dim=3, n=3, p=2, kind="mass", lf=1, nattr=2),
     "lf_3d_p4_n2_curved": dict(dim=3, n=2, p=4, kind="mass", lf=1, nattr=3, curved=1),

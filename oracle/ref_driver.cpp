@@ -512,6 +512,96 @@ static int do_dump_nonsym(const Args &A, const char *out)
    return 0;
 }
 
+// Unstructured / curved meshes from the reference's data directory (inline-hex = BASELINE
+// config C1, toroid-hex, fichera-q2, star-q3): a lean dump -- the reference's own tables, the
+// nodes E-vector and the results of the path, without the bulky geometric factors.
+static int do_dump_mesh(const Args &A, const char *out)
+{
+   Problem P(A);
+   Dump D(out);
+   P.a->Assemble();
+   FiniteElementSpace &fes = *P.fes;
+   const FiniteElement &fe = *fes.GetTypicalFE();
+   const DofToQuad &maps = fe.GetDofToQuad(*P.ir, DofToQuad::TENSOR);
+   const int D1D = maps.ndof, Q1D = maps.nqpt, NE = fes.GetNE(), ndofs = fes.GetNDofs();
+   const int dim = P.dim;
+   D.scalar("dim", dim); D.scalar("p", P.p);
+   D.scalar("D1D", D1D); D.scalar("Q1D", Q1D); D.scalar("NE", NE); D.scalar("ndofs", ndofs);
+   D.scalar("is_mass", (int)P.mass);
+   auto R = dynamic_cast<const ElementRestriction *>(
+               fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC));
+   D.ints("gather_map", R->GatherMap());
+   D.ints("offsets", R->Offsets());
+   D.ints("indices", R->Indices());
+   D.dbls("B", maps.B); D.dbls("G", maps.G);
+   D.dbls("W", P.ir->GetWeights());
+   P.mesh.EnsureNodes();
+   const GridFunction *nodes = P.mesh.GetNodes();
+   const FiniteElementSpace *nfes = nodes->FESpace();
+   const Operator *nR = nfes->GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC);
+   Vector nodesE(nR->Height());
+   nR->Mult(*nodes, nodesE);
+   D.scalar("node_D1D", nfes->GetTypicalFE()->GetOrder() + 1);
+   D.dbls("nodesE", nodesE);
+   {
+      const DofToQuad &nm = nfes->GetTypicalFE()->GetDofToQuad(*P.ir, DofToQuad::TENSOR);
+      D.dbls("Bn", nm.B); D.dbls("Gn", nm.G);
+   }
+   Vector x(ndofs); x.Randomize(1);
+   D.dbls("x", x);
+   Vector y(ndofs);
+   P.a->Mult(x, y);
+   D.dbls("y", y);
+   Vector diag(ndofs);
+   P.a->AssembleDiagonal(diag);
+   D.dbls("diag", diag);
+   Array<int> ess_bdr(P.mesh.bdr_attributes.Max()); ess_bdr = 1;
+   Array<int> ess;
+   fes.GetEssentialTrueDofs(ess_bdr, ess);
+   D.ints("ess_tdof_list", ess);
+   LinearForm b(&fes);
+   b.AddDomainIntegrator(new DomainLFIntegrator(P.one));
+   b.Assemble();
+   D.dbls("b", b);
+   GridFunction u(&fes); u = 0.0;
+   OperatorPtr Aop; Vector B, X;
+   P.a->FormLinearSystem(ess, u, b, Aop, X, B);
+   D.dbls("B_rhs", B);
+   Vector cy(ndofs);
+   Aop->Mult(x, cy);
+   D.dbls("y_constrained", cy);
+   // ex1.cpp:266-267: PCG(*A, M, B, X, 1, 400, 1e-12, 0.0) -- rel_tol^2 = 1e-12
+   const double rtol = A.getd("rtol", 1e-6);
+   OperatorJacobiSmoother M(*P.a, ess);
+   CGSolver cg;
+   cg.SetRelTol(rtol); cg.SetAbsTol(0.0); cg.SetMaxIter(A.geti("maxit", 400));
+   cg.SetOperator(*Aop);
+   cg.SetPreconditioner(M);
+   std::stringstream hist;
+   std::streambuf *old = mfem::out.rdbuf(hist.rdbuf());
+   cg.SetPrintLevel(1);
+   X = 0.0;
+   cg.Mult(B, X);
+   mfem::out.rdbuf(old);
+   std::vector<double> h;
+   {
+      string line;
+      while (std::getline(hist, line))
+      {
+         size_t pos = line.find("(B r, r) =");
+         if (pos != string::npos) { h.push_back(atof(line.c_str() + pos + 10)); }
+      }
+   }
+   D.dbls("pcg_history", h.data(), h.size());
+   D.scalar("pcg_iters", cg.GetNumIterations());
+   D.scalar("pcg_converged", (int)cg.GetConverged());
+   D.scalar("pcg_rtol", rtol);
+   D.dbls("X_sol", X);
+   std::printf("dump %s: mesh file dim=%d NE=%d p=%d ndofs=%d node order %d |y|=%.17g pcg_iters=%d\n", out, dim, NE,
+               P.p, ndofs, nfes->GetTypicalFE()->GetOrder(), y.Norml2(), cg.GetNumIterations());
+   return 0;
+}
+
 // DomainLFIntegrator / VectorDomainLFIntegrator fast assembly (LinearForm::UseFastAssembly,
 // fem/linearform_ext.cpp:20-66; fem/integ/lininteg_domain.cpp, lininteg_domain_kernels.hpp)
 static double lf_coeff(const Vector &x)
@@ -897,6 +987,7 @@ int main(int argc, char **argv)
       if (A.geti("cheb", 0)) { return do_dump_cheb(A, argv[2]); }
       if (A.geti("markers", 0)) { return do_dump_markers(A, argv[2]); }
       if (A.geti("lf", 0)) { return do_dump_lf(A, argv[2]); }
+      if (A.geti("lean", 0)) { return do_dump_mesh(A, argv[2]); }
       return A.geti("vdim", 1) > 1 ? do_dump_vector(A, argv[2]) : do_dump(A, argv[2]);
    }
    if (cmd == "bench") { Args A(argc, argv, 2); return do_bench(A); }

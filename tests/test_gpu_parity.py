@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from conftest import (chebyshev_golden_names, golden_names, lf_golden_names, load_golden, marker_golden_names,
-                      nonsym_golden_names, relerr)
+                      mesh_golden_names, nonsym_golden_names, relerr)
 
 pytestmark = pytest.mark.gpu
 
@@ -693,3 +693,65 @@ def test_domain_linear_form_device_assembly(dev, name):
     R.MultTranspose(be, b)
     assert relerr(host(b), g["b_fast"]) < TOL
     R.close()
+
+
+@pytest.mark.parametrize("name", mesh_golden_names())
+def test_reference_mesh_files(dev, name):
+    """The reference's own unstructured / curved meshes (inline-hex = BASELINE config C1 refined
+    once, toroid-hex with rotated faces and cubic nodes, fichera-q2/q3, star-q3 in 2D): its
+    tables and nodes E-vector in; quadrature data fused from the nodes, operator, diagonal,
+    constrained operator and the ex1 solve (PCG(A, M, B, X, 1, 400, 1e-12, 0)) out."""
+    import mfem_b200 as m
+    g = load_golden(name)
+    a, it, R = make_form(dev, g, ess=True, from_nodes=True)
+    nd = R.ndofs
+    x = dev.to_device(g["x"])
+    y, y2, d = dev.empty(nd), dev.empty(nd), dev.empty(nd)
+    a.Mult(x, y)
+    assert relerr(host(y), g["y"]) < TOL
+    a.MultUnfused(x, y2)
+    assert relerr(host(y2), g["y"]) < TOL
+    a.AssembleDiagonal(d)
+    assert relerr(host(d), g["diag"]) < TOL
+    ess = g["ess_tdof_list"]
+    A, X, B = a.FormLinearSystem(ess, dev.zeros(nd), dev.to_device(g["b"]))
+    assert relerr(host(B), g["B_rhs"]) < TOL
+    A.Mult(x, y)
+    assert relerr(host(y), g["y_constrained"]) < TOL
+    cg = m.CGSolver()
+    cg.SetRelTol(float(g["pcg_rtol"][0])); cg.SetAbsTol(0.0); cg.SetMaxIter(400)
+    cg.SetOperator(A); cg.SetPreconditioner(m.OperatorJacobiSmoother(a, ess))
+    X = dev.zeros(nd)
+    cg.Mult(B, X, record_history=True)
+    assert abs(cg.GetNumIterations() - int(g["pcg_iters"][0])) <= 1
+    assert cg.GetConverged() == bool(g["pcg_converged"][0])
+    assert relerr(host(X), g["X_sol"]) < 1e-6
+    n = min(len(cg.history), len(g["pcg_history"]), 6)
+    assert np.allclose(cg.history[:n], g["pcg_history"][:n], rtol=2e-5)
+    a.close(); it.close(); R.close()
+
+
+def test_config_c1_iteration_count(dev):
+    """BASELINE config C1 at full size: ex1 -pa -o 3 on inline-hex refined 3 times (32,768 hexes,
+    912,673 unknowns) takes 197 PCG+Jacobi iterations in the reference (SURVEY.md section 6,
+    examples/ex1.cpp:266).  The same domain and discretisation from the library's own tables
+    (32^3 Cartesian hexes; the iteration count does not depend on the numbering)."""
+    import mfem_b200 as m
+    p, n = 3, 32
+    fes = m.FiniteElementSpace(m.Mesh.MakeCartesian3D(n, n, n), m.H1_FECollection(p, 3))
+    assert fes.ne == 32768 and fes.ndofs == 912673
+    it = m.DiffusionIntegrator(1.0)
+    a = m.BilinearForm(dev, fes)
+    a.AddDomainIntegrator(it)
+    a.Assemble()
+    ess = fes.GetEssentialTrueDofs()
+    b = m.LinearForm(dev, fes).Assemble()
+    A, X, B = a.FormLinearSystem(ess, dev.zeros(fes.ndofs), b)
+    cg = m.CGSolver()
+    cg.SetRelTol(1e-6); cg.SetAbsTol(0.0); cg.SetMaxIter(400)
+    cg.SetOperator(A); cg.SetPreconditioner(m.OperatorJacobiSmoother(a, ess))
+    X = dev.zeros(fes.ndofs)
+    cg.Mult(B, X, record_history=True)
+    assert cg.GetConverged() and abs(cg.GetNumIterations() - 197) <= 1, cg.GetNumIterations()
+    assert abs(cg.history[0] - 1.84147e-05) < 2e-10          # (B r, r) at iteration 0, 6 printed digits
+    a.close(); it.close()
