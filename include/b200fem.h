@@ -179,6 +179,10 @@ int b2f_pa_add_mult(b2f_pa *pa, const double *x_e, double *y_e);
  * symmetric operators; like the reference (bilininteg_diffusion_pa.cpp:95-106) it fails for a
  * diffusion integrator with a non-symmetric matrix coefficient. */
 int b2f_pa_add_mult_transpose(b2f_pa *pa, const double *x_e, double *y_e);
+/* BilinearFormIntegrator::AddAbsMultPA (DiffusionIntegrator: bilininteg_diffusion_pa.cpp:196-209,
+ * MassIntegrator: bilininteg_mass_pa.cpp:207-228): the same kernels with |B|, |G| and
+ * |pa_data| (an absolute-value twin of the integrator is built on first use). */
+int b2f_pa_add_abs_mult(b2f_pa *pa, const double *x_e, double *y_e);
 /* VectorDiffusionIntegrator / VectorMassIntegrator::AddMultPA (fem/integ/
  * bilininteg_vecdiffusion_pa.cpp, bilininteg_vecmass_pa.cpp; CEED BP2/4/6): the same operator on
  * every component of an E-vector laid out (dofs, vdim, NE); one quadrature-data load serves
@@ -220,6 +224,12 @@ int b2f_operator_mult_unfused(b2f_operator *op, const double *x_l, double *y_l);
 /* ConstrainedOperator::Mult (linalg/operator.cpp:601-660, DIAG_ONE):
  * z = x; z[ess] = 0; y = A z; y[ess] = x[ess]. */
 int b2f_operator_mult_constrained(b2f_operator *op, const double *x_l, double *y_l);
+/* Operator::AbsMult (linalg/operator.hpp:96): PABilinearFormExtension::AbsMult =
+ * MultInternal(x, y, useAbs = true) (bilinearform_ext.cpp:487-564: |R|, AddAbsMultPA with
+ * markers, |R|^T), wrapped by RAPOperator::AbsMult when a halo is attached, and
+ * ConstrainedOperator::AbsMult (linalg/operator.cpp:663-735).  Scalar spaces. */
+int b2f_operator_abs_mult(b2f_operator *op, const double *x, double *y);
+int b2f_operator_abs_mult_constrained(b2f_operator *op, const double *x, double *y);
 /* PABilinearFormExtension::AssembleDiagonal (bilinearform_ext.cpp:370-454) */
 int b2f_operator_assemble_diagonal(b2f_operator *op, double *diag_l);
 /* ConstrainedOperator::EliminateRHS (linalg/operator.cpp:574-599) */

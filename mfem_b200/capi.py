@@ -79,6 +79,7 @@ PROTOTYPES = {
     "b2f_pa_destroy": (None, [vp]),
     "b2f_pa_data": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
     "b2f_pa_add_mult": (C.c_int, [vp, vp, vp]),
+    "b2f_pa_add_abs_mult": (C.c_int, [vp, vp, vp]),
     "b2f_pa_add_mult_transpose": (C.c_int, [vp, vp, vp]),
     "b2f_pa_add_mult_vec": (C.c_int, [vp, C.c_int, vp, vp]),
     "b2f_pa_assemble_diagonal": (C.c_int, [vp, vp]),
@@ -89,6 +90,8 @@ PROTOTYPES = {
     "b2f_operator_mult": (C.c_int, [vp, vp, vp]),
     "b2f_operator_mult_unfused": (C.c_int, [vp, vp, vp]),
     "b2f_operator_mult_constrained": (C.c_int, [vp, vp, vp]),
+    "b2f_operator_abs_mult": (C.c_int, [vp, vp, vp]),
+    "b2f_operator_abs_mult_constrained": (C.c_int, [vp, vp, vp]),
     "b2f_operator_assemble_diagonal": (C.c_int, [vp, vp]),
     "b2f_operator_eliminate_rhs": (C.c_int, [vp, vp, vp]),
     "b2f_operator_set_halo": (C.c_int, [vp, vp]),

@@ -444,6 +444,7 @@ int b2f_pa_setup_from_nodes(b2f_ctx *ctx, int kind, int dim, int d1d, int q1d, i
 void b2f_pa_destroy(b2f_pa *pa)
 {
    if (!pa) { return; }
+   b2f_pa_destroy(pa->abs_twin);
    cudaFree(pa->data);
    cudaFree(pa->d_B);
    cudaFree(pa->d_G);
@@ -462,6 +463,46 @@ int b2f_pa_add_mult(b2f_pa *pa, const double *x_e, double *y_e)
 {
    B2F_REQUIRE(pa && (pa->ne == 0 || (x_e && y_e)), "b2f_pa_add_mult: NULL argument");
    return pa_apply(pa, x_e, y_e, nullptr);
+}
+
+} // extern "C"
+__global__ void abs_copy_kernel(int64_t n, const double *__restrict__ src, double *__restrict__ dst)
+{
+   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+   {
+      dst[i] = fabs(src[i]);
+   }
+}
+// the integrator with |B|, |G| and |pa_data| (DiffusionIntegrator::AddAbsMultPA,
+// bilininteg_diffusion_pa.cpp:196-209; MassIntegrator::AddAbsMultPA, bilininteg_mass_pa.cpp:207-228)
+static int pa_abs_twin(b2f_pa *pa, b2f_pa **out)
+{
+   if (!pa->abs_twin)
+   {
+      double Ba[256], Ga[256];
+      for (int i = 0; i < 256; i++) { Ba[i] = fabs(pa->B[i]); Ga[i] = fabs(pa->G[i]); }
+      b2f_pa *t = nullptr;
+      B2F_TRY(pa_alloc(pa->ctx, pa->kind, pa->dim, pa->d1d, pa->q1d, pa->ne, pa->ncomp, Ba, Ga, &t));
+      t->symmetric = pa->symmetric;
+      if (pa->data_size)
+      {
+         abs_copy_kernel<<<(unsigned)std::min<int64_t>(cdiv(pa->data_size, 256), 148 * 64), 256, 0,
+                           pa->ctx->stream>>>(pa->data_size, pa->data, t->data);
+         if (cudaGetLastError() != cudaSuccess) { b2f_pa_destroy(t); B2F_REQUIRE(false, "abs twin: launch failed"); }
+      }
+      pa->abs_twin = t;
+   }
+   *out = pa->abs_twin;
+   return B2F_OK;
+}
+extern "C" {
+
+int b2f_pa_add_abs_mult(b2f_pa *pa, const double *x_e, double *y_e)
+{
+   B2F_REQUIRE(pa && (pa->ne == 0 || (x_e && y_e)), "b2f_pa_add_abs_mult: NULL argument");
+   b2f_pa *t = nullptr;
+   B2F_TRY(pa_abs_twin(pa, &t));
+   return pa_apply(t, x_e, y_e, nullptr);
 }
 
 int b2f_pa_add_mult_transpose(b2f_pa *pa, const double *x_e, double *y_e)
@@ -598,6 +639,7 @@ static int marked_rebuild(b2f_operator *op, size_t i)
    B2F_TRY(upload(rows.data(), rows.size(), &d_rows));
    const int64_t slab = pa->ne ? pa->data_size / pa->ne : 0;
    m->cpa = new b2f_pa(*pa);
+   m->cpa->abs_twin = nullptr;
    m->cpa->data = nullptr;
    m->cpa->ne = m->ne_c;
    m->cpa->data_size = slab * m->ne_c;
@@ -852,18 +894,20 @@ static bool operator_has_fused_dot(const b2f_operator *op)
    return true;
 }
 
-static int local_mult_unfused(b2f_operator *op, const double *x_l, double *y_l)
+// use_abs: PABilinearFormExtension::AbsMult -> MultInternal(x, y, true): |R|, AddAbsMultPA, |R|^T
+static int local_mult_unfused(b2f_operator *op, const double *x_l, double *y_l, bool use_abs = false)
 {
    b2f_ctx *ctx = op->ctx;
    b2f_restriction *r = op->r;
    const int64_t ne_dof = (int64_t)r->ne * r->dof * r->vdim;
    B2F_TRY(ensure(&op->xe, ne_dof));
    B2F_TRY(ensure(&op->ye, ne_dof));
-   B2F_TRY(restriction_gather(r, x_l, op->xe, false));                 // bilinearform_ext.cpp:543
+   B2F_TRY(restriction_gather(r, x_l, op->xe, use_abs));               // bilinearform_ext.cpp:537-544
    B2F_CUDA(cudaMemsetAsync(op->ye, 0, sizeof(double) * ne_dof, ctx->stream)); // :545
    for (size_t i = 0; i < op->integ.size(); i++)                       // :548
    {
       b2f_pa *pa = op->integ[i];
+      if (use_abs) { B2F_TRY(pa_abs_twin(op->integ[i], &pa)); }
       double *out = op->ye;
       if (op->marked[i])
       {
@@ -883,7 +927,7 @@ static int local_mult_unfused(b2f_operator *op, const double *x_l, double *y_l)
          B2F_LAUNCH_CHECK(ctx);
       }
    }
-   return restriction_scatter(r, op->ye, y_l, 0);                      // :557
+   return restriction_scatter(r, op->ye, y_l, use_abs ? 2 : 0);        // :551-558
 }
 
 static int local_mult(b2f_operator *op, const double *x_l, double *y_l, bool constrained_mask,
@@ -1024,6 +1068,43 @@ int b2f_operator_mult_unfused(b2f_operator *op, const double *x_l, double *y_l)
    B2F_REQUIRE(op && x_l && y_l, "b2f_operator_mult_unfused: NULL argument");
    B2F_REQUIRE(!op->halo, "b2f_operator_mult_unfused: local operators only");
    return local_mult_unfused(op, x_l, y_l);
+}
+
+// Operator::AbsMult (linalg/operator.hpp:96) of the PA operator: RAPOperator::AbsMult
+// (operator.hpp:1002; the conforming P has 0/1 entries, so |P| = P) around
+// PABilinearFormExtension::AbsMult = MultInternal(x, y, useAbs = true) (bilinearform_ext.cpp:487-564)
+static int rap_abs_mult(b2f_operator *op, const double *x, double *y)
+{
+   B2F_REQUIRE(op->r->vdim == 1, "AbsMult: scalar spaces only");
+   if (!op->halo) { return local_mult_unfused(op, x, y, true); }
+   const int nl = op->r->ndofs;
+   B2F_TRY(ensure(&op->xl, nl));
+   B2F_TRY(ensure(&op->yl, nl));
+   B2F_TRY(halo_mult(op->halo, x, op->xl));
+   B2F_TRY(local_mult_unfused(op, op->xl, op->yl, true));
+   return halo_mult_transpose(op->halo, op->yl, y);
+}
+
+int b2f_operator_abs_mult(b2f_operator *op, const double *x, double *y)
+{
+   B2F_REQUIRE(op && x && y, "b2f_operator_abs_mult: NULL argument");
+   B2F_REQUIRE(x != y, "b2f_operator_abs_mult: x and y alias");
+   return rap_abs_mult(op, x, y);
+}
+
+int b2f_operator_abs_mult_constrained(b2f_operator *op, const double *x, double *y)
+{
+   B2F_REQUIRE(op && x && y, "b2f_operator_abs_mult_constrained: NULL argument");
+   B2F_REQUIRE(x != y, "b2f_operator_abs_mult_constrained: x and y alias");
+   if (op->n_ess == 0) { return rap_abs_mult(op, x, y); }
+   // ConstrainedOperator::ConstrainedAbsMult (linalg/operator.cpp:663-722, DIAG_ONE)
+   b2f_ctx *ctx = op->ctx;
+   const int n = b2f_operator_height(op);
+   B2F_TRY(ensure(&op->z, n));
+   B2F_CUDA(cudaMemcpyAsync(op->z, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+   B2F_TRY(set_entries(ctx, op->z, op->ess, op->n_ess, 0.0));
+   B2F_TRY(rap_abs_mult(op, op->z, y));
+   return copy_entries(ctx, y, x, op->ess, op->n_ess);
 }
 
 // dot_acc != nullptr: additionally leave (x, y) = sum_e z_e.(A_e z_e) + sum_ess x_i^2 in dot_acc

@@ -116,6 +116,8 @@ struct b2f_pa
    // x[g*vxs + c*vxo]; the gather index of component c starts at idx + c*vics
    int vd = 1;
    int64_t vxs = 1, vxo = 0, vics = 0;
+   // |B|, |G|, |D| twin for AddAbsMultPA (built on first use, owned)
+   b2f_pa *abs_twin = nullptr;
 };
 
 // A domain integrator restricted to the elements whose attribute is marked

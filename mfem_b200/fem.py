@@ -435,6 +435,9 @@ class _PAIntegrator:
         else:
             call("b2f_pa_add_mult_vec", self.h, vdim, _dp(x_e), _dp(y_e))
 
+    def AddAbsMultPA(self, x_e, y_e):
+        call("b2f_pa_add_abs_mult", self.h, _dp(x_e), _dp(y_e))
+
     def AddMultTransposePA(self, x_e, y_e):
         call("b2f_pa_add_mult_transpose", self.h, _dp(x_e), _dp(y_e))
 
@@ -621,6 +624,9 @@ class BilinearForm:
     def MultUnfused(self, x, y):
         call("b2f_operator_mult_unfused", self.op, _dp(x), _dp(y))
 
+    def AbsMult(self, x, y):
+        call("b2f_operator_abs_mult", self.op, _dp(x), _dp(y))
+
     def AssembleDiagonal(self, diag):
         call("b2f_operator_assemble_diagonal", self.op, _dp(diag))
 
@@ -649,6 +655,9 @@ class ConstrainedOperator:
 
     def Mult(self, x, y):
         call("b2f_operator_mult_constrained", self.form.op, _dp(x), _dp(y))
+
+    def AbsMult(self, x, y):
+        call("b2f_operator_abs_mult_constrained", self.form.op, _dp(x), _dp(y))
 
     def EliminateRHS(self, x, b):
         call("b2f_operator_eliminate_rhs", self.form.op, _dp(x), _dp(b))

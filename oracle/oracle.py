@@ -266,6 +266,28 @@ class Operator:
         return x, its, bool(conv.value), fn.value, hist[:its + 1]
 
 
+def abs_mult(dim, d1d, q1d, ne, ndofs, gather_map, offsets, indices, B, G, D, x, is_mass=False, ess=None):
+    """Operator::AbsMult of the PA operator (PABilinearFormExtension::MultInternal with useAbs,
+    fem/bilinearform_ext.cpp:487-564; AddAbsMultPA: |B|, |G|, |pa_data|), optionally behind
+    ConstrainedOperator::AbsMult (linalg/operator.cpp:663-722).  Returns (y, y_e)."""
+    dof = d1d ** dim
+    x = _f64(x)
+    z = x.copy()
+    if ess is not None and len(ess):
+        z[ess] = 0.0
+    g = _i32(gather_map)
+    xe = z[np.where(g >= 0, g, -1 - g)]                      # |R|: signs dropped (restriction.cpp:138-157)
+    Ba, Ga, Da = np.abs(_f64(B)), np.abs(_f64(G)), np.abs(_f64(D))
+    if is_mass:
+        ye = mass_apply(dim, d1d, q1d, ne, Ba, Da, xe)
+    else:
+        ye = diffusion_apply(dim, d1d, q1d, ne, Ba, Ga, Da, xe)
+    y = restriction_abs_mult_transpose(ndofs, dof, offsets, indices, ye)
+    if ess is not None and len(ess):
+        y[ess] = x[ess]
+    return y, ye
+
+
 class MarkedForm:
     """BilinearForm with PA domain integrators restricted by element attribute
     (PABilinearFormExtension::MultInternal / AddMultWithMarkers / AssembleDiagonal,

@@ -570,6 +570,27 @@ static int do_dump_mesh(const Args &A, const char *out)
    Vector cy(ndofs);
    Aop->Mult(x, cy);
    D.dbls("y_constrained", cy);
+   {
+      // Operator::AbsMult: the extension's MultInternal(useAbs) behind ConstrainedOperator::AbsMult
+      // (with and without constraints), and the integrator's AddAbsMultPA on the E-vector
+      Vector xs(x);
+      for (int i = 0; i < ndofs; i++) { xs(i) -= 0.5; } // signed input
+      D.dbls("x_signed", xs);
+      Vector ya(ndofs);
+      Aop->AbsMult(xs, ya);
+      D.dbls("y_abs_constrained", ya);
+      Array<int> no_ess;
+      OperatorPtr A0; Vector B0, X0, b0(b);
+      GridFunction u0(&fes); u0 = 0.0;
+      P.a->FormLinearSystem(no_ess, u0, b0, A0, X0, B0);
+      A0->AbsMult(xs, ya);
+      D.dbls("y_abs", ya);
+      Vector xE(R->Height()), yE(R->Height());
+      R->Mult(xs, xE);
+      yE = 0.0;
+      P.bfi->AddAbsMultPA(xE, yE);
+      D.dbls("yE_abs", yE); // input: R applied to x_signed (bit-exact gather, not dumped)
+   }
    // ex1.cpp:266-267: PCG(*A, M, B, X, 1, 400, 1e-12, 0.0) -- rel_tol^2 = 1e-12
    const double rtol = A.getd("rtol", 1e-6);
    OperatorJacobiSmoother M(*P.a, ess);

@@ -728,6 +728,17 @@ def test_reference_mesh_files(dev, name):
     assert relerr(host(X), g["X_sol"]) < 1e-6
     n = min(len(cg.history), len(g["pcg_history"]), 6)
     assert np.allclose(cg.history[:n], g["pcg_history"][:n], rtol=2e-5)
+    # Operator::AbsMult (bilinearform_ext.cpp:487-564 with useAbs; operator.cpp:663-735)
+    xs = dev.to_device(g["x_signed"])
+    A.AbsMult(xs, y)
+    assert relerr(host(y), g["y_abs_constrained"]) < TOL
+    a.AbsMult(xs, y)   # the form still carries the essential list, but AbsMult itself is unconstrained
+    assert relerr(host(y), g["y_abs"]) < TOL
+    xe = dev.empty(R.Height())
+    R.Mult(xs, xe)
+    ye = dev.zeros(R.Height())
+    it.AddAbsMultPA(xe, ye)
+    assert relerr(host(ye), g["yE_abs"]) < TOL
     a.close(); it.close(); R.close()
 
 

