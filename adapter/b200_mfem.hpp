@@ -344,6 +344,14 @@ public:
       dy.Download(y);
    }
    void MultTranspose(const mfem::Vector &x, mfem::Vector &y) const override { Mult(x, y); } // symmetric
+   /// PABilinearFormExtension::AbsMult (fem/bilinearform_ext.hpp:166)
+   void AbsMult(const mfem::Vector &x, mfem::Vector &y) const override
+   {
+      dx.Upload(x);
+      dy.Resize(height);
+      B200_CHECK(b2f_operator_abs_mult(op, dx.Ptr(), dy.Ptr()));
+      dy.Download(y);
+   }
    void AssembleDiagonal(mfem::Vector &diag) const override
    {
       dy.Resize(height);
@@ -365,6 +373,20 @@ public:
       dy.Resize(height);
       B200_CHECK(b2f_operator_mult_constrained(op, dx.Ptr(), dy.Ptr()));
       dy.Download(y);
+   }
+   /// ConstrainedOperator::AbsMult (linalg/operator.cpp:663-735) over the extension's
+   /// MultInternal(useAbs) (fem/bilinearform_ext.cpp:487-564).
+   void AbsMult(const mfem::Vector &x, mfem::Vector &y) const override
+   {
+      dx.Upload(x);
+      dy.Resize(height);
+      B200_CHECK(b2f_operator_abs_mult_constrained(op, dx.Ptr(), dy.Ptr()));
+      dy.Download(y);
+   }
+   /// Operator::DiagonalPolicy of the constrained rows (default DIAG_ONE as FormLinearSystem).
+   void SetDiagonalPolicy(mfem::Operator::DiagonalPolicy p)
+   {
+      B200_CHECK(b2f_operator_set_diag_policy(op, p == mfem::Operator::DIAG_ZERO ? 0 : p == mfem::Operator::DIAG_ONE ? 1 : 2));
    }
    /// EliminateRHS (linalg/operator.cpp:574): b -= A w (w = x on ess); b[ess] = x[ess].
    void EliminateRHS(const mfem::Vector &x, mfem::Vector &b) const

@@ -230,6 +230,12 @@ int b2f_operator_mult_constrained(b2f_operator *op, const double *x_l, double *y
  * ConstrainedOperator::AbsMult (linalg/operator.cpp:663-735).  Scalar spaces. */
 int b2f_operator_abs_mult(b2f_operator *op, const double *x, double *y);
 int b2f_operator_abs_mult_constrained(b2f_operator *op, const double *x, double *y);
+/* Operator::DiagonalPolicy of the ConstrainedOperator (linalg/operator.hpp:47-53,
+ * operator.cpp:526-660): 0 = DIAG_ZERO, 1 = DIAG_ONE (default, what FormLinearSystem uses),
+ * 2 = DIAG_KEEP (as in the reference, Mult then fails when there are constraints). */
+int b2f_operator_set_diag_policy(b2f_operator *op, int policy);
+/* ConstrainedOperator::AssembleDiagonal (operator.cpp:543-572) */
+int b2f_operator_assemble_diagonal_constrained(b2f_operator *op, double *diag);
 /* PABilinearFormExtension::AssembleDiagonal (bilinearform_ext.cpp:370-454) */
 int b2f_operator_assemble_diagonal(b2f_operator *op, double *diag_l);
 /* ConstrainedOperator::EliminateRHS (linalg/operator.cpp:574-599) */

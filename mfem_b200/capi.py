@@ -92,6 +92,8 @@ PROTOTYPES = {
     "b2f_operator_mult_constrained": (C.c_int, [vp, vp, vp]),
     "b2f_operator_abs_mult": (C.c_int, [vp, vp, vp]),
     "b2f_operator_abs_mult_constrained": (C.c_int, [vp, vp, vp]),
+    "b2f_operator_set_diag_policy": (C.c_int, [vp, C.c_int]),
+    "b2f_operator_assemble_diagonal_constrained": (C.c_int, [vp, vp]),
     "b2f_operator_assemble_diagonal": (C.c_int, [vp, vp]),
     "b2f_operator_eliminate_rhs": (C.c_int, [vp, vp, vp]),
     "b2f_operator_set_halo": (C.c_int, [vp, vp]),

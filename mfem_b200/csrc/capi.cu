@@ -889,7 +889,7 @@ static bool operator_can_split(const b2f_operator *op)
 // 17.0 vs 17.0 GDOF/s for BP3 p=4), so the plain two-kernel form stays the default.
 static bool operator_has_fused_dot(const b2f_operator *op)
 {
-   if (op->signed_map || op->r->vdim > 1 || !getenv("B2F_FUSED_DOT")) { return false; }
+   if (op->signed_map || op->r->vdim > 1 || op->diag_policy != 1 || !getenv("B2F_FUSED_DOT")) { return false; }
    for (const b2f_pa *pa : op->integ) { if (!pa_has_fused_dot(pa)) { return false; } }
    return true;
 }
@@ -1035,6 +1035,21 @@ int b2f_operator_set_markers(b2f_operator *op, int integrator, const int *elem_a
    return marked_rebuild(op, (size_t)integrator);
 }
 
+int b2f_operator_set_diag_policy(b2f_operator *op, int policy)
+{
+   B2F_REQUIRE(op && policy >= 0 && policy <= 2, "b2f_operator_set_diag_policy: bad argument");
+   op->diag_policy = policy;
+   return B2F_OK;
+}
+
+int b2f_operator_assemble_diagonal_constrained(b2f_operator *op, double *diag)
+{
+   // ConstrainedOperator::AssembleDiagonal (linalg/operator.cpp:543-572)
+   B2F_TRY(b2f_operator_assemble_diagonal(op, diag));
+   if (op->diag_policy == 2) { return B2F_OK; }
+   return set_entries(op->ctx, diag, op->ess, op->n_ess, op->diag_policy == 1 ? 1.0 : 0.0);
+}
+
 int b2f_operator_set_interior(b2f_operator *op, int64_t n_interior)
 {
    B2F_REQUIRE(op, "b2f_operator_set_interior: NULL handle");
@@ -1068,6 +1083,15 @@ int b2f_operator_mult_unfused(b2f_operator *op, const double *x_l, double *y_l)
    B2F_REQUIRE(op && x_l && y_l, "b2f_operator_mult_unfused: NULL argument");
    B2F_REQUIRE(!op->halo, "b2f_operator_mult_unfused: local operators only");
    return local_mult_unfused(op, x_l, y_l);
+}
+
+// y[ess] after the constrained product, by Operator::DiagonalPolicy (operator.cpp:631-658)
+static int constrained_entries(b2f_operator *op, double *y, const double *x)
+{
+   if (op->diag_policy == 1) { return copy_entries(op->ctx, y, x, op->ess, op->n_ess); }
+   if (op->diag_policy == 0) { return set_entries(op->ctx, y, op->ess, op->n_ess, 0.0); }
+   B2F_REQUIRE(op->n_ess == 0, "ConstrainedOperator::Mult: DIAG_KEEP needs the action of the operator diagonal");
+   return B2F_OK;
 }
 
 // Operator::AbsMult (linalg/operator.hpp:96) of the PA operator: RAPOperator::AbsMult
@@ -1104,7 +1128,7 @@ int b2f_operator_abs_mult_constrained(b2f_operator *op, const double *x, double 
    B2F_CUDA(cudaMemcpyAsync(op->z, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
    B2F_TRY(set_entries(ctx, op->z, op->ess, op->n_ess, 0.0));
    B2F_TRY(rap_abs_mult(op, op->z, y));
-   return copy_entries(ctx, y, x, op->ess, op->n_ess);
+   return constrained_entries(op, y, x);
 }
 
 // dot_acc != nullptr: additionally leave (x, y) = sum_e z_e.(A_e z_e) + sum_ess x_i^2 in dot_acc
@@ -1132,7 +1156,7 @@ static int mult_constrained(b2f_operator *op, const double *x, double *y, bool l
       // skipped by the scatter
       B2F_TRY(rap_mult(op, x, y, true, lcap));
    }
-   return copy_entries(ctx, y, x, op->ess, op->n_ess);
+   return constrained_entries(op, y, x);
 }
 
 int b2f_operator_mult_constrained(b2f_operator *op, const double *x, double *y)

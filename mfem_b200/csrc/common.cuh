@@ -152,6 +152,7 @@ struct b2f_operator
    double *xl = nullptr, *yl = nullptr; // L-vectors when a halo is attached
    std::vector<int> ess_l_h;            // essential LOCAL dofs as given at creation
    int signed_map = 0;                  // gather_map has negative (sign-flipped) entries
+   int diag_policy = 1;                 // Operator::DiagonalPolicy: 0 = DIAG_ZERO, 1 = DIAG_ONE, 2 = DIAG_KEEP
    double *pcg_vec[4] = {nullptr, nullptr, nullptr, nullptr}; // r, d, z, q
    double *pcg_hist = nullptr;
    int pcg_hist_cap = 0;

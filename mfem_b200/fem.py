@@ -645,10 +645,14 @@ class BilinearForm:
 
 
 class ConstrainedOperator:
-    """linalg/operator.cpp:526-660 (DIAG_ONE)."""
+    """linalg/operator.cpp:526-660; diag_policy: "DIAG_ONE" (default), "DIAG_ZERO", "DIAG_KEEP"."""
 
-    def __init__(self, form):
+    def __init__(self, form, diag_policy="DIAG_ONE"):
         self.form = form
+        call("b2f_operator_set_diag_policy", form.op, {"DIAG_ZERO": 0, "DIAG_ONE": 1, "DIAG_KEEP": 2}[diag_policy])
+
+    def AssembleDiagonal(self, diag):
+        call("b2f_operator_assemble_diagonal_constrained", self.form.op, _dp(diag))
 
     def Height(self):
         return self.form.Height()

@@ -590,6 +590,15 @@ static int do_dump_mesh(const Args &A, const char *out)
       yE = 0.0;
       P.bfi->AddAbsMultPA(xE, yE);
       D.dbls("yE_abs", yE); // input: R applied to x_signed (bit-exact gather, not dumped)
+      // the other diagonal policy of the ConstrainedOperator, and its AssembleDiagonal
+      ConstrainedOperator Cz(P.a, ess, false, Operator::DIAG_ZERO);
+      Cz.Mult(x, ya);
+      D.dbls("y_constrained_diag_zero", ya);
+      Cz.AssembleDiagonal(ya);
+      D.dbls("diag_constrained_diag_zero", ya);
+      ConstrainedOperator C1(P.a, ess, false, Operator::DIAG_ONE);
+      C1.AssembleDiagonal(ya);
+      D.dbls("diag_constrained_diag_one", ya);
    }
    // ex1.cpp:266-267: PCG(*A, M, B, X, 1, 400, 1e-12, 0.0) -- rel_tol^2 = 1e-12
    const double rtol = A.getd("rtol", 1e-6);

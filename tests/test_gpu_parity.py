@@ -739,6 +739,16 @@ def test_reference_mesh_files(dev, name):
     ye = dev.zeros(R.Height())
     it.AddAbsMultPA(xe, ye)
     assert relerr(host(ye), g["yE_abs"]) < TOL
+    # Operator::DiagonalPolicy of the ConstrainedOperator (operator.cpp:526-660)
+    A.AssembleDiagonal(d)
+    assert relerr(host(d), g["diag_constrained_diag_one"]) < TOL
+    Az = m.ConstrainedOperator(a, "DIAG_ZERO")
+    Az.Mult(x, y)
+    assert relerr(host(y), g["y_constrained_diag_zero"]) < TOL
+    Az.AssembleDiagonal(d)
+    assert relerr(host(d), g["diag_constrained_diag_zero"]) < TOL
+    with pytest.raises(RuntimeError, match="DIAG_KEEP"):
+        m.ConstrainedOperator(a, "DIAG_KEEP").Mult(x, y)
     a.close(); it.close(); R.close()
 
 

@@ -33,6 +33,15 @@ def test_operator_diag_and_pcg_on_reference_meshes(name):
     assert relerr(op.mult_constrained(g["x"]), g["y_constrained"]) < TOL
     B = op.eliminate_rhs(np.zeros(len(g["b"])), g["b"])
     assert relerr(B, g["B_rhs"]) < TOL
+    # the ConstrainedOperator's other diagonal policy and AssembleDiagonal (operator.cpp:526-660)
+    ess = g["ess_tdof_list"]
+    yz = op.mult_constrained(g["x"])
+    yz[ess] = 0.0
+    assert relerr(yz, g["y_constrained_diag_zero"]) < TOL
+    for val, key in ((1.0, "diag_constrained_diag_one"), (0.0, "diag_constrained_diag_zero")):
+        dc = op.diag()
+        dc[ess] = val
+        assert relerr(dc, g[key]) < TOL
     dinv = op.jacobi(g["diag"], 1.0)
     X, its, conv, fn, hist = op.pcg(B, dinv, rel_tol=float(g["pcg_rtol"][0]), max_iter=400)
     assert abs(its - int(g["pcg_iters"][0])) <= 1 and conv == bool(g["pcg_converged"][0])
