@@ -149,11 +149,24 @@ struct EOStages
       }
       else { eo_fwd<D, Q, false>(bs.Bs, bs.Ba, s, a, vb); }
       if (DIFF) { eo_fwd<D, Q, true>(bs.Gs, bs.Ga, s, a, vg); }
-#pragma unroll
-      for (int qy = 0; qy < Q; qy++)
+      if constexpr (C::VEC1 && C::TMA_OK)
       {
-         A0[qy] = vb[qy];
-         if (DIFF) { A0[D * C::SA + qy] = vg[qy]; }
+         double2 *A2 = reinterpret_cast<double2 *>(A0);
+#pragma unroll
+         for (int j = 0; j < Q / 2; j++)
+         {
+            A2[j] = make_double2(vb[2 * j], vb[2 * j + 1]);
+            if (DIFF) { A2[(D * C::SA) / 2 + j] = make_double2(vg[2 * j], vg[2 * j + 1]); }
+         }
+      }
+      else
+      {
+#pragma unroll
+         for (int qy = 0; qy < Q; qy++)
+         {
+            A0[qy] = vb[qy];
+            if (DIFF) { A0[D * C::SA + qy] = vg[qy]; }
+         }
       }
    }
 
@@ -408,8 +421,18 @@ struct EOStages
    {
       double f[Q], s[QH], a[QH], es[DH], ea[DH];
       zero(es); zero(ea);
+      constexpr bool V1 = C::VEC1 && C::TMA_OK;
+      if constexpr (V1)
+      {
+         const double2 *F2 = reinterpret_cast<const double2 *>(F0);
 #pragma unroll
-      for (int qy = 0; qy < Q; qy++) { f[qy] = F0[qy]; }
+         for (int j = 0; j < Q / 2; j++) { const double2 v2 = F2[j]; f[2 * j] = v2.x; f[2 * j + 1] = v2.y; }
+      }
+      else
+      {
+#pragma unroll
+         for (int qy = 0; qy < Q; qy++) { f[qy] = F0[qy]; }
+      }
       if (COLLOC)
       {
 #pragma unroll
@@ -422,8 +445,17 @@ struct EOStages
       }
       if (DIFF)
       {
+         if constexpr (V1)
+         {
+            const double2 *F2 = reinterpret_cast<const double2 *>(F0 + D * C::SA);
 #pragma unroll
-         for (int qy = 0; qy < Q; qy++) { f[qy] = F0[D * C::SA + qy]; }
+            for (int j = 0; j < Q / 2; j++) { const double2 v2 = F2[j]; f[2 * j] = v2.x; f[2 * j + 1] = v2.y; }
+         }
+         else
+         {
+#pragma unroll
+            for (int qy = 0; qy < Q; qy++) { f[qy] = F0[D * C::SA + qy]; }
+         }
          eo_split<Q, true>(f, s, a);
          eo_bwd_acc<D, Q, true>(bs.Gs, bs.Ga, s, a, es, ea);
       }

@@ -67,6 +67,8 @@ struct PipeCfg
    static constexpr PipeLayout L = pipe_layout(KIND, D, Q, NEB);
    static constexpr int SA = pad16(D * YQ, L.ra); // A,F[f][dz][dx][yq]
    static constexpr int SC = pad16(Q * YQ, YQ);   // C,E[f][dx][qz][yq]
+   // stage 1 / 5: a line's Q values as Q/2 128-bit words (line starts are even: Q, YQ, SA even)
+   static constexpr bool VEC1 = (Q % 2 == 0) && (SA % 2 == 0);
    static constexpr int R1 = NA * D * SA;
    static constexpr int R2 = NC * D * SC;
    // quadrature data: per-element slabs, padded so that 128-bit row reads by consecutive
