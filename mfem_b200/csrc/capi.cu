@@ -518,7 +518,6 @@ int b2f_pa_add_mult_vec(b2f_pa *pa, int vdim, const double *x_e, double *y_e)
 {
    B2F_REQUIRE(pa && vdim >= 1 && (pa->ne == 0 || (x_e && y_e)), "b2f_pa_add_mult_vec: bad argument");
    if (vdim == 1) { return pa_apply(pa, x_e, y_e, nullptr); }
-   B2F_REQUIRE(pa_has_fused_dot(pa), "b2f_pa_add_mult_vec: vector E-vectors need the 3D even-odd kernel");
    pa->vd = vdim;
    const int rc = pa_apply(pa, x_e, y_e, nullptr);
    pa->vd = 1;
@@ -750,15 +749,6 @@ int b2f_operator_create(b2f_ctx *ctx, b2f_restriction *r, b2f_pa *const *integra
    {
       B2F_REQUIRE(ess_dofs_h[i] >= 0 && (int64_t)ess_dofs_h[i] < (int64_t)r->ndofs * r->vdim,
                   "b2f_operator_create: essential dof %d out of range", ess_dofs_h[i]);
-   }
-   if (r->vdim > 1)
-   {
-      for (int i = 0; i < n_integrators; i++)
-      {
-         B2F_REQUIRE(pa_has_fused_dot(integrators[i]),
-                     "b2f_operator_create: vector spaces need the 3D even-odd kernel (symmetric basis, "
-                     "D1D = 2..9, Q1D = D1D..D1D+2)");
-      }
    }
    b2f_operator *op = new b2f_operator;
    op->ctx = ctx;

@@ -21,10 +21,12 @@ static bool in_tables(const b2f_pa *pa)
 int pa_apply(b2f_pa *pa, const double *x, double *y, const int *idx, double *dot_acc)
 {
    if (pa->ne == 0) { return B2F_OK; }
-   if (!pa->symmetric || !in_tables(pa))
+   // full-matrix coefficients, sizes outside the tables, and vector spaces where the 3D even-odd
+   // kernel does not apply (2D, a basis without the symmetry): run-time-sized kernel
+   const bool vec_generic = pa->vd > 1 && !pa_apply_has_fused_dot(pa);
+   if (!pa->symmetric || !in_tables(pa) || vec_generic)
    {
-      // full-matrix coefficients and sizes outside the tables: run-time-sized kernel
-      if (dot_acc || pa->vd > 1 || pa->rb != 0 || pa->re >= 0)
+      if (dot_acc || pa->rb != 0 || pa->re >= 0)
       {
          set_error("pa_apply: this form needs the even-odd kernel (symmetric coefficient, D1D = 2..9, "
                    "Q1D = D1D..D1D+2)");

@@ -62,8 +62,11 @@ __global__ void __launch_bounds__(128)
 pa_apply_generic_3d_kernel(int kind, int D, int Q, int ncomp, const double *__restrict__ Bg,
                            const double *__restrict__ Gg, const double *__restrict__ qdata,
                            const double *__restrict__ x, double *__restrict__ y,
-                           const int *__restrict__ idx)
+                           const int *__restrict__ idx, int vd, long long vxs, long long vxo, long long vics)
 {
+   // vector spaces (vdim > 1): blockIdx.y = component; component c of L-dof g is x[g*vxs + c*vxo],
+   // its gather index starts at idx + c*vics, its E-vector block is (e*vd + c)
+   const int comp = blockIdx.y;
    extern __shared__ double sm[];
    const bool diff = kind == B2F_KIND_DIFFUSION;
    const int D2 = D * D, D3 = D2 * D, Q2 = Q * Q, Q3 = Q2 * Q;
@@ -76,10 +79,12 @@ pa_apply_generic_3d_kernel(int kind, int D, int Q, int ncomp, const double *__re
    const int64_t e = blockIdx.x;
    const int t = threadIdx.x, nt = blockDim.x;
    for (int i = t; i < Q * D; i += nt) { sB[i] = Bg[i]; sG[i] = Gg ? Gg[i] : 0.0; }
+   const int *ix = idx ? idx + comp * vics + e * D3 : nullptr;
+   const int64_t eoff = (e * vd + comp) * (int64_t)D3;
    for (int i = t; i < D3; i += nt)
    {
-      if (idx) { const int g = idx[e * D3 + i]; X[i] = g >= 0 ? x[g] : 0.0; }
-      else { X[i] = x[e * D3 + i]; }
+      if (idx) { const int g = ix[i]; X[i] = g >= 0 ? x[g * vxs + comp * vxo] : 0.0; }
+      else { X[i] = x[eoff + i]; }
    }
    __syncthreads();
    // x
@@ -196,8 +201,8 @@ pa_apply_generic_3d_kernel(int kind, int D, int Q, int ncomp, const double *__re
          }
          else { v = fma(sB[qx + Q * dx], A[a], v); }
       }
-      if (idx) { const int g = idx[e * D3 + i]; if (g >= 0) { atomicAdd(y + g, v); } }
-      else { y[e * D3 + i] += v; }
+      if (idx) { const int g = ix[i]; if (g >= 0) { atomicAdd(y + g * vxs + comp * vxo, v); } }
+      else { y[eoff + i] += v; }
    }
 }
 
@@ -206,8 +211,11 @@ __global__ void __launch_bounds__(128)
 pa_apply_generic_2d_kernel(int kind, int D, int Q, int ncomp, const double *__restrict__ Bg,
                            const double *__restrict__ Gg, const double *__restrict__ qdata,
                            const double *__restrict__ x, double *__restrict__ y,
-                           const int *__restrict__ idx)
+                           const int *__restrict__ idx, int vd, long long vxs, long long vxo, long long vics)
 {
+   // vector spaces (vdim > 1): blockIdx.y = component; component c of L-dof g is x[g*vxs + c*vxo],
+   // its gather index starts at idx + c*vics, its E-vector block is (e*vd + c)
+   const int comp = blockIdx.y;
    extern __shared__ double sm[];
    const bool diff = kind == B2F_KIND_DIFFUSION;
    const int D2 = D * D, Q2 = Q * Q;
@@ -218,10 +226,12 @@ pa_apply_generic_2d_kernel(int kind, int D, int Q, int ncomp, const double *__re
    const int64_t e = blockIdx.x;
    const int t = threadIdx.x, nt = blockDim.x;
    for (int i = t; i < Q * D; i += nt) { sB[i] = Bg[i]; sG[i] = Gg ? Gg[i] : 0.0; }
+   const int *ix = idx ? idx + comp * vics + e * D2 : nullptr;
+   const int64_t eoff = (e * vd + comp) * (int64_t)D2;
    for (int i = t; i < D2; i += nt)
    {
-      if (idx) { const int g = idx[e * D2 + i]; X[i] = g >= 0 ? x[g] : 0.0; }
-      else { X[i] = x[e * D2 + i]; }
+      if (idx) { const int g = ix[i]; X[i] = g >= 0 ? x[g * vxs + comp * vxo] : 0.0; }
+      else { X[i] = x[eoff + i]; }
    }
    __syncthreads();
    for (int o = t; o < D * Q; o += nt)
@@ -286,8 +296,8 @@ pa_apply_generic_2d_kernel(int kind, int D, int Q, int ncomp, const double *__re
          }
          else { v = fma(sB[qx + Q * dx], A[a], v); }
       }
-      if (idx) { const int g = idx[e * D2 + i]; if (g >= 0) { atomicAdd(y + g, v); } }
-      else { y[e * D2 + i] += v; }
+      if (idx) { const int g = ix[i]; if (g >= 0) { atomicAdd(y + g * vxs + comp * vxo, v); } }
+      else { y[eoff + i] += v; }
    }
 }
 
@@ -319,15 +329,15 @@ int pa_apply_generic(b2f_pa *pa, const double *x, double *y, const int *idx)
    {
       B2F_CUDA(cudaFuncSetAttribute(pa_apply_generic_3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
-      pa_apply_generic_3d_kernel<<<(unsigned)pa->ne, 128, smem, ctx->stream>>>(pa->kind, D, Q, pa->ncomp, pa->d_B,
-                                                                               G, pa->data, x, y, idx);
+      pa_apply_generic_3d_kernel<<<dim3((unsigned)pa->ne, (unsigned)pa->vd), 128, smem, ctx->stream>>>(
+         pa->kind, D, Q, pa->ncomp, pa->d_B, G, pa->data, x, y, idx, pa->vd, pa->vxs, pa->vxo, pa->vics);
    }
    else
    {
       B2F_CUDA(cudaFuncSetAttribute(pa_apply_generic_2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
-      pa_apply_generic_2d_kernel<<<(unsigned)pa->ne, 128, smem, ctx->stream>>>(pa->kind, D, Q, pa->ncomp, pa->d_B,
-                                                                               G, pa->data, x, y, idx);
+      pa_apply_generic_2d_kernel<<<dim3((unsigned)pa->ne, (unsigned)pa->vd), 128, smem, ctx->stream>>>(
+         pa->kind, D, Q, pa->ncomp, pa->d_B, G, pa->data, x, y, idx, pa->vd, pa->vxs, pa->vxo, pa->vics);
    }
    B2F_LAUNCH_CHECK(ctx);
    return B2F_OK;

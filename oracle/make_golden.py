@@ -63,6 +63,9 @@ CASES = {
     "vec_mass3d_p4_n2_byvdim": dict(dim=3, n=2, p=4, kind="mass", vdim=3, byvdim=1),
     "vec_bp6_3d_p3_n3_byvdim": dict(dim=3, n=3, p=3, kind="diffusion", quad="gll", vdim=3, byvdim=1),
     "vec_diff3d_p5_n2_curved": dict(dim=3, n=2, p=5, kind="diffusion", vdim=3, byvdim=1, curved=1),
+    # 2D vector spaces (run-time-sized kernels on the CUDA side)
+    "vec_diff2d_p3_n3_byvdim": dict(dim=2, n=3, p=3, kind="diffusion", vdim=2, byvdim=1),
+    "vec_mass2d_p4_n2_bynodes": dict(dim=2, n=2, p=4, kind="mass", vdim=2, byvdim=0, curved=1),
     # non-symmetric matrix coefficient (dim*dim quadrature-data components)
     "nonsym_diff3d_p2_n2": dict(dim=3, n=2, p=2, kind="diffusion", nonsym=1),
     "nonsym_diff3d_p4_n2_curved": dict(dim=3, n=2, p=4, kind="diffusion", nonsym=1, curved=1),
