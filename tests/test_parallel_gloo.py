@@ -267,3 +267,80 @@ def test_vdof_halo_tables_for_vector_spaces(grid, n, p, vdim):
     for f in spaces:
         holders[vd(f.halo_tables["ldof_lattice"])] += 1
     assert np.array_equal(counts, holders)
+
+
+def _vector_worker(rank, world, port, grid, n, p, vdim, q):
+    """2-rank vector space over gloo: the vdof halo tables drive the exchange; the local block
+    operator is the oracle's VectorOperator (byVDIM)."""
+    try:
+        import torch
+        import torch.distributed as dist
+        import mfem_b200 as m
+        from oracle import oracle as orc
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        mesh = m.Mesh(3, n[0], n[1], n[2], True, part=grid, rank=rank)
+        fes = m.FiniteElementSpace(mesh, m.H1_FECollection(p, 3))
+
+        class _V:  # what GlooHalo reads from a space: vdof-level tables and sizes
+            pass
+        v = _V()
+        v.halo_tables = m.Halo.expand_vdim(fes.halo_tables, vdim)
+        v.ndofs, v.ntdofs = fes.ndofs * vdim, fes.ntdofs * vdim
+        halo = GlooHalo(dist, torch, rank, v)
+        lat = fes.halo_tables["ldof_lattice"]
+        nlat = (p * n[0] + 1) * (p * n[1] + 1) * (p * n[2] + 1)
+
+        def vd(ids):
+            return (np.asarray(ids, np.int64)[:, None] * vdim + np.arange(vdim)[None, :]).ravel()
+        xg = orc.randomize(nlat * vdim, 1)
+        x_t = xg[vd(lat[fes.halo_tables["ltdof_ldof"]])]
+        ess_v = vd(fes.bdr_dofs)
+        op = orc.VectorOperator(_local_operator(fes, p, "diffusion", None), vdim, True, ess_v)
+        x_l = halo.mult(x_t)
+        assert np.array_equal(x_l, xg[vd(lat)])
+        y_t = halo.mult_transpose(op.mult(x_l))
+        d_t = halo.mult_transpose(op.diag())
+        q.put((rank, vd(lat[fes.halo_tables["ltdof_ldof"]]), y_t, d_t, None))
+        dist.destroy_process_group()
+    except Exception:
+        import traceback
+        q.put((rank, None, None, None, traceback.format_exc()))
+
+
+def test_vector_space_rap_operator_matches_serial():
+    import torch.multiprocessing as mp
+    import mfem_b200 as m
+    from oracle import oracle as orc
+    grid, n, p, vdim = (2, 1, 1), (4, 2, 2), 2, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_vector_worker, args=(r, 2, port, grid, n, p, vdim, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    out = [q.get(timeout=240) for _ in range(2)]
+    for pr in procs:
+        pr.join(timeout=60)
+    for o in out:
+        assert o[4] is None, o[4]
+    smesh = m.Mesh(3, n[0], n[1], n[2], True, part=(1, 1, 1), rank=0)
+    sfes = m.FiniteElementSpace(smesh, m.H1_FECollection(p, 3))
+    slat = sfes.halo_tables["ldof_lattice"]
+    nlat = len(slat)
+
+    def vd(ids):
+        return (np.asarray(ids, np.int64)[:, None] * vdim + np.arange(vdim)[None, :]).ravel()
+    sop = orc.VectorOperator(_local_operator(sfes, p, "diffusion", None), vdim, True, vd(sfes.bdr_dofs))
+    xg = orc.randomize(nlat * vdim, 1)
+    y_serial, d_serial = np.empty(nlat * vdim), np.empty(nlat * vdim)
+    y_serial[vd(slat)] = sop.mult(xg[vd(slat)])
+    d_serial[vd(slat)] = sop.diag()
+    y_par, d_par = np.full(nlat * vdim, np.nan), np.full(nlat * vdim, np.nan)
+    for rank, ids, y_t, d_t, _ in out:
+        y_par[ids] = y_t
+        d_par[ids] = d_t
+    assert not np.isnan(y_par).any()
+    assert np.linalg.norm(y_par - y_serial) <= 1e-12 * np.linalg.norm(y_serial)
+    assert np.linalg.norm(d_par - d_serial) <= 1e-12 * np.linalg.norm(d_serial)
