@@ -350,7 +350,10 @@ def main():
             pass
         peak = peaks.get("hbm_gbs", 6650.0)
         ab = alg_bytes_per_apply(w, fes.ne, fes.GetVSize())
-        k_ms = kt[0] / max(kt[1], 1)
+        # one operator application per CG iteration + the initial one; with a halo the interior /
+        # boundary split makes it several launches, whose times add up to one application
+        n_applies = a.steps * (a.iters + 1)
+        k_ms = kt[0] / max(n_applies, 1)
         achieved = ab / (k_ms * 1e-3) / 1e9
         # DRAM traffic of the operator kernel from the committed ncu capture of this workload
         traffic = None
@@ -383,6 +386,7 @@ def main():
                          "frac": achieved / peak, "traffic": traffic,
                          "kernel": "pa_apply_3d_eo_kernel (fused gather + even-odd G^T D G + scatter)",
                          "kernel_ms": k_ms, "kernel_launches": kt[1],
+                         "launches_per_application": kt[1] / max(n_applies, 1),
                          "kernel_share_of_step": kt[0] / ms,
                          "algorithmic_bytes_per_launch": ab,
                          "operator_gdofs": fes.GetVSize() / (k_ms * 1e-3) / 1e9,
