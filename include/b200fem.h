@@ -208,7 +208,8 @@ int b2f_domain_lf_assemble(b2f_ctx *ctx, int dim, int d1d, int q1d, int vdim, in
 /* ---- PABilinearFormExtension + ConstrainedOperator ---------------------------------- */
 /* PABilinearFormExtension (fem/bilinearform_ext.cpp:256-564) over one restriction and
  * n integrators.  A restriction with vdim > 1 (byNODES or byVDIM) makes it the vector operator
- * of Vector{Mass,Diffusion}Integrator on vdof vectors (single rank); ess_ldofs_h (may be NULL / 0) is the essential dof list that
+ * of Vector{Mass,Diffusion}Integrator on vdof vectors (rank-parallel with byVDIM, see
+ * b2f_halo_create); ess_ldofs_h (may be NULL / 0) is the essential dof list that
  * FormLinearSystem wraps around it as a ConstrainedOperator (linalg/operator.cpp:526). */
 int b2f_operator_create(b2f_ctx *ctx, b2f_restriction *r, b2f_pa *const *integrators,
                         int n_integrators, const int *ess_dofs_h, int n_ess,
