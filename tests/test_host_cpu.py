@@ -25,6 +25,40 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert L.b2f_version() == 100
 
 
+def test_ctypes_prototypes_match_the_header_signatures():
+    """Every prototype in mfem_b200/capi.py has the argument count and the integer / pointer /
+    floating kinds of its declaration in include/b200fem.h (a drifted ctypes signature would
+    only show up as a crash on the GPU box)."""
+    from mfem_b200 import capi
+    header = open(os.path.join(ROOT, "include", "b200fem.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    header = re.sub(r"//[^\n]*", "", header)
+    decls = re.findall(r"\b(?:int|void|int64_t|const char \*)\s*\*?\s*(b2f_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    seen = {}
+    for name, args in decls:
+        args = " ".join(args.split())
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        seen[name] = params
+    assert len(seen) > 50
+    for name, (res, argtypes) in capi.PROTOTYPES.items():
+        assert name in seen, f"{name} has a ctypes prototype but no declaration"
+        params = seen[name]
+        assert len(params) == len(argtypes), f"{name}: header has {len(params)} parameters, ctypes {len(argtypes)}"
+        for k, (decl, ct) in enumerate(zip(params, argtypes)):
+            is_ptr = "*" in decl
+            if is_ptr:
+                assert ct in (capi.vp, C.c_char_p) or hasattr(ct, "contents") or issubclass(ct, C._Pointer), \
+                    f"{name} arg {k} ({decl}): pointer in the header, {ct} in ctypes"
+            elif re.match(r"(const )?double\b", decl):
+                assert ct is C.c_double, f"{name} arg {k} ({decl})"
+            elif re.match(r"(const )?int64_t\b", decl):
+                assert ct is C.c_int64, f"{name} arg {k} ({decl})"
+            elif re.match(r"(const )?size_t\b", decl):
+                assert ct is C.c_size_t, f"{name} arg {k} ({decl})"
+            elif re.match(r"(const )?int\b", decl):
+                assert ct is C.c_int, f"{name} arg {k} ({decl})"
+
+
 def test_no_device_is_a_loud_error_not_a_fallback():
     """Without a CUDA device the context cannot be created: there is no CPU path."""
     import torch
