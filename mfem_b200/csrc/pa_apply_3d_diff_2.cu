@@ -1,6 +1,7 @@
 // 3D diffusion PA kernels, D1D = 2..5 (split for parallel compilation)
 #include <cstdlib>
 #include "pa_dispatch.cuh"
+#include "pa_apply_eo_lean.cuh"
 namespace b2f
 {
 // experiment hook: B2F_VARIANT selects a kernel variant for (D1D,Q1D) = (5,6)
@@ -23,6 +24,8 @@ int pa_apply_3d_diffusion_2(b2f_pa *pa, const double *x, double *y, const int *i
          case 25: return launch_3d_pipe<K, 5, 6, 4, 3>(pa, x, y, idx);          // persistent pipelined, plain contraction
          case 40: return launch_3d_eo<K, 5, 6, 3, 4, 1, true>(pa, x, y, idx);   // persistent pipelined, even-odd
          case 42: return launch_3d_eo<K, 5, 6, 4, 3, 1, true>(pa, x, y, idx);
+         // short-prologue form of the default kernel (pa_apply_eo_lean.cuh), not yet validated
+         case 60: if (!dot_acc && pa->vd == 1) { return launch_3d_eo_lean<K, 5, 6, 3, 4>(pa, x, y, idx); } break;
          default: break;
       }
    }
