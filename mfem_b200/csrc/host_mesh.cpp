@@ -491,6 +491,17 @@ extern "C" int b2f_cartesian_h1_space_h(int dim, int nx, int ny, int nz, int p, 
       }
    }
    if (!elem_dof_h && !bdr_dofs_h && !nbdr) { return B2F_OK; }
+   // The caller asks in steps (sizes; element table and number of boundary dofs; boundary dofs):
+   // the boundary list of the last numbering is kept so that the last step does not redo it.
+   struct BdrCache { bool valid = false; int key[6]; std::vector<int> bdr; };
+   static thread_local BdrCache cache;
+   const int key[6] = {dim, nx, ny, nz, p, sfc_ordering};
+   if (!elem_dof_h && cache.valid && std::equal(key, key + 6, cache.key))
+   {
+      if (nbdr) { *nbdr = (int)cache.bdr.size(); }
+      if (bdr_dofs_h) { std::copy(cache.bdr.begin(), cache.bdr.end(), bdr_dofs_h); }
+      return B2F_OK;
+   }
    H1Space S;
    const int vstride[3] = {1, nx + 1, (nx + 1) * (ny + 1)};
    h1_number(dim, p, nverts, ev, S, vstride);
@@ -502,5 +513,8 @@ extern "C" int b2f_cartesian_h1_space_h(int dim, int nx, int ny, int nz, int p, 
    if (elem_dof_h) { std::copy(S.elem_dof.begin(), S.elem_dof.end(), elem_dof_h); }
    if (nbdr) { *nbdr = (int)S.bdr_dofs.size(); }
    if (bdr_dofs_h) { std::copy(S.bdr_dofs.begin(), S.bdr_dofs.end(), bdr_dofs_h); }
+   std::copy(key, key + 6, cache.key);
+   cache.bdr.swap(S.bdr_dofs);
+   cache.valid = true;
    return B2F_OK;
 }
