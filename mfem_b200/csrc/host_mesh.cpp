@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "../../include/b200fem.h"
+#include "host_parallel.h"
 
 namespace b2f
 {
@@ -346,7 +347,9 @@ void h1_number(int dim, int p, int nverts, const std::vector<int> &elem_vert, H1
    S.ne = ne;
    S.ndofs = nvdofs + nedofs + nfdofs + ne * nb;
    S.elem_dof.resize((size_t)ne * dof);
-   for (int e = 0; e < ne; e++)
+   parallel_for(ne, [&](int64_t e_begin, int64_t e_end)
+   {
+   for (int e = (int)e_begin; e < (int)e_end; e++)
    {
       const int *v = &elem_vert[(size_t)e * nv];
       int *out = &S.elem_dof[(size_t)e * dof];
@@ -386,6 +389,7 @@ void h1_number(int dim, int p, int nverts, const std::vector<int> &elem_vert, H1
       const int base = nvdofs + nedofs + nfdofs + e * nb;
       for (int i = 0; i < nb; i++) { out[o++] = base + i; }
    }
+   });
    // --- boundary dofs (all boundary attributes essential, as ex1.cpp:165-183 / bench_ceed)
    std::vector<char> mark(S.ndofs, 0);
    for (int e = 0; e < ne; e++)

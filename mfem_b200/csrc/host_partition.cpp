@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "../../include/b200fem.h"
+#include "host_parallel.h"
 
 namespace b2f
 {
@@ -53,25 +54,6 @@ struct Tables
 };
 thread_local Tables g_tables;
 
-// plain std::thread fan-out for the few loops over all E-dofs / L-dofs (hundreds of millions of
-// independent iterations at benchmark sizes); no OpenMP runtime is pulled into the host process
-template <typename F>
-void parallel_for(int64_t n, F &&body)
-{
-   unsigned nt = std::thread::hardware_concurrency();
-   if (const char *s = getenv("B2F_HOST_THREADS")) { nt = (unsigned)atoi(s); }
-   if (nt > 16) { nt = 16; }
-   if (nt < 2 || n < (1 << 16)) { body((int64_t)0, n); return; }
-   std::vector<std::thread> th;
-   const int64_t chunk = (n + nt - 1) / nt;
-   for (unsigned k = 0; k < nt; k++)
-   {
-      const int64_t b = (int64_t)k * chunk, e = std::min<int64_t>(n, b + chunk);
-      if (b >= e) { break; }
-      th.emplace_back([&body, b, e]() { body(b, e); });
-   }
-   for (auto &t : th) { t.join(); }
-}
 } // namespace
 
 extern "C" int b2f_cartesian_partition_h(int dim, int nx, int ny, int nz, int p, int sfc_ordering,
@@ -144,7 +126,7 @@ extern "C" int b2f_cartesian_partition_h(int dim, int nx, int ny, int nz, int p,
    const int64_t L[3] = {(int64_t)p * nx + 1, (int64_t)p * ny + 1, (int64_t)p * nz + 1};
    std::vector<int64_t> lat(nl, -1);
    // (a dof shared by several elements receives the same value from each of them)
-   parallel_for(ne, [&](int64_t eb, int64_t ee)
+   b2f::parallel_for(ne, [&](int64_t eb, int64_t ee)
    {
    for (int e = (int)eb; e < (int)ee; e++)
    {
@@ -202,7 +184,7 @@ extern "C" int b2f_cartesian_partition_h(int dim, int nx, int ny, int nz, int p,
       for (int a = 0; a < dim; a++) { on_bdr = on_bdr || g[a] == 0 || g[a] == L[a] - 1; }
       return own;
    };
-   parallel_for(nl, [&](int64_t lb, int64_t le)
+   b2f::parallel_for(nl, [&](int64_t lb, int64_t le)
    {
       int sharers[27], ns;
       bool on_bdr;
@@ -239,7 +221,7 @@ extern "C" int b2f_cartesian_partition_h(int dim, int nx, int ny, int nz, int p,
       nown = 0;
       for (int l = 0; l < nl; l++) { perm[l] = owner[l] == rank ? nown++ : next++; }
       std::vector<char> is_bdr(ne, 0);
-      parallel_for(ne, [&](int64_t eb, int64_t ee)
+      b2f::parallel_for(ne, [&](int64_t eb, int64_t ee)
       {
          for (int64_t e = eb; e < ee; e++)
          {
@@ -254,7 +236,7 @@ extern "C" int b2f_cartesian_partition_h(int dim, int nx, int ny, int nz, int p,
       }
       std::vector<int> ed2(ed.size());
       std::vector<double> ev2(ev.size());
-      parallel_for(ne, [&](int64_t eb, int64_t ee)
+      b2f::parallel_for(ne, [&](int64_t eb, int64_t ee)
       {
          for (int64_t e = eb; e < ee; e++)
          {
@@ -268,7 +250,7 @@ extern "C" int b2f_cartesian_partition_h(int dim, int nx, int ny, int nz, int p,
       ev.swap(ev2);
       std::vector<int64_t> lat2(nl);
       std::vector<int> own2(nl);
-      parallel_for(nl, [&](int64_t lb, int64_t le)
+      b2f::parallel_for(nl, [&](int64_t lb, int64_t le)
       {
          for (int64_t l = lb; l < le; l++) { lat2[perm[l]] = lat[l]; own2[perm[l]] = owner[l]; }
       });
