@@ -84,6 +84,9 @@ int b2f_gauss_lobatto_h(int np, double *pts_h, double *wts_h);
 int b2f_h1_dof_to_quad_h(int p, int nq, const double *qpts_h, double *B_h, double *G_h);
 /* IntegrationRule tensor weights (fem/intrules.cpp:43-96): W_h has nq^dim entries. */
 int b2f_tensor_weights_h(int dim, int nq, const double *w1_h, double *W_h);
+/* Vector::Randomize(seed) (linalg/vector.cpp:955-966): srand(seed), v[i] = rand()/(RAND_MAX+1.0);
+ * seed 0 draws the seed from time(), as the reference does.  Uses the C library's global generator. */
+int b2f_vector_randomize_h(double *v_h, int64_t n, int seed);
 
 /* Structured hex/quad mesh + H1 space with the reference's numbering
  * (Mesh::MakeCartesian2D/3D mesh/mesh.cpp:3841,4388 incl. the space-filling-curve element

@@ -5,7 +5,9 @@
 #include <cmath>
 #include <cstdio>
 #include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/b200fem.h"
@@ -90,6 +92,30 @@ inline void timing_mark(b2f_ctx *ctx)
 }
 } // namespace b2f
 
+namespace b2f
+{
+// opt-in shared memory and residency of a kernel, per (device, kernel): the attribute is per
+// device and several contexts (devices, host threads) may share the process
+template <class K>
+inline int kernel_residency(b2f_ctx *ctx, K kern, int nt, size_t smem, int &resident)
+{
+   static std::map<std::pair<int, const void *>, int> cache;
+   static std::mutex mtx;
+   std::lock_guard<std::mutex> lock(mtx);
+   int &r = cache[{ctx->device, (const void *)kern}];
+   if (r == 0)
+   {
+      B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int occ = 0;
+      B2F_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem));
+      r = (occ < 1 ? 1 : occ) * ctx->sm_count;
+   }
+   resident = r;
+   return B2F_OK;
+}
+
+} // namespace b2f
+
 struct b2f_restriction
 {
    b2f_ctx *ctx;
@@ -118,6 +144,11 @@ struct b2f_pa
    int64_t vxs = 1, vxo = 0, vics = 0;
    // |B|, |G|, |D| twin for AddAbsMultPA (built on first use, owned)
    b2f_pa *abs_twin = nullptr;
+   // TMA tensor map over `data` (swizzled copies of the Q = 8 kernels, pa_apply_eo.cuh) and the
+   // (data, ne) it was built for
+   alignas(64) unsigned char tmap[128];
+   const double *tmap_data = nullptr;
+   int64_t tmap_ne = -1;
 };
 
 // A domain integrator restricted to the elements whose attribute is marked

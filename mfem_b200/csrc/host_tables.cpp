@@ -9,6 +9,8 @@
 // the reference to the last bit (checked in tests/test_host_tables.py against fixtures
 // dumped from the reference).
 #include <cmath>
+#include <cstdlib>
+#include <ctime>
 #include <vector>
 
 #include "../../include/b200fem.h"
@@ -214,6 +216,15 @@ int b2f_tensor_weights_h(int dim, int nq, const double *w1, double *W)
          for (int j = 0; j < nq; j++)
             for (int i = 0; i < nq; i++) { W[(k * nq + j) * nq + i] = w1[i] * w1[j] * w1[k]; }
    }
+   return B2F_OK;
+}
+
+int b2f_vector_randomize_h(double *v, int64_t n, int seed)
+{
+   if (n < 0 || (n > 0 && !v)) { b2f::set_error("b2f_vector_randomize_h: bad arguments"); return B2F_ERR_ARG; }
+   const double scale = 1.0 / ((double)RAND_MAX + 1.0);
+   srand(seed == 0 ? (unsigned)time(nullptr) : (unsigned)seed);
+   for (int64_t i = 0; i < n; i++) { v[i] = std::fabs(rand() * scale); }
    return B2F_OK;
 }
 

@@ -765,20 +765,11 @@ int launch_3d(b2f_pa *pa, const double *x, double *y, const int *idx)
    const int64_t grid = cdiv(pa->ne, NEB);
    auto go = [&](auto kern) -> int
    {
-      // once per instantiation: opt in to the shared memory size and find how many CTAs are
-      // resident on the device -- that is the L2 prefetch distance (the slab a CTA prefetches
+      // once per (device, instantiation): opt in to the shared memory size and find how many CTAs
+      // are resident on the device -- that is the L2 prefetch distance (the slab a CTA prefetches
       // belongs to the CTA that takes over its slot)
-      // (keyed by the kernel's address: instantiations that differ only in bool template
-      // arguments share one function-pointer type, hence one lambda specialisation)
-      static std::map<const void *, int> cache;
-      int &resident = cache[(const void *)kern];
-      if (resident == 0)
-      {
-         B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-         int occ = 0;
-         B2F_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NT, C::SMEM));
-         resident = (occ < 1 ? 1 : occ) * ctx->sm_count;
-      }
+      int resident = 0;
+      if (int rc = kernel_residency(ctx, kern, C::NT, C::SMEM, resident)) { return rc; }
       const char *pfs = getenv("B2F_PF");
       const int pf = pfs ? atoi(pfs) : resident;
       timing_mark(ctx);

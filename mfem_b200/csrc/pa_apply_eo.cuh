@@ -13,12 +13,12 @@
 //    DFMA needs its own basis entry from the constant bank -- halves the constant loads:
 //    per 1D transform D*Q FMAs + D*Q constant loads become D*Q/2 FMAs + D*Q/2 loads + (D+Q)
 //    adds.  Results differ from the plain contraction by rounding only (~1e-16).
-//  * the shared-memory layout of pa_apply_pipe.cuh: stage order y -> z -> x with
+//  * the shared-memory layout of pa_eo_cfg.cuh: stage order y -> z -> x with
 //    yq = qy + Q*e the fastest lane AND address index of stages 2-4 (consecutive lanes touch
 //    consecutive words: no bank conflicts, no transposition), the x-stage overwrites its
 //    own input column in place (no staging registers, one barrier fewer), quadrature-data
 //    rows are read with 128-bit LDS from per-element TMA slabs padded so that lanes of
-//    neighbouring elements hit different bank groups.
+//    neighbouring elements hit different bank groups (Q = 8: swizzled tensor copies instead).
 //
 // Streams: one TMA bulk copy per element (cp.async.bulk + mbarrier complete_tx) at kernel
 // entry; an L2 bulk prefetch of the slab and gather indices of the CTA that will take over
@@ -26,7 +26,9 @@
 // the integrator is set up; otherwise pa_apply.cuh's general kernel runs).
 #pragma once
 #include <map>
-#include "pa_apply_pipe.cuh"
+#include <cuda.h>
+#include <mutex>
+#include "pa_eo_cfg.cuh"
 
 namespace b2f
 {
@@ -267,7 +269,8 @@ struct EOStages
 #pragma unroll
          for (int k = 0; k < C::NQD; k++)
          {
-            if constexpr (C::VEC) { load_row<Q, false>(dq + k * Q3, dv[k]); }
+            if constexpr (C::SWZ) { load_row_swz8(dq + k * Q3, (qy >> 1) & 3, dv[k]); }
+            else if constexpr (C::VEC) { load_row<Q, false>(dq + k * Q3, dv[k]); }
             else
             {
 #pragma unroll
@@ -289,7 +292,8 @@ struct EOStages
       else
       {
          double dv[Q];
-         if constexpr (C::VEC) { load_row<Q, false>(dq, dv); }
+         if constexpr (C::SWZ) { load_row_swz8(dq, (qy >> 1) & 3, dv); }
+         else if constexpr (C::VEC) { load_row<Q, false>(dq, dv); }
          else
          {
 #pragma unroll
@@ -503,16 +507,20 @@ __global__ void __launch_bounds__(PipeCfg<KIND, D, Q, NEB>::NT, MINB)
 pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__restrict__ qdata,
                       const double *__restrict__ x, double *__restrict__ y,
                       const int *__restrict__ idx, const int64_t ne, const int pf,
-                      double *__restrict__ dot_acc, const int64_t e_first, const VecArgs va)
+                      double *__restrict__ dot_acc, const int64_t e_first, const VecArgs va,
+                      const __grid_constant__ TmapArg<PipeCfg<KIND, D, Q, NEB>::SWZ> tmap)
 {
    using C = PipeCfg<KIND, D, Q, NEB>;
    using S = EOStages<KIND, D, Q, NEB, COLLOC, DOT>;
    constexpr int D2 = C::D2, D3 = C::D3, Q3 = C::Q3, YQ = C::YQ;
    extern __shared__ __align__(16) unsigned char smem_raw[];
-   uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-   double *qd = reinterpret_cast<double *>(smem_raw + 16);
+   // swizzled slabs: the quadrature data leads, at a 1024-byte aligned address (the swizzle is a
+   // function of the shared-memory address bits); the mbarrier follows the buffers
+   unsigned char *sbase = C::SWZ ? smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) : smem_raw;
+   double *qd = reinterpret_cast<double *>(C::SWZ ? sbase : sbase + 16);
    double *r1 = qd + C::QD;
    double *r2 = r1 + C::R1;
+   uint64_t *bar = reinterpret_cast<uint64_t *>(C::SWZ ? reinterpret_cast<unsigned char *>(r2 + C::R2) : sbase);
 
    const int t = threadIdx.x;
    const int64_t e0 = e_first + (int64_t)blockIdx.x * NEB; // elements [e_first, ne) of this launch
@@ -556,7 +564,19 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
                mbar_expect_tx(bar, (uint32_t)(nev * C::NQD * Q3) * 8u);
                for (int e = 0; e < nev; e++)
                {
-                  bulk_g2s(qd + e * C::DS, qslab + (int64_t)e * (C::NQD * Q3), (uint32_t)(C::NQD * Q3) * 8u, bar);
+                  if constexpr (C::SWZ)
+                  {
+#pragma unroll
+                     for (int b = 0; b < C::NBOX; b++)
+                     {
+                        tensor_g2s_3d(qd + e * C::DS + b * (C::BOX_ROWS * Q), &tmap, 0, b * C::BOX_ROWS,
+                                      (int)(e0 + e), bar);
+                     }
+                  }
+                  else
+                  {
+                     bulk_g2s(qd + e * C::DS, qslab + (int64_t)e * (C::NQD * Q3), (uint32_t)(C::NQD * Q3) * 8u, bar);
+                  }
                }
             }
          }
@@ -640,151 +660,6 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
    }
 }
 
-// ---- persistent CTAs, every stream prefetched one tile ahead (see pa_apply_pipe.cuh) -----------
-template <int KIND, int D, int Q, int NEB, bool FUSED, bool COLLOC, int MINB>
-__global__ void __launch_bounds__(PipeCfg<KIND, D, Q, NEB>::NT, MINB)
-pa_apply_3d_eop_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__restrict__ qdata,
-                       const double *__restrict__ x, double *__restrict__ y,
-                       const int *__restrict__ idx, const int64_t ne, const int pf)
-{
-   using C = PipeCfg<KIND, D, Q, NEB>;
-   using S = EOStages<KIND, D, Q, NEB, COLLOC>;
-   constexpr int D2 = C::D2, D3 = C::D3, Q3 = C::Q3, YQ = C::YQ;
-   extern __shared__ __align__(16) unsigned char smem_raw[];
-   uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-   double *qd = reinterpret_cast<double *>(smem_raw + 16);
-   double *r1 = qd + C::QD;
-   double *r2 = r1 + C::R1;
-   int *idx_s = reinterpret_cast<int *>(r2 + C::R2);
-   (void)pf;
-
-   const int t = threadIdx.x;
-   const int64_t ntiles = (ne + NEB - 1) / NEB;
-   int e1, dx1, dz1;
-   eo_line_coords<D, NEB, C::L.order>(t, e1, dx1, dz1);
-   const bool has1 = t < C::T1;
-   const int loc1 = dx1 + D2 * dz1;
-   const int a1 = Q * e1 + YQ * dx1 + C::SA * dz1;
-
-   auto issue_qdata = [&](int64_t tile)
-   {
-      const int64_t e0 = tile * NEB;
-      const int nev = (int)((ne - e0) < NEB ? (ne - e0) : NEB);
-      const double *src = qdata + e0 * (int64_t)(C::NQD * Q3);
-      if constexpr (C::TMA_OK)
-      {
-         if (t == 0)
-         {
-            fence_proxy_async(); // the slab was just read through the generic proxy
-            mbar_expect_tx(bar, (uint32_t)(nev * C::NQD * Q3) * 8u);
-            for (int e = 0; e < nev; e++)
-            {
-               bulk_g2s(qd + e * C::DS, src + (int64_t)e * (C::NQD * Q3), (uint32_t)(C::NQD * Q3) * 8u, bar);
-            }
-         }
-      }
-      else
-      {
-         for (int i = t; i < nev * C::NQD * Q3; i += C::NT) { cp_async8(qd + i, src + i); }
-      }
-   };
-   auto issue_idx = [&](int64_t tile)
-   {
-      if constexpr (FUSED)
-      {
-         const int64_t e0 = tile * NEB;
-         const int nev = (int)((ne - e0) < NEB ? (ne - e0) : NEB);
-         const int *src = idx + e0 * D3;
-         for (int i = t; i < nev * D3; i += C::NT) { cp_async4(idx_s + i, src + i); }
-      }
-   };
-   auto load_inputs = [&](int64_t tile, int (&gi)[D], double (&u)[D])
-   {
-      const int64_t e0 = tile * NEB;
-      const int nev = (int)((ne - e0) < NEB ? (ne - e0) : NEB);
-#pragma unroll
-      for (int dy = 0; dy < D; dy++) { gi[dy] = -1; u[dy] = 0.0; }
-      if (has1 && e1 < nev)
-      {
-         if constexpr (FUSED)
-         {
-#pragma unroll
-            for (int dy = 0; dy < D; dy++) { gi[dy] = idx_s[e1 * D3 + loc1 + D * dy]; }
-#pragma unroll
-            for (int dy = 0; dy < D; dy++) { u[dy] = gi[dy] >= 0 ? __ldg(x + gi[dy]) : 0.0; }
-         }
-         else
-         {
-            const double *xe = x + (e0 + e1) * D3 + loc1;
-#pragma unroll
-            for (int dy = 0; dy < D; dy++) { gi[dy] = 0; u[dy] = __ldg(xe + D * dy); }
-         }
-      }
-   };
-
-   int64_t tile = blockIdx.x;
-   if (tile >= ntiles) { return; }
-   if (t == 0) { mbar_init(bar, 1); }
-   __syncthreads();
-   issue_qdata(tile);
-   issue_idx(tile);
-   cp_async_wait_all();
-   __syncthreads();
-   int gi[D], gi_n[D];
-   double u[D], u_n[D];
-   load_inputs(tile, gi, u);
-   uint32_t parity = 0;
-
-   for (; tile < ntiles; tile += gridDim.x)
-   {
-      const int64_t e0 = tile * NEB;
-      const int nev = (int)((ne - e0) < NEB ? (ne - e0) : NEB);
-      const int64_t next = tile + gridDim.x;
-      const bool more = next < ntiles;
-
-      if (has1) { S::stage1(bs, u, r1 + a1); }
-      if (more) { issue_idx(next); } // idx_s was consumed when this tile's inputs were gathered
-      __syncthreads();
-      if (t < C::T2) { S::stage2(bs, r1, r2, t); }
-      if constexpr (!C::TMA_OK) { cp_async_wait_all(); }
-      __syncthreads();
-      if (t < C::T3) { S::stage3(bs, r2, qd, t, bar, parity); }
-      parity ^= 1u;
-      if (FUSED && more) { cp_async_wait_all(); } // this thread's share of the next indices landed
-      __syncthreads();
-      // the slab is free: stream the next tile's quadrature data while stages 4, 5 and the next
-      // tile's stages 1, 2 run; gather the next tile's inputs into registers
-      if (more)
-      {
-         issue_qdata(next);
-         load_inputs(next, gi_n, u_n);
-      }
-      if (t < C::T2) { S::stage4(bs, r2, r1, t); }
-      __syncthreads();
-      if (has1 && e1 < nev)
-      {
-         double v[D];
-         S::stage5(bs, r1 + a1, v);
-         double *ye = y + (e0 + e1) * D3 + loc1;
-#pragma unroll
-         for (int dy = 0; dy < D; dy++)
-         {
-            if (FUSED)
-            {
-               if (gi[dy] >= 0) { atomicAdd(y + gi[dy], v[dy]); }
-            }
-            else { ye[D * dy] += v[dy]; }
-         }
-      }
-      if (more)
-      {
-#pragma unroll
-         for (int dy = 0; dy < D; dy++) { gi[dy] = gi_n[dy]; u[dy] = u_n[dy]; }
-      }
-      __syncthreads(); // F consumed before the next tile's stage 1 overwrites the region
-   }
-}
-
 // host: even-odd tables from the (Q x D, q fastest) tables; returns false when the basis does
 // not have the required symmetry (relative 1e-12)
 template <int D, int Q>
@@ -828,7 +703,51 @@ inline bool fill_eo_basis(const b2f_pa *pa, EOBasis<D, Q> &bs)
    return true;
 }
 
-template <int KIND, int D, int Q, int NEB, int MINB = 1, int FUSEDSEL = 1, bool PERSIST = false>
+// host: the (Q, rows-per-element, NE) tensor map over an integrator's quadrature data, boxes of
+// (Q, box_rows, 1), 64-byte swizzle (Q = 8).  Cached in the b2f_pa (rebuilt when the data
+// pointer or the element count changes: compacted copies of marked integrators, |D| twins).
+inline int make_qdata_tensor_map(b2f_pa *pa, int q, int rows, int box_rows)
+{
+   if (pa->tmap_data == pa->data && pa->tmap_ne == pa->ne) { return B2F_OK; }
+   typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                 CUtensorMapFloatOOBfill);
+   static encode_fn encode = nullptr;
+   static std::mutex mtx;
+   std::lock_guard<std::mutex> lock(mtx);
+   if (!encode)
+   {
+      void *fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      B2F_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      if (!fn || qres != cudaDriverEntryPointSuccess)
+      {
+         set_error("cuTensorMapEncodeTiled is not available from this driver");
+         return B2F_ERR_UNSUPPORTED;
+      }
+      encode = reinterpret_cast<encode_fn>(fn);
+   }
+   static_assert(sizeof(CUtensorMap) == sizeof(pa->tmap), "tensor map size");
+   const cuuint64_t dims[3] = {(cuuint64_t)q, (cuuint64_t)rows, (cuuint64_t)pa->ne};
+   const cuuint64_t strides[2] = {(cuuint64_t)q * 8u, (cuuint64_t)q * 8u * (cuuint64_t)rows};
+   const cuuint32_t box[3] = {(cuuint32_t)q, (cuuint32_t)box_rows, 1u};
+   const cuuint32_t estr[3] = {1u, 1u, 1u};
+   const CUresult r = encode(reinterpret_cast<CUtensorMap *>(pa->tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+                             pa->data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+   if (r != CUDA_SUCCESS)
+   {
+      set_error("cuTensorMapEncodeTiled failed (%d) for q=%d rows=%d ne=%lld", (int)r, q, rows, (long long)pa->ne);
+      return B2F_ERR_CUDA;
+   }
+   pa->tmap_data = pa->data;
+   pa->tmap_ne = pa->ne;
+   return B2F_OK;
+}
+
+template <int KIND, int D, int Q, int NEB, int MINB = 1, int FUSEDSEL = 1>
 int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx, double *dot_acc = nullptr)
 {
    using C = PipeCfg<KIND, D, Q, NEB>;
@@ -848,82 +767,60 @@ int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx, double 
    // interior and boundary elements around the halo exchange)
    const int64_t e_first = pa->rb, e_last = pa->re < 0 ? pa->ne : pa->re;
    if (e_last <= e_first) { return B2F_OK; }
-   int64_t grid = cdiv(e_last - e_first, NEB);
+   const int64_t grid = cdiv(e_last - e_first, NEB);
+   TmapArg<C::SWZ> tm;
+   if constexpr (C::SWZ)
+   {
+      if (int rc = make_qdata_tensor_map(pa, Q, C::ROWS, C::BOX_ROWS)) { return rc; }
+      memcpy(tm.bytes, pa->tmap, sizeof(tm.bytes));
+   }
    auto go = [&](auto kern) -> int
    {
-      // (keyed by the kernel's address: instantiations that differ only in bool template
-      // arguments share one function-pointer type, hence one lambda specialisation)
-      static std::map<const void *, int> cache;
-      int &resident = cache[(const void *)kern];
-      if (resident == 0)
-      {
-         B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-         int occ = 0;
-         B2F_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NT, C::SMEM));
-         resident = (occ < 1 ? 1 : occ) * ctx->sm_count;
-      }
+      int resident = 0;
+      if (int rc = kernel_residency(ctx, kern, C::NT, C::SMEM, resident)) { return rc; }
       const char *pfs = getenv("B2F_PF");
       const int pf = pfs ? atoi(pfs) : resident;
-      if (PERSIST && grid > resident) { grid = resident; }
+      const VecArgs va = {pa->vd, (long long)pa->vxs, (long long)pa->vxo, (long long)pa->vics};
       timing_mark(ctx);
-      if constexpr (PERSIST) { kern<<<(unsigned)grid, C::NT, C::SMEM, ctx->stream>>>(bs, pa->data, x, y, idx, pa->ne, pf); }
-      else
-      {
-         const VecArgs va = {pa->vd, (long long)pa->vxs, (long long)pa->vxo, (long long)pa->vics};
-         kern<<<(unsigned)grid, C::NT, C::SMEM, ctx->stream>>>(bs, pa->data, x, y, idx, e_last, pf, dot_acc,
-                                                              e_first, va);
-      }
+      kern<<<(unsigned)grid, C::NT, C::SMEM, ctx->stream>>>(bs, pa->data, x, y, idx, e_last, pf, dot_acc,
+                                                           e_first, va, tm);
       timing_mark(ctx);
       B2F_LAUNCH_CHECK(ctx);
       return B2F_OK;
    };
    const bool fused = idx != nullptr;
    const bool vec = pa->vd > 1;
-   if ((fused && FUSEDSEL == 0) || (!fused && FUSEDSEL == 1) || (dot_acc && (!fused || PERSIST || vec)) ||
-       (vec && PERSIST))
+   if ((fused && FUSEDSEL == 0) || (!fused && FUSEDSEL == 1) || (dot_acc && (!fused || vec)))
    {
       set_error("pa_apply_3d_eo: kernel form not instantiated");
       return B2F_ERR_UNSUPPORTED;
    }
    constexpr bool CL = (D == Q);
-   if constexpr (PERSIST)
+   // (the vector form has its own instantiation so that the scalar hot path is untouched)
+   if (pa->collocated && CL)
    {
-      if (pa->collocated && CL)
-      {
-         if constexpr (FUSEDSEL != 0) { if (fused) { return go(pa_apply_3d_eop_kernel<KIND, D, Q, NEB, true, CL, MINB>); } }
-         if constexpr (FUSEDSEL != 1) { if (!fused) { return go(pa_apply_3d_eop_kernel<KIND, D, Q, NEB, false, CL, MINB>); } }
-      }
-      if constexpr (FUSEDSEL != 0) { if (fused) { return go(pa_apply_3d_eop_kernel<KIND, D, Q, NEB, true, false, MINB>); } }
-      if constexpr (FUSEDSEL != 1) { if (!fused) { return go(pa_apply_3d_eop_kernel<KIND, D, Q, NEB, false, false, MINB>); } }
-   }
-   else
-   {
-      // (the vector form has its own instantiation so that the scalar hot path is untouched)
-      if (pa->collocated && CL)
-      {
-         if constexpr (FUSEDSEL != 0)
-         {
-            if (fused && vec) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, CL, MINB, false, true>); }
-            if (fused && dot_acc) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, CL, MINB, true>); }
-            if (fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, CL, MINB>); }
-         }
-         if constexpr (FUSEDSEL != 1)
-         {
-            if (!fused && vec) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, CL, MINB, false, true>); }
-            if (!fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, CL, MINB>); }
-         }
-      }
       if constexpr (FUSEDSEL != 0)
       {
-         if (fused && vec) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, false, MINB, false, true>); }
-         if (fused && dot_acc) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, false, MINB, true>); }
-         if (fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, false, MINB>); }
+         if (fused && vec) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, CL, MINB, false, true>); }
+         if (fused && dot_acc) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, CL, MINB, true>); }
+         if (fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, CL, MINB>); }
       }
       if constexpr (FUSEDSEL != 1)
       {
-         if (!fused && vec) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, false, MINB, false, true>); }
-         if (!fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, false, MINB>); }
+         if (!fused && vec) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, CL, MINB, false, true>); }
+         if (!fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, CL, MINB>); }
       }
+   }
+   if constexpr (FUSEDSEL != 0)
+   {
+      if (fused && vec) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, false, MINB, false, true>); }
+      if (fused && dot_acc) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, false, MINB, true>); }
+      if (fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, true, false, MINB>); }
+   }
+   if constexpr (FUSEDSEL != 1)
+   {
+      if (!fused && vec) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, false, MINB, false, true>); }
+      if (!fused) { return go(pa_apply_3d_eo_kernel<KIND, D, Q, NEB, false, false, MINB>); }
    }
    return B2F_ERR_UNSUPPORTED;
 }

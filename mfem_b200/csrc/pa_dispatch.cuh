@@ -81,8 +81,9 @@ constexpr int smem_eo(int kind, int D, int Q, int n)
    const PipeLayout L = pipe_layout(kind, D, Q, n);
    const int sa = pad16(D * yq, L.ra), sc = pad16(Q * yq, yq);
    const int q3 = Q * Q * Q;
-   const int dp = (nqd * q3) % 2 == 0 ? L.dpad : 0;
-   return 16 + 8 * (n * (nqd * q3 + dp) + na * D * sa + nc * D * sc) + 4 * (((n * D * D * D + 3) / 4) * 4);
+   const bool tma = (nqd * q3) % 2 == 0, swz = tma && Q == 8;
+   const int dp = (tma && !swz) ? L.dpad : 0;
+   return 16 + 8 * (n * (nqd * q3 + dp) + na * D * sa + nc * D * sc) + (swz ? 1024 : 0);
 }
 
 // Elements per CTA, candidate i: 0 -> >= 4 CTAs per SM, 1 -> 3 CTAs, 2 -> 2 CTAs; <= 512 threads

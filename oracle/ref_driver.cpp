@@ -932,6 +932,7 @@ static int do_dump_cheb(const Args &A, const char *out)
 
 // Timing of the reference CPU path.  Prints one JSON object.
 //   mode=mult : y = A x (BilinearForm::Mult, PA) repeated `reps` times
+//   mode=kernel : AddMultPA on E-vectors (bench_ceed.cpp BK style), `reps` times
 //   mode=pcg  : bench_ceed.cpp BP style: CG (optionally Jacobi), fixed `iters` iterations
 static int do_bench(const Args &A)
 {
@@ -947,14 +948,35 @@ static int do_bench(const Args &A)
    Vector x(ndofs), y(ndofs);
    x.UseDevice(true); y.UseDevice(true);
    x.Randomize(1);
-   double sec = 0, ynorm = 0; int its = 0;
+   double sec = 0, ynorm = 0, final_norm = 0, initial_norm = 0; int its = 0;
    if (mode == "mult")
    {
       P.a->Mult(x, y); // warm-up
+      MFEM_DEVICE_SYNC;
       double t1 = now();
       for (int i = 0; i < reps; i++) { P.a->Mult(x, y); }
+      MFEM_DEVICE_SYNC;
       sec = (now() - t1) / reps; its = 1;
       ynorm = y.Norml2();
+   }
+   else if (mode == "kernel")
+   {
+      // BK style (bench_ceed.cpp:258-298): AddMultPA on E-vectors only, i.e. the reference's
+      // SmemPADiffusionApply3D / SmemPAMassApply3D (or its fallback) without the restriction.
+      const Operator *R = fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC);
+      Vector xe(R->Height()), ye(R->Height());
+      xe.UseDevice(true); ye.UseDevice(true);
+      R->Mult(x, xe);
+      ye = 0.0;
+      P.bfi->AddMultPA(xe, ye); // warm-up
+      ye = 0.0;
+      MFEM_DEVICE_SYNC;
+      double t1 = now();
+      for (int i = 0; i < reps; i++) { P.bfi->AddMultPA(xe, ye); }
+      MFEM_DEVICE_SYNC;
+      sec = (now() - t1) / reps; its = 1;
+      ye *= 1.0 / reps;
+      ynorm = ye.Norml2();
    }
    else
    {
@@ -982,21 +1004,24 @@ static int do_bench(const Args &A)
       for (int r = 0; r < reps; r++)
       {
          X = 0.0;
+         MFEM_DEVICE_SYNC;
          double t1 = now();
          cg.Mult(B, X);
+         MFEM_DEVICE_SYNC;
          double t = now() - t1;
          best = std::min(best, t);
          sec += t;
       }
       sec /= reps; its = cg.GetNumIterations();
       ynorm = X.Norml2();
+      final_norm = cg.GetFinalNorm(); initial_norm = cg.GetInitialNorm();
    }
    const char *dev = getenv("MFEM_DEVICE");
    std::printf("{\"mode\": \"%s\", \"ndofs\": %d, \"ne\": %d, \"p\": %d, \"iters\": %d, "
                "\"seconds\": %.6e, \"setup_seconds\": %.3f, \"dofs_iters_per_s\": %.6e, "
-               "\"norm\": %.17g, \"device\": \"%s\"}\n",
+               "\"norm\": %.17g, \"final_norm\": %.17g, \"initial_norm\": %.17g, \"device\": \"%s\"}\n",
                mode.c_str(), ndofs, fes.GetNE(), P.p, its, sec, t_setup,
-               (double)ndofs * its / sec, ynorm, dev ? dev : "cpu");
+               (double)ndofs * its / sec, ynorm, final_norm, initial_norm, dev ? dev : "cpu");
    return 0;
 }
 
