@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--n", type=int, default=None, help="elements per side per GPU")
     ap.add_argument("--iters", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the reference-checksum parity check")
     ap.add_argument("--cpu-n", type=int, default=None, help="elements per side of the CPU sample")
     ap.add_argument("--curved", type=int, default=None,
                     help="1: order-3 nodes displaced by the smooth map of BASELINE config C5 (default for --bp 5)")
@@ -234,6 +235,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- parity first: the reference-checksum sample on the same N ranks ---------------------
+    parity = None if a.no_parity else parity_check(m, np, torch, dev, dist, rank, world, w, a.iters)
+
     # ---- problem ------------------------------------------------------------------------
     px, py, pz = w["grid"]
     n, p = w["n"], w["p"]
@@ -393,6 +397,7 @@ def main():
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks
                          else "fallback 6650 GB/s"},
             "clocks": clocks,
+            "parity_check": parity,
         }
         if a.gpus == 1 and not a.no_cpu_baseline:
             try:
@@ -404,11 +409,126 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": "GDOF/s", "cores": 0, "kind": "reference",
                                         "sample": f"failed: {ex}"}
         print(json.dumps(line), flush=True)
+    if parity is not None and parity.get("ok") is False:
+        if rank == 0:
+            print(f"PARITY CHECK FAILED: {parity}", file=sys.stderr, flush=True)
+        sys.exit(3)
     if dist:
         dist.barrier()
         if halo:
             halo.close()
         dist.destroy_process_group()
+
+
+def serial_dof_of_lattice(m, np, n, p):
+    """Reference (serial MakeCartesian3D + H1 numbering) dof id of every point of the global
+    (p n + 1)^3 lattice, from the serial space's own element-dof table."""
+    fes = m.FiniteElementSpace(m.Mesh.MakeCartesian3D(n, n, n), m.H1_FECollection(p, 3))
+    D, L = p + 1, p * n + 1
+    ev = fes.elem_vertices.reshape(fes.ne, 3, 8)
+    ijk = np.rint(ev.min(axis=2) * n).astype(np.int64)  # element coordinates
+    a = np.arange(D, dtype=np.int64)
+    gx = ijk[:, 0, None, None, None] * p + a[None, None, None, :]
+    gy = ijk[:, 1, None, None, None] * p + a[None, None, :, None]
+    gz = ijk[:, 2, None, None, None] * p + a[None, :, None, None]
+    lat = (gx + L * (gy + L * gz)).reshape(fes.ne, D ** 3)          # lexicographic, x fastest
+    dofs = fes.elem_dof.reshape(fes.ne, D ** 3)[:, fes.dof_map]    # restriction.cpp:60-75
+    s_of_lat = np.empty(L ** 3, np.int64)
+    s_of_lat[lat.ravel()] = dofs.ravel()
+    return s_of_lat, fes.ndofs
+
+
+def parity_check(m, np, torch, dev, dist, rank, world, w, iters):
+    """Driver-visible parity of the GPU arm, at every N, before anything is timed: a sample of the
+    bench's own BP (partitioned over the N ranks, same halo mode) against the UNMODIFIED
+    reference's checksums (tests/golden/checksums.json, written by oracle/make_checksums.py):
+    ||A x||_2 for x = Vector::Randomize(1) in the reference's numbering, and ||X||_2 and
+    GetFinalNorm() of `iters` fixed Jacobi-PCG iterations (bench_ceed.cpp:222-243 protocol)."""
+    import ctypes as C
+    from mfem_b200.capi import call
+    with open(os.path.join(ROOT, "tests", "golden", "checksums.json")) as f:
+        cases = json.load(f)["cases"]
+    sbp = w["bp"] - 1 if w["vdim"] == 3 else w["bp"]
+    px, py, pz = w["grid"]
+    cand = [c for c in cases.values() if c["bp"] == sbp and c["p"] == w["p"] and bool(c["curved"]) == w["curved"]
+            and c["n"] % 2 == 0 and c["pcg_iters"] == iters]
+    if not cand or w["vdim"] != 1:
+        return {"skipped": f"no reference checksum for BP{w['bp']} p={w['p']} curved={w['curved']}"}
+    ref = max(cand, key=lambda c: c["n"])
+    n, p = ref["n"], w["p"]
+    if world > 1:
+        mesh = m.Mesh(3, n, n, n, True, part=(px, py, pz), rank=rank)
+    else:
+        mesh = m.Mesh.MakeCartesian3D(n, n, n)
+    if w["curved"]:
+        mesh.SetCurvature(3)
+        mesh.Transform(m.curve_map)
+    fes = m.FiniteElementSpace(mesh, m.H1_FECollection(p, 3))
+    ir = m.IntegrationRules(gll=w["gll"]).Get(3, 2 * p - 1 if w["gll"] else 2 * p + 3)
+    it = (m.MassIntegrator if w["kind"] == "mass" else m.DiffusionIntegrator)(1.0, ir)
+    form = m.BilinearForm(dev, fes)
+    form.SetAssemblyLevel("PARTIAL")
+    form.AddDomainIntegrator(it)
+    form.Assemble()
+    halo = None
+    xs = np.empty(ref["ndofs"])
+    call("b2f_vector_randomize_h", xs.ctypes.data_as(C.c_void_p), xs.size, 1)
+    if world > 1:
+        ids = [m.Halo.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        halo = m.Halo(dev, rank, world, fes.ndofs, fes.halo_tables, ids[0])
+        if os.environ.get("B2F_HALO", "p2p") != "nccl":
+            halo.connect_p2p(dist)
+        form.SetHalo(halo)
+        s_of_lat, nser = serial_dof_of_lattice(m, np, n, p)
+        assert nser == ref["ndofs"]
+        t2s = s_of_lat[fes.halo_tables["ldof_lattice"][fes.halo_tables["ltdof_ldof"]]]
+        x_t = dev.to_device(np.ascontiguousarray(xs[t2s]))
+    else:
+        assert fes.ndofs == ref["ndofs"], (fes.ndofs, ref["ndofs"])
+        x_t = dev.to_device(xs)
+    nt = fes.GetTrueVSize()
+
+    def gnorm(v):
+        s = (v.double() ** 2).sum().reshape(1)
+        if dist:
+            dist.all_reduce(s)
+        return float(s.sqrt().item())
+
+    y_t = dev.empty(nt)
+    form.Mult(x_t, y_t)
+    dev.sync()
+    op_norm = gnorm(y_t)
+    ess = fes.GetEssentialTrueDofs()
+    b_l = m.LinearForm(dev, fes).Assemble()
+    if halo:
+        b = dev.empty(nt)
+        halo.MultTranspose(b_l, b)
+    else:
+        b = b_l
+    A, _, B = form.FormLinearSystem(ess, dev.zeros(nt), b)
+    M = m.OperatorJacobiSmoother(form, ess)
+    cg = m.CGSolver()
+    cg.SetRelTol(0.0); cg.SetAbsTol(0.0); cg.SetMaxIter(iters)
+    cg.SetOperator(A); cg.SetPreconditioner(M)
+    X = dev.zeros(nt)
+    cg.Mult(B, X)
+    dev.sync()
+    x_norm, fin = gnorm(X), cg.GetFinalNorm()
+    res = {"case": f"BP{sbp} p={p} {n}^3 hexes{' curved' if w['curved'] else ''}, {ref['ndofs']} dofs, over {world} rank(s)",
+           "reference": "tests/golden/checksums.json (unmodified MFEM -pa, oracle/make_checksums.py)",
+           "n_ranks": world,
+           "rel_err_y": abs(op_norm - ref["op_norm"]) / ref["op_norm"],
+           "x_norm_rel": abs(x_norm - ref["pcg_x_norm"]) / ref["pcg_x_norm"],
+           # relative to the INITIAL norm: a solve that has converged to round-off (BP1) ends on noise
+           "final_norm_rel": abs(fin - ref["pcg_final_norm"]) / ref["pcg_initial_norm"],
+           "tol": {"rel_err_y": 1e-12, "x_norm_rel": 1e-9, "final_norm_rel": 1e-9}}
+    res["ok"] = bool(res["rel_err_y"] < 1e-12 and res["x_norm_rel"] < 1e-9 and res["final_norm_rel"] < 1e-9
+                     and cg.GetNumIterations() == ref["pcg_iters"])
+    if halo:
+        halo.close()
+    form.close(); it.close()
+    return res
 
 
 def it_bytes(w, ne):

@@ -1162,6 +1162,24 @@ int b2f_operator_assemble_diagonal(b2f_operator *op, double *diag)
    b2f_ctx *ctx = op->ctx;
    b2f_restriction *r = op->r;
    const int64_t ne_dof = (int64_t)r->ne * r->dof;
+   bool any_marked = false;
+   for (size_t i = 0; i < op->integ.size(); i++) { any_marked = any_marked || op->marked[i]; }
+   if (r->vdim == 1 && !any_marked)
+   {
+      // hot form: every integrator's element diagonal goes straight into the L-vector with unsigned
+      // reductions (AssembleDiagonalPA + AbsMultTranspose, bilinearform_ext.cpp:370-430, in one
+      // kernel per integrator); the E-vector diagonal never exists
+      double *dl = diag;
+      if (op->halo)
+      {
+         B2F_TRY(ensure(&op->yl, r->ndofs));
+         dl = op->yl;
+      }
+      B2F_CUDA(cudaMemsetAsync(dl, 0, sizeof(double) * (size_t)r->ndofs, ctx->stream));
+      for (size_t i = 0; i < op->integ.size(); i++) { B2F_TRY(pa_diag_fused(op->integ[i], r->gather_map, dl)); }
+      // ParBilinearForm::AssembleDiagonal (fem/pbilinearform.cpp:293): P^T of the local diagonal
+      return op->halo ? halo_mult_transpose(op->halo, op->yl, diag) : B2F_OK;
+   }
    B2F_TRY(ensure(&op->ye, ne_dof));
    B2F_CUDA(cudaMemsetAsync(op->ye, 0, sizeof(double) * ne_dof, ctx->stream)); // bilinearform_ext.cpp:385
    for (size_t i = 0; i < op->integ.size(); i++)

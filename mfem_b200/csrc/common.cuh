@@ -199,8 +199,10 @@ namespace b2f
 // pa_has_fused_dot)
 int pa_apply(b2f_pa *pa, const double *x, double *y, const int *idx, double *dot_acc = nullptr);
 bool pa_has_fused_dot(const b2f_pa *pa);
-// pa_diag.cu
+// pa_diag.cu: E-vector form (diag_e += diagonal), and fused with the unsigned scatter
+// (diag_l[|gather_map[i]|] += diagonal, ElementRestriction::AbsMultTranspose)
 int pa_diag(b2f_pa *pa, double *diag_e);
+int pa_diag_fused(b2f_pa *pa, const int *gather_map, double *diag_l);
 // pa_setup.cu
 int diffusion_setup(b2f_ctx *ctx, int dim, int q1d, int64_t ne, const double *W_d,
                     const double *J, const double *coeff, int coeff_dim, int coeff_const,

@@ -134,6 +134,11 @@ int lf_domain(b2f_ctx *ctx, int dim, int d, int q, int vdim, int64_t ne, const i
       const size_t smem = sizeof(double) * ((size_t)d * q + (size_t)n * n * n);
       if (smem > 48 * 1024)
       {
+         if ((int)smem > ctx->max_smem_optin)
+         {
+            set_error("lf_domain: D1D=%d Q1D=%d needs %zu B of shared memory", d, q, smem);
+            return B2F_ERR_UNSUPPORTED;
+         }
          B2F_CUDA(cudaFuncSetAttribute(lf_domain_3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
       }
@@ -144,6 +149,16 @@ int lf_domain(b2f_ctx *ctx, int dim, int d, int q, int vdim, int64_t ne, const i
    else
    {
       const size_t smem = sizeof(double) * ((size_t)2 * d * q + (size_t)q * q);
+      if (smem > 48 * 1024)
+      {
+         if ((int)smem > ctx->max_smem_optin)
+         {
+            set_error("lf_domain: D1D=%d Q1D=%d needs %zu B of shared memory", d, q, smem);
+            return B2F_ERR_UNSUPPORTED;
+         }
+         B2F_CUDA(cudaFuncSetAttribute(lf_domain_2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+      }
       const int nt = ((q * q + 31) / 32) * 32;
       lf_domain_2d_kernel<<<(unsigned)ne, nt, smem, ctx->stream>>>(d, q, vdim, ne, markers, B_d, W_d, detJ,
                                                                    coeff, cst, y_e);

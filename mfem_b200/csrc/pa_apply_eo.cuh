@@ -660,6 +660,167 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
    }
 }
 
+// ---- persistent CTAs: every stream of the next tile is in flight while this tile computes ------
+// One CTA per resident slot loops over tiles (tile += gridDim.x).  The one-shot kernel above pays,
+// per tile, the lane -> (element, dx, dz) set-up and the dependent load chain gather index -> x ->
+// stage 1 (65 % of the stall samples of the BP1 kernels, profiles/r01_bp1_p4_tuned_ncu.txt; with
+// <= 3 resident CTAs at p >= 7 nothing hides it).  Here the set-up runs once per CTA and the chain
+// is broken across tiles: the next tile's gather indices are loaded during stages 2-3, its x values
+// during stages 4-5, and its quadrature-data slab is requested (TMA) the moment stage 3 has
+// consumed the current one.  Scalar spaces only; same stages, same results as the one-shot kernel.
+template <int KIND, int D, int Q, int NEB, bool FUSED, bool COLLOC, int MINB>
+__global__ void __launch_bounds__(PipeCfg<KIND, D, Q, NEB>::NT, MINB)
+pa_apply_3d_eo_persistent_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__restrict__ qdata,
+                                 const double *__restrict__ x, double *__restrict__ y,
+                                 const int *__restrict__ idx, const int64_t ne, const int64_t e_first,
+                                 const __grid_constant__ TmapArg<PipeCfg<KIND, D, Q, NEB>::SWZ> tmap)
+{
+   using C = PipeCfg<KIND, D, Q, NEB>;
+   using S = EOStages<KIND, D, Q, NEB, COLLOC, false>;
+   constexpr int D2 = C::D2, D3 = C::D3, Q3 = C::Q3, YQ = C::YQ;
+   extern __shared__ __align__(16) unsigned char smem_raw[];
+   unsigned char *sbase = C::SWZ ? smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) : smem_raw;
+   double *qd = reinterpret_cast<double *>(C::SWZ ? sbase : sbase + 16);
+   double *r1 = qd + C::QD;
+   double *r2 = r1 + C::R1;
+   uint64_t *bar = reinterpret_cast<uint64_t *>(C::SWZ ? reinterpret_cast<unsigned char *>(r2 + C::R2) : sbase);
+
+   const int t = threadIdx.x;
+   const int64_t ntiles = (ne - e_first + NEB - 1) / NEB;
+   int e1, dx1, dz1;
+   eo_line_coords<D, NEB, C::L.order>(t, e1, dx1, dz1);
+   const bool has1 = t < C::T1;
+   const int loc1 = dx1 + D2 * dz1;
+   const int a1 = Q * e1 + YQ * dx1 + C::SA * dz1;
+
+   auto tile_nev = [&](int64_t tile) -> int
+   {
+      const int64_t left = ne - (e_first + tile * NEB);
+      return (int)(left < NEB ? left : NEB);
+   };
+   auto issue_qdata = [&](int64_t tile)
+   {
+      const int64_t e0 = e_first + tile * NEB;
+      const int nev = tile_nev(tile);
+      const double *qslab = qdata + e0 * (int64_t)(C::NQD * Q3);
+      if constexpr (C::TMA_OK)
+      {
+         if (t == 0)
+         {
+            fence_proxy_async(); // the slab was just read through the generic proxy
+            mbar_expect_tx(bar, (uint32_t)(nev * C::NQD * Q3) * 8u);
+            for (int e = 0; e < nev; e++)
+            {
+               if constexpr (C::SWZ)
+               {
+#pragma unroll
+                  for (int b = 0; b < C::NBOX; b++)
+                  {
+                     tensor_g2s_3d(qd + e * C::DS + b * (C::BOX_ROWS * Q), &tmap, 0, b * C::BOX_ROWS, (int)(e0 + e), bar);
+                  }
+               }
+               else
+               {
+                  bulk_g2s(qd + e * C::DS, qslab + (int64_t)e * (C::NQD * Q3), (uint32_t)(C::NQD * Q3) * 8u, bar);
+               }
+            }
+         }
+      }
+      else
+      {
+         for (int i = t; i < nev * C::NQD * Q3; i += C::NT) { cp_async8(qd + i, qslab + i); }
+      }
+   };
+   // gather indices of a tile (FUSED), -1 where this thread has no line or the dof is essential
+   auto load_idx = [&](int64_t tile, int (&g)[D])
+   {
+#pragma unroll
+      for (int dy = 0; dy < D; dy++) { g[dy] = -1; }
+      if constexpr (FUSED)
+      {
+         if (has1 && e1 < tile_nev(tile))
+         {
+            const int *ip = idx + (e_first + tile * NEB + e1) * D3 + loc1;
+#pragma unroll
+            for (int dy = 0; dy < D; dy++) { g[dy] = __ldg(ip + D * dy); }
+         }
+      }
+   };
+   auto load_x = [&](int64_t tile, const int (&g)[D], double (&u)[D])
+   {
+#pragma unroll
+      for (int dy = 0; dy < D; dy++) { u[dy] = 0.0; }
+      if (has1 && e1 < tile_nev(tile))
+      {
+         if constexpr (FUSED)
+         {
+#pragma unroll
+            for (int dy = 0; dy < D; dy++) { u[dy] = g[dy] >= 0 ? __ldg(x + g[dy]) : 0.0; }
+         }
+         else
+         {
+            const double *xe = x + (e_first + tile * NEB + e1) * D3 + loc1;
+#pragma unroll
+            for (int dy = 0; dy < D; dy++) { u[dy] = __ldg(xe + D * dy); }
+         }
+      }
+   };
+
+   int64_t tile = blockIdx.x; // the launcher keeps gridDim.x <= ntiles
+   if (t == 0) { mbar_init(bar, 1); }
+   __syncthreads();
+   issue_qdata(tile);
+   int gi[D], gi_n[D];
+   double u[D], u_n[D];
+   load_idx(tile, gi);
+   load_x(tile, gi, u);
+   uint32_t parity = 0;
+
+   for (;;)
+   {
+      const int64_t next = tile + gridDim.x;
+      const bool more = next < ntiles;
+      const int nev = tile_nev(tile);
+      if (has1) { S::stage1(bs, u, r1 + a1); }
+      if (more) { load_idx(next, gi_n); }
+      __syncthreads();
+      if (t < C::T2) { S::stage2(bs, r1, r2, t); }
+      if constexpr (!C::TMA_OK) { cp_async_wait_all(); }
+      __syncthreads();
+      if (t < C::T3) { S::stage3(bs, r2, qd, t, bar, parity); }
+      parity ^= 1u;
+      __syncthreads();
+      // the slab is free: request the next tile's quadrature data and gather its inputs
+      if (more)
+      {
+         issue_qdata(next);
+         load_x(next, gi_n, u_n);
+      }
+      if (t < C::T2) { S::stage4(bs, r2, r1, t); }
+      __syncthreads();
+      if (has1 && e1 < nev)
+      {
+         double v[D];
+         S::stage5(bs, r1 + a1, v);
+         double *ye = y + (e_first + tile * NEB + e1) * D3 + loc1; // E-vector form
+#pragma unroll
+         for (int dy = 0; dy < D; dy++)
+         {
+            if (FUSED)
+            {
+               if (gi[dy] >= 0) { atomicAdd(y + gi[dy], v[dy]); }
+            }
+            else { ye[D * dy] += v[dy]; }
+         }
+      }
+      if (!more) { break; }
+#pragma unroll
+      for (int dy = 0; dy < D; dy++) { gi[dy] = gi_n[dy]; u[dy] = u_n[dy]; }
+      tile = next;
+      __syncthreads(); // F consumed before the next tile's stage 1 overwrites the region
+   }
+}
+
 // host: even-odd tables from the (Q x D, q fastest) tables; returns false when the basis does
 // not have the required symmetry (relative 1e-12)
 template <int D, int Q>
@@ -747,7 +908,9 @@ inline int make_qdata_tensor_map(b2f_pa *pa, int q, int rows, int box_rows)
    return B2F_OK;
 }
 
-template <int KIND, int D, int Q, int NEB, int MINB = 1, int FUSEDSEL = 1>
+// PERSIST: -1 = one-shot kernel only (persistent form not instantiated), 0 = one-shot by default,
+// 1 = persistent by default (both instantiated; B2F_PERSIST overrides)
+template <int KIND, int D, int Q, int NEB, int MINB = 1, int FUSEDSEL = 1, int PERSIST = -1>
 int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx, double *dot_acc = nullptr)
 {
    using C = PipeCfg<KIND, D, Q, NEB>;
@@ -790,6 +953,34 @@ int launch_3d_eo(b2f_pa *pa, const double *x, double *y, const int *idx, double 
    };
    const bool fused = idx != nullptr;
    const bool vec = pa->vd > 1;
+   // persistent form (scalar spaces, no fused dot): tuned per (kind, D, Q), B2F_PERSIST=0|1 overrides
+   if constexpr (PERSIST >= 0)
+   {
+      const char *ps = getenv("B2F_PERSIST");
+      const bool persist = ps ? atoi(ps) != 0 : PERSIST > 0;
+      if (persist && !vec && !dot_acc && ((fused && FUSEDSEL != 0) || (!fused && FUSEDSEL != 1)))
+      {
+         auto gop = [&](auto kern) -> int
+         {
+            int resident = 0;
+            if (int rc = kernel_residency(ctx, kern, C::NT, C::SMEM, resident)) { return rc; }
+            const int64_t g = grid < resident ? grid : resident;
+            timing_mark(ctx);
+            kern<<<(unsigned)g, C::NT, C::SMEM, ctx->stream>>>(bs, pa->data, x, y, idx, e_last, e_first, tm);
+            timing_mark(ctx);
+            B2F_LAUNCH_CHECK(ctx);
+            return B2F_OK;
+         };
+         constexpr bool CLP = (D == Q);
+         if (pa->collocated && CLP)
+         {
+            if constexpr (FUSEDSEL != 0) { if (fused) { return gop(pa_apply_3d_eo_persistent_kernel<KIND, D, Q, NEB, true, CLP, MINB>); } }
+            if constexpr (FUSEDSEL != 1) { if (!fused) { return gop(pa_apply_3d_eo_persistent_kernel<KIND, D, Q, NEB, false, CLP, MINB>); } }
+         }
+         if constexpr (FUSEDSEL != 0) { if (fused) { return gop(pa_apply_3d_eo_persistent_kernel<KIND, D, Q, NEB, true, false, MINB>); } }
+         if constexpr (FUSEDSEL != 1) { if (!fused) { return gop(pa_apply_3d_eo_persistent_kernel<KIND, D, Q, NEB, false, false, MINB>); } }
+      }
+   }
    if ((fused && FUSEDSEL == 0) || (!fused && FUSEDSEL == 1) || (dot_acc && (!fused || vec)))
    {
       set_error("pa_apply_3d_eo: kernel form not instantiated");

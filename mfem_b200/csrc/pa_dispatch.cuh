@@ -120,6 +120,17 @@ constexpr int tuned_cand_eo(int kind, int D, int Q)
    return 1;
 }
 
+// persistent form of the fused kernel (pa_apply_3d_eo_persistent_kernel): 1 = instantiated and the
+// default, -1 = not instantiated.  Measured over BP1/BP3/BP5, p = 1..8
+// (profiles/r02_sweep_persistent.txt): with >= 3 resident CTAs per SM the one-shot kernel already
+// overlaps one CTA's gather chain with the others' arithmetic, and the kernels are bound by the
+// LSU data pipe, not by latency; the persistent form wins only where a CTA is short-lived.
+constexpr int tuned_persist_eo(int kind, int D, int Q)
+{
+   if (kind == B2F_KIND_DIFFUSION && ((D == 3 && Q == 4) || (D == 2 && Q == 2) || (D == 8 && Q == 8))) { return 1; }
+   return -1;
+}
+
 // the even-odd kernel (and with it the fused x.(Ax) accumulation) runs for 3D integrators with
 // a symmetric basis and a (D,Q) in the dispatch tables
 inline bool basis_is_symmetric(const b2f_pa *pa);
@@ -163,15 +174,16 @@ int run_3d(b2f_pa *pa, const double *x, double *y, const int *idx, double *dot_a
    if (!idx) { return launch_3d_eo<KIND, D, Q, N1, 1, 0>(pa, x, y, idx); }
    const char *s = getenv("B2F_NEB_CAND");
    const int cand = s ? atoi(s) : tuned_cand_eo(KIND, D, Q);
+   constexpr int PS = tuned_persist_eo(KIND, D, Q);
    if (cand == 0 || (cand == 1 && N1 == N0) || (cand == 2 && N2 == N0))
    {
-      return launch_3d_eo<KIND, D, Q, N0, minb_eo(KIND, D, Q, N0), 1>(pa, x, y, idx, dot_acc);
+      return launch_3d_eo<KIND, D, Q, N0, minb_eo(KIND, D, Q, N0), 1, PS>(pa, x, y, idx, dot_acc);
    }
    if (cand == 1 || (cand == 2 && N2 == N1))
    {
-      if constexpr (N1 != N0) { return launch_3d_eo<KIND, D, Q, N1, minb_eo(KIND, D, Q, N1), 1>(pa, x, y, idx, dot_acc); }
+      if constexpr (N1 != N0) { return launch_3d_eo<KIND, D, Q, N1, minb_eo(KIND, D, Q, N1), 1, PS>(pa, x, y, idx, dot_acc); }
    }
-   if constexpr (N2 != N1 && N2 != N0) { return launch_3d_eo<KIND, D, Q, N2, minb_eo(KIND, D, Q, N2), 1>(pa, x, y, idx, dot_acc); }
+   if constexpr (N2 != N1 && N2 != N0) { return launch_3d_eo<KIND, D, Q, N2, minb_eo(KIND, D, Q, N2), 1, PS>(pa, x, y, idx, dot_acc); }
    return B2F_ERR_UNSUPPORTED;
 }
 

@@ -312,6 +312,16 @@ int setup_from_nodes(b2f_ctx *ctx, int kind, int dim, int q1d, int64_t ne, const
    const int64_t n = ne * NQ;
    if (n == 0) { return B2F_OK; }
    const size_t smem = sizeof(double) * 2 * q1d * nd;
+   if (smem > 48 * 1024)
+   {
+      if ((int)smem > ctx->max_smem_optin)
+      {
+         set_error("setup_from_nodes: Q1D=%d node_d1d=%d needs %zu B of shared memory", q1d, nd, smem);
+         return B2F_ERR_UNSUPPORTED;
+      }
+      B2F_CUDA(cudaFuncSetAttribute(setup_from_nodes_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      B2F_CUDA(cudaFuncSetAttribute(setup_from_nodes_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+   }
    const unsigned grid = (unsigned)cdiv(n, 256);
    if (dim == 3)
    {

@@ -379,9 +379,11 @@ class _PAIntegrator:
         # MassIntegrator::GetRule :1459 (2p + dim - 1 on affine tensor meshes): Q = p + 2 in 3D
         return IntRules.Get(fes.dim, 2 * fes.p + fes.dim - 1)
 
-    def AssemblePA(self, device, fes):
+    def AssemblePA(self, device, fes, weights=None):
         """AssemblePA (bilininteg_diffusion_pa.cpp:108 / bilininteg_mass_pa.cpp:25) with the
-        geometric factors fused in: D is computed straight from the nodes, J never exists."""
+        geometric factors fused in: D is computed straight from the nodes, J never exists.
+        weights: quadrature weights to use instead of the rule's (LinearForm passes ones to
+        obtain detJ itself)."""
         self.dev = device
         ir = self.ir or self.GetRule(fes)
         self.ir = ir
@@ -392,8 +394,8 @@ class _PAIntegrator:
         nodes_d = device.to_device(_f64(nodes))
         h = vp()
         call("b2f_pa_setup_from_nodes", device.ctx, self.kind, fes.dim, fes.d1d, ir.nq1d, fes.ne,
-             _np_ptr(self.B), _np_ptr(self.G), _np_ptr(ir.weights), nd, _np_ptr(Bn), _np_ptr(Gn),
-             _dp(nodes_d), self.coeff, C.byref(h))
+             _np_ptr(self.B), _np_ptr(self.G), _np_ptr(_f64(ir.weights if weights is None else weights)), nd,
+             _np_ptr(Bn), _np_ptr(Gn), _dp(nodes_d), self.coeff, C.byref(h))
         self.h = h
         device.sync()
         del nodes_d
@@ -804,24 +806,30 @@ def domain_lf_assemble(device, dim, d1d, q1d, vdim, ne, B, W, detJ_d, coeff_d, y
 
 
 class LinearForm:
-    """b_i = (1, phi_i): LinearForm + DomainLFIntegrator(one) (fem/lininteg.hpp:116,
-    fem/integ/lininteg_domain.cpp; rule order 2p + 0).  With a constant coefficient this is
-    B^T (W detJ) at that rule, i.e. the PA mass operator applied to the constant 1."""
+    """b_i = (1, phi_i): LinearForm + DomainLFIntegrator(one) (fem/lininteg.hpp:116, rule order
+    2p + 0), assembled on the device as LinearForm::UseFastAssembly does
+    (fem/linearform_ext.cpp:20-66): DomainLFIntegrator::AssembleDevice on E-vectors
+    (b2f_domain_lf_assemble), then ElementRestriction::MultTranspose.  detJ at the rule's points
+    comes from the fused geometric-factor kernel (mass set-up with unit weights: D = detJ)."""
 
     def __init__(self, device, fes):
         self.dev, self.fes = device, fes
 
     def Assemble(self):
         fes, dev = self.fes, self.dev
-        m = MassIntegrator(1.0, IntRules.Get(fes.dim, 2 * fes.p))
-        m.AssemblePA(dev, fes)
+        ir = IntRules.Get(fes.dim, 2 * fes.p)
+        g = MassIntegrator(1.0, ir)
+        g.AssemblePA(dev, fes, weights=np.ones(ir.nq1d ** fes.dim))
+        detJ, n = vp(), capi.i64()
+        call("b2f_pa_data", g.h, C.byref(detJ), C.byref(n))
         R = fes.GetElementRestriction(dev)
         vd = getattr(fes, "vdim", 1)
-        xe = dev.empty(R.Height()).fill_(1.0)
+        one = dev.empty(vd).fill_(1.0)
         ye = dev.zeros(R.Height())
-        m.AddMultPA(xe, ye, vdim=vd)
+        call("b2f_domain_lf_assemble", dev.ctx, fes.dim, fes.d1d, ir.nq1d, vd, fes.ne, vp(0), _np_ptr(_f64(g.B)),
+             _np_ptr(_f64(ir.weights)), detJ, _dp(one), vd, _dp(ye))
         b = dev.empty(fes.ndofs * vd)
         R.MultTranspose(ye, b)
         dev.sync()
-        m.close()
+        g.close()
         return b

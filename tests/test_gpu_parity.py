@@ -206,7 +206,7 @@ def test_constrained_operator_jacobi_and_pcg(dev, golden):
     cg.check_every = 8
     X2 = dev.zeros(ndofs)
     cg.Mult(B, X2)
-    assert cg.GetNumIterations() == len(cg.history or []) - 1 or True
+    assert abs(cg.GetNumIterations() - ref_its) <= 1  # the device stops at the converged iteration
     assert np.array_equal(host(X2), host(X)) or relerr(host(X2), host(X)) < 1e-9
     # unpreconditioned CG, fixed iteration count (bench_ceed.cpp:222-243) vs the C oracle
     from oracle import oracle as orc
@@ -305,7 +305,7 @@ def test_end_to_end_own_tables(dev, name):
     ess = fes.GetEssentialTrueDofs()
     assert np.array_equal(ess, g["ess_tdof_list"])
     b = m.LinearForm(dev, fes).Assemble()
-    assert relerr(host(b), g["b"]) < (1e-12 if not int(g["curved"][0]) else 1e-3)
+    assert relerr(host(b), g["b"]) < 1e-12
     u = dev.zeros(ndofs)
     A, X, B = a.FormLinearSystem(ess, u, b)
     M = m.OperatorJacobiSmoother(a, ess)
@@ -776,3 +776,89 @@ def test_config_c1_iteration_count(dev):
     assert cg.GetConverged() and abs(cg.GetNumIterations() - 197) <= 1, cg.GetNumIterations()
     assert abs(cg.history[0] - 1.84147e-05) < 2e-10          # (B r, r) at iteration 0, 6 printed digits
     a.close(); it.close()
+
+
+def _checksum_cases():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "checksums.json")) as f:
+        return sorted(json.load(f)["cases"].items())
+
+
+@pytest.mark.parametrize("key,ref", _checksum_cases(), ids=[k for k, _ in _checksum_cases()])
+def test_reference_checksums_at_machine_filling_sizes(dev, key, ref):
+    """Sizes that fill the GPU (up to 4.8 M dofs, thousands of CTAs) against the UNMODIFIED
+    reference's checksums (tests/golden/checksums.json, oracle/make_checksums.py; the values of
+    SURVEY.md section 6 among them): ||A x||_2 for x = Vector::Randomize(1) to 1e-12 and the
+    32-iteration Jacobi-PCG solve of bench_ceed.cpp's protocol (||X||_2, GetFinalNorm) to 1e-9."""
+    import ctypes as C
+    import mfem_b200 as m
+    from mfem_b200.capi import call
+    bp, p, n, curved = ref["bp"], ref["p"], ref["n"], bool(ref["curved"])
+    mesh = m.Mesh.MakeCartesian3D(n, n, n)
+    if curved:
+        mesh.SetCurvature(3)
+        mesh.Transform(m.curve_map)
+    fes = m.FiniteElementSpace(mesh, m.H1_FECollection(p, 3))
+    assert fes.ndofs == ref["ndofs"] and fes.ne == ref["ne"]
+    gll = bp == 5
+    ir = m.IntegrationRules(gll=gll).Get(3, 2 * p - 1 if gll else 2 * p + 3)
+    it = (m.MassIntegrator if bp == 1 else m.DiffusionIntegrator)(1.0, ir)
+    a = m.BilinearForm(dev, fes)
+    a.SetAssemblyLevel("PARTIAL")
+    a.AddDomainIntegrator(it)
+    a.Assemble()
+    xs = np.empty(fes.ndofs)
+    call("b2f_vector_randomize_h", xs.ctypes.data_as(C.c_void_p), xs.size, 1)
+    y = dev.empty(fes.ndofs)
+    a.Mult(dev.to_device(xs), y)
+    dev.sync()
+    op_norm = float(np.linalg.norm(host(y)))
+    assert abs(op_norm - ref["op_norm"]) < 1e-12 * ref["op_norm"], (op_norm, ref["op_norm"])
+    ess = fes.GetEssentialTrueDofs()
+    b = m.LinearForm(dev, fes).Assemble()
+    A, _, B = a.FormLinearSystem(ess, dev.zeros(fes.ndofs), b)
+    M = m.OperatorJacobiSmoother(a, ess)
+    cg = m.CGSolver()
+    cg.SetRelTol(0.0); cg.SetAbsTol(0.0); cg.SetMaxIter(32)
+    cg.SetOperator(A); cg.SetPreconditioner(M)
+    X = dev.zeros(fes.ndofs)
+    cg.Mult(B, X)
+    dev.sync()
+    assert cg.GetNumIterations() == ref["pcg_iters"]
+    x_norm = float(np.linalg.norm(host(X)))
+    assert abs(x_norm - ref["pcg_x_norm"]) < 1e-9 * ref["pcg_x_norm"], (x_norm, ref["pcg_x_norm"])
+    # relative to the initial norm: a solve converged to round-off (BP1) ends on noise
+    assert abs(cg.GetFinalNorm() - ref["pcg_final_norm"]) < 1e-9 * ref["pcg_initial_norm"]
+    a.close(); it.close()
+
+
+@pytest.mark.parametrize("kind,dim,D1D,Q1D", [("diffusion", 3, 14, 16), ("mass", 3, 11, 12), ("diffusion", 2, 12, 14),
+                                               ("mass", 2, 16, 16), ("diffusion", 3, 3, 7)])
+def test_diagonal_out_of_table_sizes(dev, kind, dim, D1D, Q1D):
+    """(D1D, Q1D) outside the dispatch table run the run-time sized kernels; above 48 KB of shared
+    memory they must opt in (14 x 16 diffusion needs 116 KB) instead of failing at launch."""
+    import mfem_b200 as m
+    from oracle import oracle as orc
+    rng = np.random.default_rng(11)
+    NE = 3
+    nq, ncomp = Q1D ** dim, (1 if kind == "mass" else (6 if dim == 3 else 3))
+    B, G = rng.random(Q1D * D1D), rng.random(Q1D * D1D) - 0.5
+    W = rng.random(nq) + 0.5
+    it = m.MassIntegrator() if kind == "mass" else m.DiffusionIntegrator()
+    if kind == "mass":
+        detJ = rng.random(nq * NE) + 0.5
+        it.assemble_from_factors(dev, dim, D1D, Q1D, NE, B, None, W, detJ=detJ)
+    else:
+        J = rng.random(nq * dim * dim * NE) + np.tile(np.repeat(np.eye(dim).ravel() * 3.0, nq), NE)
+        it.assemble_from_factors(dev, dim, D1D, Q1D, NE, B, G, W, J=J)
+    D = it.pa_data()
+    assert D.size == nq * ncomp * NE
+    de = dev.zeros(D1D ** dim * NE)
+    ref = (orc.mass_diag(dim, D1D, Q1D, NE, B, D) if kind == "mass"
+           else orc.diffusion_diag(dim, D1D, Q1D, NE, B, G, D))
+    it.AssembleDiagonalPA(de)
+    assert relerr(host(de), ref) < TOL
+    it.AssembleDiagonalPA(de)  # accumulates
+    assert relerr(host(de), 2 * ref) < TOL
+    it.close()
