@@ -6,8 +6,13 @@
 // path and the B200 path behind the same interfaces (adapter/b200_mfem.hpp) -- and checks
 //   seam 3: MFEM's PABilinearFormExtension::Mult with the b200 integrator == MFEM's   (1e-12)
 //   seam 1: fused b200::PAOperator::Mult == MFEM's a.Mult, AssembleDiagonal          (1e-12)
+//   seam 2: the ex1 driver itself (examples/ex1.cpp:203-268) with `b200::BilinearForm` as the only
+//           changed type: STOCK integrators, a.Assemble(), a.FormLinearSystem(), MFEM's own
+//           OperatorJacobiSmoother M(a, ess), PCG(*A, M, B, X, ...), a.RecoverFEMSolution()
 //   solve : b200::CGSolver iteration count within +-1 of mfem::CGSolver, same solution.
-// usage: ex1_b200 [-o order] [-n elems_per_side | -m mesh -r refinements] [-k mass|diffusion]
+// -d cuda (an MFEM built with MFEM_USE_CUDA, oracle/_ref_cuda): device-resident mode, every call
+// takes MFEM's own device pointers (x.Read() / y.Write()); -d cpu: host-MFEM mode.
+// usage: ex1_b200 [-d cpu|cuda] [-o order] [-n elems_per_side | -m mesh -r refinements] [-k mass|diffusion]
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -29,7 +34,9 @@ int main(int argc, char *argv[])
    int order = 3, n = 6, ref = 0, vdim = 1;
    const char *mesh_file = "";
    const char *kind = "diffusion";
+   const char *device_config = "cpu";
    OptionsParser args(argc, argv);
+   args.AddOption(&device_config, "-d", "--device", "MFEM device configuration string (examples/ex1.cpp:76)");
    args.AddOption(&order, "-o", "--order", "H1 order");
    args.AddOption(&n, "-n", "--elems", "elements per side of the Cartesian hex mesh");
    args.AddOption(&mesh_file, "-m", "--mesh", "mesh file (instead of the Cartesian mesh)");
@@ -38,7 +45,9 @@ int main(int argc, char *argv[])
    args.AddOption(&vdim, "-vd", "--vdim", "vector dimension (3: CEED BP2/BP4 style vector problem, byVDIM)");
    args.Parse();
    if (!args.Good()) { args.PrintUsage(std::cout); return 1; }
-   Device device("cpu"); // MFEM itself stays on the host ("host-MFEM" mode)
+   Device device(device_config); // "cpu": host-MFEM mode; "cuda": device-resident mode
+   device.Print();
+   std::printf("b200 memory mode: %s\n", b200::DeviceMode() ? "device-resident (MFEM device pointers)" : "host-MFEM (adapter-owned copies)");
 
    Mesh mesh = strlen(mesh_file) ? Mesh(mesh_file, 1, 1)
                : Mesh::MakeCartesian3D(n, n, n, Element::HEXAHEDRON);
@@ -137,6 +146,50 @@ int main(int argc, char *argv[])
    std::printf("  PCG iterations: MFEM %d, b200 %d\n", cg.GetNumIterations(), cg2.GetNumIterations());
    check("PCG iteration count |difference|", std::abs(cg.GetNumIterations() - cg2.GetNumIterations()), 1.0);
    check("PCG solution", relerr(X2, X), 1e-5);
+
+   // seam 2: the ex1 driver, unchanged except for the form's type (stock integrator, stock
+   // Jacobi smoother, FormLinearSystem / RecoverFEMSolution of the form itself)
+   if (vdim == 1)
+   {
+      b200::BilinearForm a(&fes);
+      a.SetAssemblyLevel(AssemblyLevel::PARTIAL);
+      if (mass) { a.AddDomainIntegrator(new MassIntegrator(one)); }
+      else { a.AddDomainIntegrator(new DiffusionIntegrator(one)); }
+      a.Assemble();
+      check("seam 2: the form took the fused path (1 = yes)", a.Fused() ? 0.0 : 1.0, 0.0);
+      a.Mult(x, y);
+      check("seam 2: b200::BilinearForm::Mult (stock integrator)", relerr(y, y_ref), 1e-12);
+      a.AssembleDiagonal(d);
+      check("seam 2: b200::BilinearForm::AssembleDiagonal", relerr(d, d_ref), 1e-12);
+      GridFunction u2(&fes);
+      u2 = 0.0;
+      Vector b2(b);
+      OperatorPtr A2;
+      Vector Bs, Xs;
+      a.FormLinearSystem(ess, u2, b2, A2, Xs, Bs);
+      A2->Mult(x, yc);
+      check("seam 2: FormLinearSystem operator (fused, constrained)", relerr(yc, yc_ref), 1e-12);
+      check("seam 2: FormLinearSystem right-hand side", relerr(Bs, B), 1e-12);
+      OperatorJacobiSmoother M2(a, ess); // MFEM's own smoother over the form's (fused) diagonal
+      b200::PCG(*A2, M2, Bs, Xs, 0, 2000, 1e-12, 0.0);
+      a.RecoverFEMSolution(Xs, b2, u2);
+      check("seam 2: PCG(*A, M, B, X) + RecoverFEMSolution", relerr(u2, X), 1e-5);
+      // the same through mfem::CGSolver: MFEM's own solver driving the fused operator
+      CGSolver cgm;
+      cgm.SetRelTol(1e-6); cgm.SetAbsTol(0.0); cgm.SetMaxIter(2000); cgm.SetPrintLevel(-1);
+      cgm.SetOperator(*A2);
+      cgm.SetPreconditioner(M2);
+      Vector X4(N);
+      X4.UseDevice(true);
+      X4 = 0.0;
+      cgm.Mult(Bs, X4);
+      check("seam 2: mfem::CGSolver over the fused operator, iteration count |difference|",
+            std::abs(cg.GetNumIterations() - cgm.GetNumIterations()), 1.0);
+      check("seam 2: mfem::CGSolver over the fused operator, solution", relerr(X4, X), 1e-5);
+      // MultTranspose: the same operator for symmetric coefficients (bilininteg_diffusion_pa.cpp:95)
+      a.MultTranspose(x, y);
+      check("seam 2: MultTranspose (symmetric coefficient)", relerr(y, y_ref), 1e-12);
+   }
 
    // spatially varying scalar and full-matrix coefficients through the reference's own
    // CoefficientVector projection (seam 3 + the fused operator)

@@ -330,6 +330,12 @@ def main():
             tm = torch.tensor([ms], dtype=torch.float64, device=dev.tdev)
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             ms = float(tm.item())
+        if dist and kt is not None:
+            # the operator kernel time of the SLOWEST rank (rank 0 owns every shared dof and has no
+            # boundary-element launch: it is the lightest rank, not the one to report)
+            tk = torch.tensor([kt[0]], dtype=torch.float64, device=dev.tdev)
+            dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+            kt = (float(tk.item()), kt[1], kt[0])
         return ms, launches, kt
 
     from mfem_b200.capi import call as capi_call
@@ -389,7 +395,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "kernel": "pa_apply_3d_eo_kernel (fused gather + even-odd G^T D G + scatter)",
-                         "kernel_ms": k_ms, "kernel_launches": kt[1],
+                         "kernel_ms": k_ms, "kernel_ms_is": "max over ranks" if a.gpus > 1 else "this GPU",
+                         "kernel_ms_rank0": (kt[2] / max(n_applies, 1)) if len(kt) > 2 else k_ms,
+                         "kernel_launches": kt[1],
                          "launches_per_application": kt[1] / max(n_applies, 1),
                          "kernel_share_of_step": kt[0] / ms,
                          "algorithmic_bytes_per_launch": ab,
@@ -408,6 +416,31 @@ def main():
             except Exception as ex:  # the baseline is reported, never required
                 line["cpu_baseline"] = {"value": None, "unit": "GDOF/s", "cores": 0, "kind": "reference",
                                         "sample": f"failed: {ex}"}
+    if a.gpus == 1:
+        # free the headline problem before the baselines and the table
+        form.close(); it.close()
+        del A, B, X, M, cg, b, b_l, B_in, B_h, X_h, form, it
+        torch.cuda.empty_cache()
+        if not a.no_gpu_baseline:
+            line["gpu_baseline"] = run_gpu_baseline(w, a.iters)
+            gb = line["gpu_baseline"]
+            if "value" in gb:
+                gb["b200_over_reference"] = {"pcg": line["value"] / gb["value"],
+                                             "operator": line["roofline"]["operator_gdofs"] / gb["operator_gdofs"],
+                                             "operator_vs_element_kernel_alone":
+                                             line["roofline"]["operator_gdofs"] / gb["kernel_gdofs"]}
+        if not a.no_anchor and w["bp"] == 3 and p == 4 and not a.n:
+            # the per-GPU problem of the --gpus N > 1 runs (116^3 hexes), on one GPU: the equal-size
+            # anchor for weak-scaling efficiency (the headline N=1 config is the larger 133^3 one)
+            line["weak_anchor"] = anchor_run(m, torch, dev, w, 116, a.iters, a.steps, a.warmup)
+        if not a.no_sweep:
+            t_sw = time.time()
+            line["sweep"] = {"what": "BP1/BP3/BP5 x p=1..8, Jacobi-PCG GDOF/s and the fused operator's share of the "
+                                     f"HBM roofline, ~{a.sweep_dofs:.0e} dofs per case, {a.iters} fixed iterations, "
+                                     "2 timed solves after 2 warm-up solves",
+                             "rows": sweep_table(m, torch, dev, capi_call, peak, a.sweep_dofs, a.iters)}
+            line["sweep"]["seconds"] = round(time.time() - t_sw, 1)
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if parity is not None and parity.get("ok") is False:
         if rank == 0:
@@ -418,6 +451,143 @@ def main():
         if halo:
             halo.close()
         dist.destroy_process_group()
+
+
+def ref_cuda_driver_path():
+    p = os.path.join(ROOT, "oracle", "_ref_cuda", "ref_driver_cuda")
+    return p if os.path.isfile(p) and os.access(p, os.X_OK) else None
+
+
+REF_KERNEL = {"diffusion": "SmemPADiffusionApply3D (fem/integ/bilininteg_diffusion_kernels.hpp:989-1215)",
+              "mass": "SmemPAMassApply3D (fem/integ/bilininteg_mass_kernels.hpp:815-1050)"}
+
+
+def run_gpu_baseline(w, iters, n=None):
+    """The UNMODIFIED reference's own CUDA backend (MFEM_USE_CUDA, generic MFEM_FORALL kernels,
+    oracle/Makefile target ref_cuda) on this GPU, same BP, at the largest size its 32-bit offsets and
+    its resident Jacobians allow: AddMultPA on E-vectors (the element kernel alone), BilinearForm::Mult
+    (restriction + kernel + restriction^T) and the Jacobi-PCG solve.  A baseline, like cpu_baseline."""
+    drv = ref_cuda_driver_path()
+    if not drv:
+        return {"unavailable": "oracle/_ref_cuda/ref_driver_cuda not built (make -C oracle ref_cuda)"}
+    p = w["p"]
+    if n is None:
+        # 9 Q^3 doubles of J per element in one 32-bit sized Vector (mesh/mesh.cpp:15467), <= ~64 M dofs
+        n_j = int(((2 ** 31 - 1) // (9 * w["q1d"] ** 3)) ** (1 / 3))
+        n = int(min(w["n"], n_j, round(64e6 ** (1 / 3) / p)))
+    cmd = [drv, "bench", "--mode", "all", "--dim", "3", "--n", str(n), "--p", str(p), "--kind", w["kind"],
+           "--quad", "gll" if w["gll"] else "gl", "--curved", str(int(w["curved"])), "--iters", str(iters),
+           "--reps", "3", "--jacobi", "1"]
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900,
+                           env=dict(os.environ, REF_DRIVER_DEVICE="cuda"))
+        if r.returncode != 0:
+            err = r.stderr.decode(errors="replace").strip().splitlines()
+            why = next((ln.strip() for ln in err if "-->" in ln), err[-1] if err else "no output")
+            return {"unavailable": f"the reference's CUDA backend failed at p={p}, n={n}: {why}"}
+        j = json.loads(r.stdout.decode().strip().splitlines()[-1])
+    except Exception as ex:  # a baseline is reported, never required
+        return {"unavailable": f"{type(ex).__name__}: {ex}"}
+    nd = j["ndofs"]
+    return {"value": j["dofs_iters_per_s"] / 1e9, "unit": "GDOF/s",
+            "operator_gdofs": nd / j["mult_seconds"] / 1e9, "kernel_gdofs": nd / j["kernel_seconds"] / 1e9,
+            "operator_ms": j["mult_seconds"] * 1e3, "kernel_ms": j["kernel_seconds"] * 1e3,
+            "kernel": REF_KERNEL[w["kind"]] + ("; (9,10) is not in its dispatch table: thread-per-element fallback"
+                                              if p == 8 else ""),
+            "config": f"BP{w['bp']} p={p} {n}^3 hexes, {nd} dofs, MFEM -pa -d cuda (sm_100), {iters} Jacobi-PCG "
+                      f"iterations", "dofs": nd, "final_norm": j["final_norm"]}
+
+
+def sweep_table(m, torch, dev, capi_call, peak, dofs, iters):
+    """The BASELINE metric as a table (tests/benchmarks/bench_ceed.cpp:95-176, 301-357): BP1 / BP3 / BP5,
+    p = 1..8, ~`dofs` dofs each: Jacobi-PCG GDOF/s and the fused operator's share of the HBM roofline."""
+    import ctypes as C
+    rows = []
+    for bp in (1, 3, 5):
+        for p in range(1, 9):
+            gll = bp == 5
+            n = max(2, round(dofs ** (1 / 3) / p))
+            fes = m.FiniteElementSpace(m.Mesh.MakeCartesian3D(n, n, n), m.H1_FECollection(p, 3))
+            ir = m.IntegrationRules(gll).Get(3, 2 * p - 1 if gll else 2 * p + 3)
+            it = (m.MassIntegrator if bp == 1 else m.DiffusionIntegrator)(1.0, ir)
+            form = m.BilinearForm(dev, fes)
+            form.AddDomainIntegrator(it)
+            form.Assemble()
+            nd = fes.ndofs
+            ess = fes.GetEssentialTrueDofs()
+            b = m.LinearForm(dev, fes).Assemble()
+            A, _, B = form.FormLinearSystem(ess, dev.zeros(nd), b)
+            M = m.OperatorJacobiSmoother(form, ess)
+            cg = m.CGSolver()
+            cg.SetRelTol(0.0); cg.SetAbsTol(0.0); cg.SetMaxIter(iters)
+            cg.SetOperator(A); cg.SetPreconditioner(M)
+            cg.check_every = iters
+            X = dev.zeros(nd)
+            del fes.elem_dof
+            for _ in range(2):
+                cg.Mult(B, X)
+            torch.cuda.synchronize()
+            capi_call("b2f_ctx_kernel_timing", dev.ctx, 1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            steps = 2
+            e0.record()
+            for _ in range(steps):
+                cg.Mult(B, X)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            tot, cnt = C.c_double(), C.c_int()
+            capi_call("b2f_ctx_kernel_time", dev.ctx, C.byref(tot), C.byref(cnt))
+            capi_call("b2f_ctx_kernel_timing", dev.ctx, 0)
+            k_ms = tot.value / max(cnt.value, 1)
+            k = 1 if bp == 1 else 6
+            ab = (k * ir.nq1d ** 3 * 8 + 4 * (p + 1) ** 3) * fes.ne + 16 * nd
+            rows.append({"bp": bp, "p": p, "n": n, "dofs": nd,
+                         "pcg_gdofs": round(nd * iters * steps / (ms * 1e-3) / 1e9, 3),
+                         "operator_gdofs": round(nd / (k_ms * 1e-3) / 1e9, 3), "operator_ms": round(k_ms, 4),
+                         "operator_frac_of_hbm_roofline": round(ab / (k_ms * 1e-3) / 1e9 / peak, 4)})
+            form.close(); it.close()
+            del A, B, X, M, cg, b, form, fes
+            torch.cuda.empty_cache()
+    return rows
+
+
+def anchor_run(m, torch, dev, w, n, iters, steps, warmup):
+    """One more device-resident timing of the same BP at `n`^3 hexes on this GPU."""
+    p = w["p"]
+    fes = m.FiniteElementSpace(m.Mesh.MakeCartesian3D(n, n, n), m.H1_FECollection(p, 3))
+    ir = m.IntegrationRules(gll=w["gll"]).Get(3, 2 * p - 1 if w["gll"] else 2 * p + 3)
+    it = (m.MassIntegrator if w["kind"] == "mass" else m.DiffusionIntegrator)(1.0, ir)
+    form = m.BilinearForm(dev, fes)
+    form.AddDomainIntegrator(it)
+    form.Assemble()
+    nd = fes.ndofs
+    ess = fes.GetEssentialTrueDofs()
+    b = m.LinearForm(dev, fes).Assemble()
+    A, _, B = form.FormLinearSystem(ess, dev.zeros(nd), b)
+    M = m.OperatorJacobiSmoother(form, ess)
+    cg = m.CGSolver()
+    cg.SetRelTol(0.0); cg.SetAbsTol(0.0); cg.SetMaxIter(iters)
+    cg.SetOperator(A); cg.SetPreconditioner(M)
+    cg.check_every = iters
+    X = dev.zeros(nd)
+    del fes.elem_dof
+    for _ in range(warmup):
+        cg.Mult(B, X)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        cg.Mult(B, X)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out = {"workload": f"BP{w['bp']} p={p} {n}^3 hexes, {nd} dofs on 1 GPU (the per-GPU block of --gpus N > 1)",
+           "value": nd * iters * steps / (ms * 1e-3) / 1e9, "unit": "GDOF/s", "ms_per_step": ms / steps, "dofs": nd}
+    form.close(); it.close()
+    del A, B, X, M, cg, b, form, fes
+    torch.cuda.empty_cache()
+    return out
 
 
 def serial_dof_of_lattice(m, np, n, p):

@@ -345,6 +345,20 @@ int b2f_halo_create(b2f_ctx *ctx, const void *nccl_id128_h, int rank, int nranks
                     const int *ext_ldof_h,           /* ldofs owned by each neighbour      */
                     b2f_halo **out);
 void b2f_halo_destroy(b2f_halo *h);
+/* The ParFiniteElementSpace binding: b2f_halo_create's tables from the reference's own group
+ * tables -- GroupTopology (master rank and the group's number on the master, member ranks),
+ * GroupCommunicator::GroupLDofTable and the ldof -> ltdof map (-1 = not owned).  Restates
+ * GroupCommunicator::Finalize / GetNeighborLTDofTable / GetNeighborLDofTable
+ * (general/communication.cpp:368-612) and the table part of DeviceConformingProlongationOperator's
+ * constructor (fem/pfespace.cpp:5625-5690); host code, no MPI (include/b200fem_groups.hpp is the
+ * header-only C++ form an MPI adapter calls).  Group 0 (the local group) is ignored.  Two-call
+ * pattern: array arguments may be NULL; sizes_h[4] = {n_tdofs, n_nbr, n_shr, n_ext}. */
+int b2f_halo_tables_from_groups_h(int my_rank, int n_groups, const int *group_master_rank_h,
+                                  const int *group_master_group_h, const int *group_rank_offsets_h,
+                                  const int *group_ranks_h, const int *group_ldof_offsets_h,
+                                  const int *group_ldofs_h, int n_ldofs, const int *ldof_ltdof_h,
+                                  int *sizes_h, int *ltdof_ldof_h, int *nbr_rank_h, int *shr_offsets_h,
+                                  int *shr_ltdof_h, int *ext_offsets_h, int *ext_ldof_h);
 /* Peer-memory exchange (one process per GPU on one NVLink/NVSwitch node): instead of
  * pack + MPI_Isend/Irecv (pfespace.cpp:5786-5803) or pack + ncclSend/ncclRecv, the pack
  * kernel stores straight into the neighbour's receive buffer through a CUDA-IPC mapping and

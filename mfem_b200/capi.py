@@ -60,6 +60,8 @@ PROTOTYPES = {
     "b2f_h1_dof_to_quad_h": (C.c_int, [C.c_int, C.c_int, vp, vp, vp]),
     "b2f_tensor_weights_h": (C.c_int, [C.c_int, C.c_int, vp, vp]),
     "b2f_vector_randomize_h": (C.c_int, [vp, i64, C.c_int]),
+    "b2f_halo_tables_from_groups_h": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, vp,
+                                                vp, vp, vp, vp, vp, vp, vp]),
     "b2f_cartesian_h1_space_h": (C.c_int, [C.c_int] * 6 + [c_int_p, c_int_p, vp, vp, c_int_p, vp, vp]),
     "b2f_restriction_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp,
                                          C.POINTER(vp)]),

@@ -251,9 +251,13 @@ void h1_number(int dim, int p, int nverts, const std::vector<int> &elem_vert, H1
    std::vector<int> edge_slot; // direct table: 3*min vertex + direction
    if (vstride) { edge_slot.assign((size_t)3 * nverts, -1); }
    else { edge_id.reserve((size_t)ne * 4); }
-   std::vector<int> el_edge((size_t)ne * nedge);
+   // (order 1 in 3D has no edge or face dofs: the edge numbering is not needed at all, and on a
+   // structured grid neither is the face numbering -- the boundary dofs are the boundary vertices)
+   const bool need_edges = pm1 > 0 || dim == 2;
+   const bool need_faces = dim == 3 && (pm1 > 0 || !vstride);
+   std::vector<int> el_edge(need_edges ? (size_t)ne * nedge : 0);
    int nedges = 0;
-   for (int e = 0; e < ne; e++)
+   for (int e = 0; need_edges && e < ne; e++)
    {
       const int *v = &elem_vert[(size_t)e * nv];
       for (int j = 0; j < nedge; j++)
@@ -292,7 +296,7 @@ void h1_number(int dim, int p, int nverts, const std::vector<int> &elem_vert, H1
    int nfaces = 0;
    std::vector<int> el_face, face_count;
    std::vector<std::array<int, 4>> face_base; // vertices of the owning element's local face
-   if (dim == 3)
+   if (need_faces)
    {
       std::unordered_map<FaceKey, int, FaceHash> face_id;
       std::vector<int> face_slot; // direct table: 3*min vertex + normal direction
@@ -355,14 +359,14 @@ void h1_number(int dim, int p, int nverts, const std::vector<int> &elem_vert, H1
       int *out = &S.elem_dof[(size_t)e * dof];
       int o = 0;
       for (int i = 0; i < nv; i++) { out[o++] = v[i]; }
-      for (int j = 0; j < nedge; j++)
+      for (int j = 0; pm1 > 0 && j < nedge; j++)
       {
          const int *ev = dim == 2 ? kQuadEdge[j] : kHexEdge[j];
          const bool fwd = v[ev[0]] < v[ev[1]];
          const int base = nvdofs + el_edge[(size_t)e * nedge + j] * pm1;
          for (int i = 0; i < pm1; i++) { out[o++] = base + (fwd ? i : pm1 - 1 - i); }
       }
-      for (int j = 0; j < nface; j++)
+      for (int j = 0; pm1 > 0 && j < nface; j++)
       {
          const int f = el_face[(size_t)e * 6 + j];
          const std::array<int, 4> &bv = face_base[f];
@@ -392,7 +396,20 @@ void h1_number(int dim, int p, int nverts, const std::vector<int> &elem_vert, H1
    });
    // --- boundary dofs (all boundary attributes essential, as ex1.cpp:165-183 / bench_ceed)
    std::vector<char> mark(S.ndofs, 0);
-   for (int e = 0; e < ne; e++)
+   if (dim == 3 && !need_faces)
+   {
+      // structured grid, order 1: the boundary vertices, from their grid coordinates
+      const int sy = vstride[1], sz = vstride[2], ny1 = sz / sy, nz1 = nverts / sz;
+      parallel_for(nverts, [&](int64_t b, int64_t e_)
+      {
+         for (int64_t id = b; id < e_; id++)
+         {
+            const int x = (int)(id % sy), y = (int)((id / sy) % ny1), z = (int)(id / sz);
+            mark[id] = x == 0 || x == sy - 1 || y == 0 || y == ny1 - 1 || z == 0 || z == nz1 - 1;
+         }
+      });
+   }
+   for (int e = 0; (dim == 2 || need_faces) && e < ne; e++)
    {
       const int *v = &elem_vert[(size_t)e * nv];
       const int *ed = &S.elem_dof[(size_t)e * dof];
@@ -467,39 +484,51 @@ extern "C" int b2f_cartesian_h1_space_h(int dim, int nx, int ny, int nz, int p, 
    if (dof_map_h) { h1_dof_map(dim, p, dof_map_h); }
    if (!elem_dof_h && !bdr_dofs_h && !elem_vertices_h && !nbdr) { return B2F_OK; }
 
+   // The caller asks in steps (sizes; element table, vertices and number of boundary dofs;
+   // boundary dofs): the boundary list of the last numbering is kept so that the last step is a copy.
+   struct BdrCache { bool valid = false; int key[6]; std::vector<int> bdr; };
+   static thread_local BdrCache cache;
+   const int key[6] = {dim, nx, ny, nz, p, sfc_ordering};
+   if (!elem_dof_h && !elem_vertices_h && cache.valid && std::equal(key, key + 6, cache.key))
+   {
+      if (nbdr) { *nbdr = (int)cache.bdr.size(); }
+      if (bdr_dofs_h) { std::copy(cache.bdr.begin(), cache.bdr.end(), bdr_dofs_h); }
+      return B2F_OK;
+   }
    const std::vector<V3> ord = grid_order(dim, nx, ny, nz, sfc_ordering != 0);
    const int nverts = dim == 2 ? (nx + 1) * (ny + 1) : (nx + 1) * (ny + 1) * (nz + 1);
    auto vtx = [&](int x, int y, int z) { return x + (y + z * (ny + 1)) * (nx + 1); };
    std::vector<int> ev((size_t)nel * nv);
-   for (int64_t e = 0; e < nel; e++)
+   parallel_for(nel, [&](int64_t e_begin, int64_t e_end)
    {
-      const V3 c = ord[e];
-      const int(*vc)[3] = dim == 2 ? kQuadVert : kHexVert;
-      for (int k = 0; k < nv; k++) { ev[e * nv + k] = vtx(c.x + vc[k][0], c.y + vc[k][1], c.z + vc[k][2]); }
-   }
+      for (int64_t e = e_begin; e < e_end; e++)
+      {
+         const V3 c = ord[e];
+         const int(*vc)[3] = dim == 2 ? kQuadVert : kHexVert;
+         for (int k = 0; k < nv; k++) { ev[e * nv + k] = vtx(c.x + vc[k][0], c.y + vc[k][1], c.z + vc[k][2]); }
+      }
+   });
    if (elem_vertices_h)
    {
       // nodes E-vector of the order-1 mesh: (2^dim lexicographic, dim, NE); coordinates
       // computed as the reference does, ((real_t) x / nx) * sx with sx = 1
-      for (int64_t e = 0; e < nel; e++)
+      parallel_for(nel, [&](int64_t e_begin, int64_t e_end)
       {
-         const V3 c = ord[e];
-         for (int k = 0; k < nv; k++)
+         for (int64_t e = e_begin; e < e_end; e++)
          {
-            const int ix = c.x + (k & 1), iy = c.y + ((k >> 1) & 1), iz = c.z + ((k >> 2) & 1);
-            double *o = elem_vertices_h + e * nv * dim;
-            o[k + nv * 0] = ((double)ix / nx) * 1.0;
-            o[k + nv * 1] = ((double)iy / ny) * 1.0;
-            if (dim == 3) { o[k + nv * 2] = ((double)iz / nz) * 1.0; }
+            const V3 c = ord[e];
+            for (int k = 0; k < nv; k++)
+            {
+               const int ix = c.x + (k & 1), iy = c.y + ((k >> 1) & 1), iz = c.z + ((k >> 2) & 1);
+               double *o = elem_vertices_h + e * nv * dim;
+               o[k + nv * 0] = ((double)ix / nx) * 1.0;
+               o[k + nv * 1] = ((double)iy / ny) * 1.0;
+               if (dim == 3) { o[k + nv * 2] = ((double)iz / nz) * 1.0; }
+            }
          }
-      }
+      });
    }
    if (!elem_dof_h && !bdr_dofs_h && !nbdr) { return B2F_OK; }
-   // The caller asks in steps (sizes; element table and number of boundary dofs; boundary dofs):
-   // the boundary list of the last numbering is kept so that the last step does not redo it.
-   struct BdrCache { bool valid = false; int key[6]; std::vector<int> bdr; };
-   static thread_local BdrCache cache;
-   const int key[6] = {dim, nx, ny, nz, p, sfc_ordering};
    if (!elem_dof_h && cache.valid && std::equal(key, key + 6, cache.key))
    {
       if (nbdr) { *nbdr = (int)cache.bdr.size(); }

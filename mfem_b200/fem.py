@@ -249,11 +249,10 @@ class FiniteElementSpace:
             self.elem_vertices = np.empty(self.ne * nv * dim)
             call("b2f_cartesian_h1_space_h", dim, mesh.nx, mesh.ny, mesh.nz, p, int(mesh.sfc),
                  C.byref(ne), C.byref(nd), _np_ptr(self.elem_dof), _np_ptr(self.dof_map),
-                 C.byref(nb), None, None)
+                 C.byref(nb), None, _np_ptr(self.elem_vertices))
             self.bdr_dofs = np.empty(nb.value, np.int32)
             call("b2f_cartesian_h1_space_h", dim, mesh.nx, mesh.ny, mesh.nz, p, int(mesh.sfc),
-                 C.byref(ne), C.byref(nd), None, None, C.byref(nb), _np_ptr(self.bdr_dofs),
-                 _np_ptr(self.elem_vertices))
+                 C.byref(ne), C.byref(nd), None, None, C.byref(nb), _np_ptr(self.bdr_dofs), None)
             self.ntdofs = self.ndofs
         else:
             px, py, pz = mesh.part

@@ -933,6 +933,7 @@ static int do_dump_cheb(const Args &A, const char *out)
 // Timing of the reference CPU path.  Prints one JSON object.
 //   mode=mult : y = A x (BilinearForm::Mult, PA) repeated `reps` times
 //   mode=kernel : AddMultPA on E-vectors (bench_ceed.cpp BK style), `reps` times
+//   mode=all  : kernel, mult and pcg on one problem set-up (mult_seconds / kernel_seconds / seconds)
 //   mode=pcg  : bench_ceed.cpp BP style: CG (optionally Jacobi), fixed `iters` iterations
 static int do_bench(const Args &A)
 {
@@ -949,7 +950,9 @@ static int do_bench(const Args &A)
    x.UseDevice(true); y.UseDevice(true);
    x.Randomize(1);
    double sec = 0, ynorm = 0, final_norm = 0, initial_norm = 0; int its = 0;
-   if (mode == "mult")
+   double sec_mult = 0, sec_kernel = 0; // mode=all: the three timings of one problem set-up
+   const bool all = mode == "all";
+   if (mode == "mult" || all)
    {
       P.a->Mult(x, y); // warm-up
       MFEM_DEVICE_SYNC;
@@ -957,9 +960,10 @@ static int do_bench(const Args &A)
       for (int i = 0; i < reps; i++) { P.a->Mult(x, y); }
       MFEM_DEVICE_SYNC;
       sec = (now() - t1) / reps; its = 1;
+      sec_mult = sec;
       ynorm = y.Norml2();
    }
-   else if (mode == "kernel")
+   if (mode == "kernel" || all)
    {
       // BK style (bench_ceed.cpp:258-298): AddMultPA on E-vectors only, i.e. the reference's
       // SmemPADiffusionApply3D / SmemPAMassApply3D (or its fallback) without the restriction.
@@ -975,11 +979,13 @@ static int do_bench(const Args &A)
       for (int i = 0; i < reps; i++) { P.bfi->AddMultPA(xe, ye); }
       MFEM_DEVICE_SYNC;
       sec = (now() - t1) / reps; its = 1;
+      sec_kernel = sec;
       ye *= 1.0 / reps;
-      ynorm = ye.Norml2();
+      if (!all) { ynorm = ye.Norml2(); }
    }
-   else
+   if (mode == "pcg" || all)
    {
+      sec = 0;
       Array<int> ess_bdr(P.mesh.bdr_attributes.Max()); ess_bdr = 1;
       Array<int> ess;
       fes.GetEssentialTrueDofs(ess_bdr, ess);
@@ -1016,12 +1022,15 @@ static int do_bench(const Args &A)
       ynorm = X.Norml2();
       final_norm = cg.GetFinalNorm(); initial_norm = cg.GetInitialNorm();
    }
-   const char *dev = getenv("MFEM_DEVICE");
+   const char *dev = getenv("REF_DRIVER_DEVICE");
+   if (!dev) { dev = getenv("MFEM_DEVICE"); }
    std::printf("{\"mode\": \"%s\", \"ndofs\": %d, \"ne\": %d, \"p\": %d, \"iters\": %d, "
                "\"seconds\": %.6e, \"setup_seconds\": %.3f, \"dofs_iters_per_s\": %.6e, "
-               "\"norm\": %.17g, \"final_norm\": %.17g, \"initial_norm\": %.17g, \"device\": \"%s\"}\n",
+               "\"norm\": %.17g, \"final_norm\": %.17g, \"initial_norm\": %.17g, "
+               "\"mult_seconds\": %.6e, \"kernel_seconds\": %.6e, \"device\": \"%s\"}\n",
                mode.c_str(), ndofs, fes.GetNE(), P.p, its, sec, t_setup,
-               (double)ndofs * its / sec, ynorm, final_norm, initial_norm, dev ? dev : "cpu");
+               (double)ndofs * its / sec, ynorm, final_norm, initial_norm, sec_mult, sec_kernel,
+               dev ? dev : "cpu");
    return 0;
 }
 
@@ -1032,7 +1041,11 @@ int main(int argc, char **argv)
       std::fprintf(stderr, "usage: ref_driver dump <out.bin> [--key val ...] | bench [--key val ...]\n");
       return 1;
    }
-   const char *dev = getenv("MFEM_DEVICE"); // "omp" uses all host threads (device.cpp:145)
+   // MFEM_DEVICE (read by the reference itself, device.cpp:145): "omp" uses all host threads.
+   // REF_DRIVER_DEVICE: configured here, in main, as examples/ex1.cpp does with -d (the CUDA
+   // backend must not be brought up from the singleton's static initialiser).
+   const char *dev = getenv("REF_DRIVER_DEVICE");
+   if (!dev) { dev = getenv("MFEM_DEVICE"); }
    Device device(dev ? dev : "cpu");
    string cmd = argv[1];
    if (cmd == "dump")

@@ -221,3 +221,91 @@ def test_partition_rejects_bad_arguments():
         m.FiniteElementSpace(m.Mesh(3, 2, 2, 2, True, part=(3, 1, 1), rank=0), m.H1_FECollection(2, 3))
     with pytest.raises(B2FError):
         m.FiniteElementSpace(m.Mesh(3, 4, 4, 4, True, part=(2, 1, 1), rank=2), m.H1_FECollection(2, 3))
+
+
+@pytest.mark.parametrize("dim,n,p,grid", [(3, (4, 4, 4), 2, (2, 2, 2)), (3, (4, 2, 2), 3, (2, 1, 1)),
+                                          (2, (4, 4, 1), 3, (2, 2, 1)), (3, (6, 4, 2), 1, (2, 2, 1))])
+def test_halo_tables_from_group_tables(dim, n, p, grid):
+    """The ParFiniteElementSpace binding (b2f_halo_tables_from_groups_h / include/b200fem_groups.hpp):
+    hand-built GroupTopology / GroupCommunicator tables of a Cartesian partition -- groups = sets of
+    ranks sharing a dof, master = lowest rank, every rank numbering its groups in its OWN order --
+    must flatten to the same per-neighbour lists the Cartesian partitioner produces, and sender and
+    receiver must enumerate every pair's dofs in the same order."""
+    import ctypes as C
+    from mfem_b200.capi import call, vp
+    ranks = partition(dim, n, p, grid)
+    nr = len(ranks)
+    L = [p * n[a] + 1 for a in range(3)]
+    nlat = L[0] * L[1] * (L[2] if dim == 3 else 1)
+    holders = [[] for _ in range(nlat)]
+    for r, f in enumerate(ranks):
+        for pt in f.halo_tables["ldof_lattice"]:
+            holders[pt].append(r)
+    # every rank's groups: the sharing sets among its dofs, numbered by first appearance in a
+    # rank-dependent traversal (so group numbers differ from rank to rank, as in MFEM)
+    group_id = []
+    for r, f in enumerate(ranks):
+        ids, order = {}, np.argsort((f.halo_tables["ldof_lattice"] * (2 * r + 3)) % 1009, kind="stable")
+        for l in order:
+            s = tuple(holders[f.halo_tables["ldof_lattice"][l]])
+            if len(s) > 1 and s not in ids:
+                ids[s] = len(ids) + 1  # group 0 is the local group
+        group_id.append(ids)
+
+    def ptr(a):
+        return a.ctypes.data_as(vp)
+
+    out = []
+    for r, f in enumerate(ranks):
+        t, ids = f.halo_tables, group_id[r]
+        lat = t["ldof_lattice"]
+        ng = len(ids) + 1
+        sets = [(r,)] + [None] * len(ids)
+        for s, g in ids.items():
+            sets[g] = s
+        master_rank = np.array([min(s) for s in sets], np.int32)
+        master_group = np.array([0] + [group_id[min(s)][s] for s in sets[1:]], np.int32)
+        rank_off = np.zeros(ng + 1, np.int32)
+        rank_off[1:] = np.cumsum([len(s) for s in sets])
+        ranks_flat = np.array([q for s in sets for q in s], np.int32)
+        members = [[] for _ in range(ng)]
+        for l in np.argsort(lat, kind="stable"):       # a group's dofs in ascending lattice order
+            s = tuple(holders[lat[l]])
+            members[ids[s] if len(s) > 1 else 0].append(l)
+        members[0] = []                                 # the local group is ignored anyway
+        ldof_off = np.zeros(ng + 1, np.int32)
+        ldof_off[1:] = np.cumsum([len(mm) for mm in members])
+        ldofs_flat = np.array([l for mm in members for l in mm], np.int32)
+        ldof_ltdof = np.full(f.ndofs, -1, np.int32)
+        ldof_ltdof[t["ltdof_ldof"]] = np.arange(f.ntdofs, dtype=np.int32)
+        sizes = (C.c_int * 4)()
+        args = (r, ng, ptr(master_rank), ptr(master_group), ptr(rank_off), ptr(ranks_flat), ptr(ldof_off),
+                ptr(ldofs_flat), f.ndofs, ptr(ldof_ltdof))
+        call("b2f_halo_tables_from_groups_h", *args, sizes, None, None, None, None, None, None)
+        nt, nn, ns, nx = list(sizes)
+        h = dict(ltdof_ldof=np.empty(nt, np.int32), nbr_rank=np.empty(nn, np.int32),
+                 shr_offsets=np.empty(nn + 1, np.int32), shr_ltdof=np.empty(ns, np.int32),
+                 ext_offsets=np.empty(nn + 1, np.int32), ext_ldof=np.empty(nx, np.int32))
+        call("b2f_halo_tables_from_groups_h", *args, sizes, ptr(h["ltdof_ldof"]), ptr(h["nbr_rank"]),
+             ptr(h["shr_offsets"]), ptr(h["shr_ltdof"]), ptr(h["ext_offsets"]), ptr(h["ext_ldof"]))
+        out.append(h)
+        # against the Cartesian partitioner: same true dofs, same neighbours, same dof SETS per neighbour
+        assert np.array_equal(h["ltdof_ldof"], t["ltdof_ldof"])
+        assert sorted(h["nbr_rank"]) == sorted(t["nbr_rank"])
+        for k, q in enumerate(h["nbr_rank"]):
+            j = list(t["nbr_rank"]).index(q)
+            mine = h["shr_ltdof"][h["shr_offsets"][k]:h["shr_offsets"][k + 1]]
+            theirs = t["shr_ltdof"][t["shr_offsets"][j]:t["shr_offsets"][j + 1]]
+            assert sorted(mine) == sorted(theirs)
+            mine = h["ext_ldof"][h["ext_offsets"][k]:h["ext_offsets"][k + 1]]
+            theirs = t["ext_ldof"][t["ext_offsets"][j]:t["ext_offsets"][j + 1]]
+            assert sorted(mine) == sorted(theirs)
+    # pairwise order: what s sends to q is, point for point, what q expects from s
+    for s in range(nr):
+        for k, q in enumerate(out[s]["nbr_rank"]):
+            sent = out[s]["shr_ltdof"][out[s]["shr_offsets"][k]:out[s]["shr_offsets"][k + 1]]
+            pts_s = ranks[s].halo_tables["ldof_lattice"][out[s]["ltdof_ldof"][sent]]
+            j = list(out[q]["nbr_rank"]).index(s)
+            got = out[q]["ext_ldof"][out[q]["ext_offsets"][j]:out[q]["ext_offsets"][j + 1]]
+            pts_q = ranks[q].halo_tables["ldof_lattice"][got]
+            assert np.array_equal(pts_s, pts_q), (s, q)
