@@ -52,6 +52,11 @@ def parse():
     ap.add_argument("--iters", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the reference-checksum parity check")
+    ap.add_argument("--no-gpu-baseline", action="store_true",
+                    help="skip timing the reference's own CUDA backend (oracle/_ref_cuda) on this GPU")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the BP1/BP3/BP5 x p=1..8 table after the headline")
+    ap.add_argument("--sweep-dofs", type=float, default=50e6, help="dofs per sweep case (BASELINE config C2: ~50 M)")
+    ap.add_argument("--no-anchor", action="store_true", help="skip the 1-GPU run at the per-GPU size of --gpus N > 1")
     ap.add_argument("--cpu-n", type=int, default=None, help="elements per side of the CPU sample")
     ap.add_argument("--curved", type=int, default=None,
                     help="1: order-3 nodes displaced by the smooth map of BASELINE config C5 (default for --bp 5)")
@@ -296,12 +301,45 @@ def main():
     def solve_resident():
         cg.Mult(B, X)
 
-    B_in = dev.empty(nt)
+    # end to end: every step copies its right-hand side from pinned host memory and its solution back.
+    # The steps are independent solves, so the copies are double-buffered on two copy streams: the
+    # H2D of step k+1 and the D2H of step k-1 overlap the solve of step k (all three inside the timed
+    # region; the event chain below orders buffer reuse).
+    B_in = [dev.empty(nt), dev.empty(nt)]
+    X_out = [dev.empty(nt), dev.empty(nt)]
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_solved = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_out = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"k": 0, "primed": False}
+
+    def h2d(slot):
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_solved[slot])  # the solve that last read this buffer is done
+            B_in[slot].copy_(B_h, non_blocking=True)
+            ev_in[slot].record(s_in)
 
     def solve_e2e():
-        B_in.copy_(B_h, non_blocking=True)
-        cg.Mult(B_in, X)
-        X_h.copy_(X, non_blocking=True)
+        k = e2e_state["k"]
+        slot = k % 2
+        if not e2e_state["primed"]:
+            h2d(slot)
+            e2e_state["primed"] = True
+        h2d(1 - slot)                    # next step's input, in flight during this solve
+        main.wait_event(ev_in[slot])
+        main.wait_event(ev_out[slot])    # the D2H that last read this output buffer is done
+        cg.Mult(B_in[slot], X_out[slot])
+        ev_solved[slot].record(main)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_solved[slot])
+            X_h.copy_(X_out[slot], non_blocking=True)
+            ev_out[slot].record(s_out)
+        e2e_state["k"] = k + 1
+
+    def drain_e2e():
+        main.wait_event(ev_out[0])
+        main.wait_event(ev_out[1])
 
     def timed(fn, steps, warmup, kernel_timing=False):
         for _ in range(warmup):
@@ -314,6 +352,8 @@ def main():
         e0.record()
         for _ in range(steps):
             fn()
+        if fn is solve_e2e:
+            drain_e2e()  # the last solutions have reached the host buffer
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -390,7 +430,9 @@ def main():
                        f"{it_bytes(w, fes.ne) / 1e9:.1f} GB per GPU) far exceed the 126 MB L2",
                        "final_norm": final_norm, "setup_seconds": round(t_setup, 1)},
             "e2e": {"value": e2e, "unit": "GDOF/s", "h2d_bytes_per_step": nt * 8 * a.gpus,
-                    "d2h_bytes_per_step": nt * 8 * a.gpus, "ms_per_step": ms_e2e / a.steps},
+                    "d2h_bytes_per_step": nt * 8 * a.gpus, "ms_per_step": ms_e2e / a.steps,
+                    "copies": "pinned host buffers; double-buffered on two copy streams: the H2D of step k+1 and the "
+                              "D2H of step k-1 overlap the solve of step k, all inside the timed region"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
@@ -419,7 +461,7 @@ def main():
     if a.gpus == 1:
         # free the headline problem before the baselines and the table
         form.close(); it.close()
-        del A, B, X, M, cg, b, b_l, B_in, B_h, X_h, form, it
+        del A, B, X, M, cg, b, b_l, B_in, X_out, B_h, X_h, form, it
         torch.cuda.empty_cache()
         if not a.no_gpu_baseline:
             line["gpu_baseline"] = run_gpu_baseline(w, a.iters)

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstring>
 
+#include <climits>
 #include "common.cuh"
 
 namespace b2f
@@ -340,8 +341,9 @@ static int pa_alloc(b2f_ctx *ctx, int kind, int dim, int d1d, int q1d, int64_t n
    memset(pa->G, 0, sizeof(pa->G));
    memcpy(pa->B, B_h, sizeof(double) * d1d * q1d);
    if (G_h) { memcpy(pa->G, G_h, sizeof(double) * d1d * q1d); }
-   // collocated (BP5): B is exactly the identity -> the interpolation is skipped.  "Exactly"
-   // up to 2 ulp: the reference's barycentric evaluation at a node gives 1 +- eps.
+   // collocated (BP5): B is EXACTLY the identity (the reference's barycentric evaluation at a node
+   // returns exactly 1 and 0, measured max|B - I| = 0) -> the interpolation is skipped.  Anything
+   // else, however close, takes the general path.
    pa->collocated = 0;
    if (d1d == q1d)
    {
@@ -745,6 +747,9 @@ int b2f_operator_create(b2f_ctx *ctx, b2f_restriction *r, b2f_pa *const *integra
       dim_dof = dof;
    }
    (void)dim_dof;
+   B2F_REQUIRE((int64_t)r->ndofs * r->vdim <= INT32_MAX,
+               "b2f_operator_create: %lld vdofs exceed the int32 index range of the operator's dof lists",
+               (long long)r->ndofs * r->vdim);
    for (int i = 0; i < n_ess; i++)
    {
       B2F_REQUIRE(ess_dofs_h[i] >= 0 && (int64_t)ess_dofs_h[i] < (int64_t)r->ndofs * r->vdim,
@@ -942,7 +947,7 @@ static int rap_mult(b2f_operator *op, const double *x, double *y, bool constrain
 {
    if (!op->halo) { return local_mult(op, x, y, constrained_mask, dot_acc); }
    b2f_ctx *ctx = op->ctx;
-   const int nl = op->r->ndofs * op->r->vdim; // local (v)dofs; the halo tables are per vdof
+   const int64_t nl = (int64_t)op->r->ndofs * op->r->vdim; // local (v)dofs; the halo tables are per vdof
    if (halo_is_prefix(op->halo))
    {
       int nl2 = 0, nt = 0;

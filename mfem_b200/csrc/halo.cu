@@ -115,6 +115,13 @@ struct b2f_halo
    double **peer_shr_dst = nullptr;          // [n_nbr] where my contributions land in neighbour k
    unsigned long long **peer_flag_p = nullptr, **peer_flag_pt = nullptr;
    unsigned long long epoch_p = 0, epoch_pt = 0;
+   // Protocol invariant of the peer-memory exchange: on every rank a P push is followed by exactly
+   // one P^T push before the next P push (one operator application = P ... P^T).  That alternation
+   // is what makes the single receive buffer per direction race-free: a neighbour can only start
+   // its next P push after it has waited for my P^T data, which I send after consuming its P data.
+   // phase: 0 = a P push is next, 1 = a P^T push is next.  A call out of order (an application that
+   // failed half-way) is refused here instead of leaving the neighbours spinning on a flag.
+   int phase = 0;
    int max_shr = 0, max_ext = 0;
    std::vector<void *> opened;               // cudaIpcOpenMemHandle results to close
 };
@@ -251,11 +258,18 @@ static int p2p_p_push(b2f_halo *h, const double *v)
 {
    b2f_ctx *ctx = h->ctx;
    if (h->n_nbr == 0) { return B2F_OK; }
-   const unsigned long long ep = ++h->epoch_p;
+   if (h->phase != 0)
+   {
+      set_error("halo (peer-memory): P exchange started while a P^T exchange is pending -- the ranks are out of step");
+      return B2F_ERR_ARG;
+   }
+   const unsigned long long ep = h->epoch_p + 1;
    const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(h->max_shr, 256), 64)), h->n_nbr);
    p2p_push_kernel<<<grid, 256, 0, ctx->stream>>>(h->shr_ltdof, h->shr_off_d, v, h->peer_ext_dst,
                                                   h->peer_flag_p, h->tickets, ep);
    B2F_LAUNCH_CHECK(ctx);
+   h->epoch_p = ep; // only a launch that went out advances the epoch
+   h->phase = 1;
    return B2F_OK;
 }
 
@@ -281,11 +295,18 @@ static int p2p_pt_push(b2f_halo *h, const double *v)
 {
    b2f_ctx *ctx = h->ctx;
    if (h->n_nbr == 0) { return B2F_OK; }
-   const unsigned long long ep = ++h->epoch_pt;
+   if (h->phase != 1)
+   {
+      set_error("halo (peer-memory): P^T exchange without a preceding P exchange -- the ranks are out of step");
+      return B2F_ERR_ARG;
+   }
+   const unsigned long long ep = h->epoch_pt + 1;
    const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(h->max_ext, 256), 64)), h->n_nbr);
    p2p_push_kernel<<<grid, 256, 0, ctx->stream>>>(h->ext_ldof, h->ext_off_d, v, h->peer_shr_dst,
                                                   h->peer_flag_pt, h->tickets + 32, ep);
    B2F_LAUNCH_CHECK(ctx);
+   h->epoch_pt = ep;
+   h->phase = 0;
    return B2F_OK;
 }
 

@@ -17,6 +17,7 @@
 // applied by expressing that lattice point in the parametrisation of the entity's first
 // (owning) element.
 #include <algorithm>
+#include <exception>
 #include <array>
 #include <cstdint>
 #include <cstdlib>
@@ -456,7 +457,7 @@ void h1_number(int dim, int p, int nverts, const std::vector<int> &elem_vert, H1
 
 } // namespace b2f
 
-extern "C" int b2f_cartesian_h1_space_h(int dim, int nx, int ny, int nz, int p, int sfc_ordering,
+static int cartesian_h1_space_impl(int dim, int nx, int ny, int nz, int p, int sfc_ordering,
                                         int *ne, int *ndofs, int *elem_dof_h, int *dof_map_h,
                                         int *nbdr, int *bdr_dofs_h, double *elem_vertices_h)
 {
@@ -550,4 +551,21 @@ extern "C" int b2f_cartesian_h1_space_h(int dim, int nx, int ny, int nz, int p, 
    cache.bdr.swap(S.bdr_dofs);
    cache.valid = true;
    return B2F_OK;
+}
+
+// nothing may throw across the C ABI (allocation failures of the multi-GB tables)
+extern "C" int b2f_cartesian_h1_space_h(int dim, int nx, int ny, int nz, int p, int sfc_ordering,
+                                        int *ne, int *ndofs, int *elem_dof_h, int *dof_map_h,
+                                        int *nbdr, int *bdr_dofs_h, double *elem_vertices_h)
+{
+   try
+   {
+      return cartesian_h1_space_impl(dim, nx, ny, nz, p, sfc_ordering, ne, ndofs, elem_dof_h, dof_map_h, nbdr,
+                                     bdr_dofs_h, elem_vertices_h);
+   }
+   catch (const std::exception &ex)
+   {
+      b2f::set_error("b2f_cartesian_h1_space_h: %s", ex.what());
+      return B2F_ERR_ARG;
+   }
 }

@@ -15,6 +15,7 @@
 // the block extents, and both sides of every neighbour pair list their common dofs in
 // ascending lattice order, so send and receive buffers line up.
 #include <algorithm>
+#include <exception>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -56,7 +57,7 @@ thread_local Tables g_tables;
 
 } // namespace
 
-extern "C" int b2f_cartesian_partition_h(int dim, int nx, int ny, int nz, int p, int sfc_ordering,
+static int cartesian_partition_impl(int dim, int nx, int ny, int nz, int p, int sfc_ordering,
                                          int px, int py, int pz, int rank, int *sizes_h,
                                          int *elem_dof_h, int *dof_map_h, int *bdr_ldofs_h,
                                          double *elem_vertices_h, int *ltdof_ldof_h,
@@ -311,4 +312,26 @@ extern "C" int b2f_cartesian_partition_h(int dim, int nx, int ny, int nz, int p,
    T.valid = true;
    lap("tables");
    return hand_out();
+}
+
+// nothing may throw across the C ABI: multi-GB std::vector growth and std::thread creation can
+extern "C" int b2f_cartesian_partition_h(int dim, int nx, int ny, int nz, int p, int sfc_ordering,
+                                         int px, int py, int pz, int rank, int *sizes_h,
+                                         int *elem_dof_h, int *dof_map_h, int *bdr_ldofs_h,
+                                         double *elem_vertices_h, int *ltdof_ldof_h,
+                                         int *nbr_rank_h, int *shr_offsets_h, int *shr_ltdof_h,
+                                         int *ext_offsets_h, int *ext_ldof_h,
+                                         int64_t *ldof_lattice_h)
+{
+   try
+   {
+      return cartesian_partition_impl(dim, nx, ny, nz, p, sfc_ordering, px, py, pz, rank, sizes_h, elem_dof_h,
+                                      dof_map_h, bdr_ldofs_h, elem_vertices_h, ltdof_ldof_h, nbr_rank_h,
+                                      shr_offsets_h, shr_ltdof_h, ext_offsets_h, ext_ldof_h, ldof_lattice_h);
+   }
+   catch (const std::exception &ex)
+   {
+      b2f::set_error("b2f_cartesian_partition_h: %s", ex.what());
+      return B2F_ERR_ARG;
+   }
 }
