@@ -228,6 +228,9 @@ def main():
             pass
         else:
             raise SystemExit(f"--gpus {a.gpus} needs torchrun with {a.gpus} ranks (WORLD_SIZE={world})")
+    # host table generation fans out over std::threads: share the cores between the ranks of the node
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)
+    os.environ.setdefault("B2F_HOST_THREADS", str(max(2, min(16, cores // max(world, 1)))))
     dist = None
     if world > 1:
         import torch.distributed as dist

@@ -269,7 +269,7 @@ struct EOStages
 #pragma unroll
          for (int k = 0; k < C::NQD; k++)
          {
-            if constexpr (C::SWZ) { load_row_swz8(dq + k * Q3, (qy >> 1) & 3, dv[k]); }
+            if constexpr (C::SWZ) { load_row_swz<Q>(dq + k * Q3, swz_phase<Q>(e, qy, qz), dv[k]); }
             else if constexpr (C::VEC) { load_row<Q, false>(dq + k * Q3, dv[k]); }
             else
             {
@@ -292,7 +292,7 @@ struct EOStages
       else
       {
          double dv[Q];
-         if constexpr (C::SWZ) { load_row_swz8(dq, (qy >> 1) & 3, dv); }
+         if constexpr (C::SWZ) { load_row_swz<Q>(dq, swz_phase<Q>(e, qy, qz), dv); }
          else if constexpr (C::VEC) { load_row<Q, false>(dq, dv); }
          else
          {
@@ -867,7 +867,7 @@ inline bool fill_eo_basis(const b2f_pa *pa, EOBasis<D, Q> &bs)
 // host: the (Q, rows-per-element, NE) tensor map over an integrator's quadrature data, boxes of
 // (Q, box_rows, 1), 64-byte swizzle (Q = 8).  Cached in the b2f_pa (rebuilt when the data
 // pointer or the element count changes: compacted copies of marked integrators, |D| twins).
-inline int make_qdata_tensor_map(b2f_pa *pa, int q, int rows, int box_rows)
+inline int make_qdata_tensor_map(b2f_pa *pa, int q, int rows, int box_rows)  // q = 8: 64-byte swizzle, q = 4: 32-byte
 {
    if (pa->tmap_data == pa->data && pa->tmap_ne == pa->ne) { return B2F_OK; }
    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -896,7 +896,8 @@ inline int make_qdata_tensor_map(b2f_pa *pa, int q, int rows, int box_rows)
    const cuuint32_t estr[3] = {1u, 1u, 1u};
    const CUresult r = encode(reinterpret_cast<CUtensorMap *>(pa->tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
                              pa->data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             q == 8 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
    if (r != CUDA_SUCCESS)
    {

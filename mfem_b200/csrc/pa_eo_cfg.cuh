@@ -71,12 +71,18 @@ struct PipeCfg
    static constexpr bool VEC = TMA_OK && (Q % 2 == 0);   // rows 16-byte aligned
    // Q = 8: 64-byte rows, TMA tensor copies with the 64-byte swizzle (see the file header);
    // slabs are unpadded (24 576 / 4 096 B, multiples of the 512-byte swizzle period) and the
-   // tile starts at a 1024-byte aligned shared-memory address found at run time
-   static constexpr bool SWZ = TMA_OK && (Q == 8);
+   // tile starts at a 1024-byte aligned shared-memory address found at run time.
+   // Q = 4: 32-byte rows, eight lanes = four rows of each of two elements (or of two qz planes):
+   // 2-way conflict.  32-byte swizzle (chunk ^= address bit 7, i.e. qz & 1) plus 128 B of padding
+   // per element slab (an odd number of 128-byte lines per slab flips the phase from one element
+   // to the next): the eight lanes then hit the eight bank groups.
+   static constexpr bool SWZ = TMA_OK && (Q == 8 || Q == 4);
+   static constexpr int SWZ_PAD = (SWZ && Q == 4) ? 16 : 0; // doubles
    static constexpr int ROWS = NQD * Q2;                  // rows of Q doubles per element
    static constexpr int BOX_ROWS = ROWS <= 256 ? ROWS : ROWS / 2; // tensor-copy box (<= 256 rows)
    static constexpr int NBOX = ROWS / BOX_ROWS;
-   static constexpr int DS = NQD * Q3 + ((TMA_OK && !SWZ) ? L.dpad : 0);
+   static constexpr int DS = NQD * Q3 + ((TMA_OK && !SWZ) ? L.dpad : SWZ_PAD);
+   static_assert(!SWZ || Q == 8 || ((DS * 8) % 256) == 128, "Q = 4 slabs must be an odd number of 128-byte lines");
    static constexpr int QD = NEB * DS;
    static constexpr size_t SMEM = 16 + sizeof(double) * (size_t)(QD + R1 + R2) + (SWZ ? 1024 : 0);
    static_assert(T1 <= NT && T2 <= NT, "one task per thread per stage");
@@ -99,17 +105,25 @@ __device__ __forceinline__ void tensor_g2s_3d(void *dst, const void *tmap, int c
       : "memory");
 }
 
-// one swizzled row of 8 doubles -> registers: chunk j (16 B) of the row sits at chunk j ^ s,
-// s = (row >> 1) & 3 with the row counted from a 512-byte aligned address
-__device__ __forceinline__ void load_row_swz8(const double *__restrict__ row, int s, double (&v)[8])
+// one swizzled row of Q doubles -> registers: chunk j (16 B) of the row sits at chunk j ^ s.
+// Q = 8 (64-byte swizzle): s = (row >> 1) & 3, the row counted from a 512-byte aligned address;
+// Q = 4 (32-byte swizzle): s = bit 7 of the row's shared-memory address.
+template <int Q>
+__device__ __forceinline__ void load_row_swz(const double *__restrict__ row, int s, double (&v)[Q])
 {
    const char *p = reinterpret_cast<const char *>(row);
 #pragma unroll
-   for (int j = 0; j < 4; j++)
+   for (int j = 0; j < Q / 2; j++)
    {
       const double2 w = *reinterpret_cast<const double2 *>(p + ((j ^ s) << 4));
       v[2 * j] = w.x; v[2 * j + 1] = w.y;
    }
+}
+// swizzle phase of the row (qy, qz) of element e of the tile
+template <int Q>
+__device__ __forceinline__ int swz_phase(int e, int qy, int qz)
+{
+   return Q == 8 ? (qy >> 1) & 3 : (qz ^ e) & 1;
 }
 
 __device__ __forceinline__ void cp_async4(void *dst, const void *src)

@@ -309,3 +309,29 @@ def test_halo_tables_from_group_tables(dim, n, p, grid):
             got = out[q]["ext_ldof"][out[q]["ext_offsets"][j]:out[q]["ext_offsets"][j + 1]]
             pts_q = ranks[q].halo_tables["ldof_lattice"][got]
             assert np.array_equal(pts_s, pts_q), (s, q)
+
+
+@pytest.mark.parametrize("p,n", [(1, 5), (3, 4), (4, 3)])
+def test_threaded_host_loops_match_the_serial_ones(monkeypatch, p, n):
+    """The std::thread fan-out of the numbering / partition loops only engages above 65536
+    iterations; B2F_HOST_PAR_MIN=1 forces it on small meshes: identical tables, bit for bit."""
+    import mfem_b200 as m
+
+    def tables():
+        f = m.FiniteElementSpace(m.Mesh.MakeCartesian3D(n, n, n + 1), m.H1_FECollection(p, 3))
+        out = [f.elem_dof.copy(), f.dof_map.copy(), f.bdr_dofs.copy(), f.elem_vertices.copy()]
+        for r in range(4):
+            g = m.FiniteElementSpace(m.Mesh(3, n, n, n + 1, True, part=(2, 2, 1), rank=r), m.H1_FECollection(p, 3))
+            out += [g.elem_dof.copy(), g.bdr_dofs.copy(), g.elem_vertices.copy()]
+            out += [g.halo_tables[k].copy() for k in sorted(g.halo_tables)]
+        return out
+
+    monkeypatch.setenv("B2F_HOST_PAR_MIN", str(1 << 40))
+    monkeypatch.setenv("B2F_HOST_THREADS", "1")
+    serial = tables()
+    monkeypatch.setenv("B2F_HOST_PAR_MIN", "1")
+    monkeypatch.setenv("B2F_HOST_THREADS", "7")
+    threaded = tables()
+    assert len(serial) == len(threaded)
+    for a, b in zip(serial, threaded):
+        assert np.array_equal(a, b)
