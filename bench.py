@@ -133,7 +133,12 @@ def ref_driver_path():
     return p if os.path.isfile(p) and os.access(p, os.X_OK) else None
 
 
-def run_reference(w, n_cpu, iters, reps):
+def cpu_sample_n(p):
+    """elements per side of the CPU sample: ~17 M dofs (a 4-5 s solve at p=4 on 16 cores)"""
+    return max(8, round(256 / p))
+
+
+def run_reference(w, n_cpu, iters, reps, skip=0):
     """The unmodified reference's CPU PA path on all host cores (MFEM_DEVICE=omp), or the C
     oracle port on one core when oracle/_ref was not built."""
     cores = os.cpu_count() or 1
@@ -148,7 +153,7 @@ def run_reference(w, n_cpu, iters, reps):
                "--kind", w["kind"], "--quad", "gll" if w["gll"] else "gl", "--curved", str(int(w["curved"])),
                "--vdim", str(w.get("vdim", 1)),
                "--iters", str(iters),
-               "--reps", str(reps), "--jacobi", "1"]
+               "--reps", str(reps), "--skip", str(skip), "--jacobi", "1"]
         out = subprocess.run(cmd, check=True, stdout=subprocess.PIPE, env=env).stdout.decode()
         r = json.loads(out.strip().splitlines()[-1])
         return dict(value=r["dofs_iters_per_s"] / 1e9, seconds=r["seconds"], ndofs=r["ndofs"],
@@ -185,17 +190,12 @@ def main_reference(a, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_cpu = a.cpu_n or {4: 40}.get(w["p"], max(8, round(160 / w["p"])))
-    # warm-up + timed steps: each step is one bounded-sample solve
-    t = []
-    res = None
-    for i in range(a.warmup + a.steps):
-        if i < a.warmup and i > 0:
-            continue  # the sample is seconds long: one warm-up solve is enough to page in
-        res = run_reference(w, n_cpu, a.iters, 1)
-        if i >= a.warmup:
-            t.append(res["seconds"])
-    sec = sum(t) / len(t)
+    n_cpu = a.cpu_n or cpu_sample_n(w["p"])
+    # one process: `warmup` untimed solves (capped at 1: a solve is seconds long, one is enough to
+    # page everything in), then `steps` timed ones, averaged
+    wu = min(a.warmup, 1)
+    res = run_reference(w, n_cpu, a.iters, wu + a.steps, skip=wu)
+    sec = res["seconds"]
     val = res["ndofs"] * a.iters / sec / 1e9
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "GDOF/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
@@ -454,8 +454,8 @@ def main():
         }
         if a.gpus == 1 and not a.no_cpu_baseline:
             try:
-                n_cpu = a.cpu_n or {4: 40}.get(p, max(8, round(160 / p)))
-                r = run_reference(w, n_cpu, a.iters, 1)
+                n_cpu = a.cpu_n or cpu_sample_n(p)
+                r = run_reference(w, n_cpu, a.iters, 2, skip=1)
                 line["cpu_baseline"] = {"value": r["value"], "unit": "GDOF/s", "cores": r["cores"],
                                         "kind": r["kind"], "sample": r["sample"]}
             except Exception as ex:  # the baseline is reported, never required

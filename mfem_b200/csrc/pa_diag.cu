@@ -43,11 +43,13 @@ struct DiagCfg
    static constexpr int NX = DIFF ? 6 : 1; // fields after the x-contraction
    static constexpr int NY = DIFF ? 3 : 1; // fields after the y-contraction
    static constexpr int YQ = Q * NEB;      // yq = qy + Q e, zq = qz + Q e
-   static constexpr int YQP = YQ | 1;      // odd pitch: strided reads of the next stage spread over the banks
+   // a 1D line of Q values is stored with an ODD pitch: the next stage's lanes each read one line,
+   // the same position of every line per instruction, i.e. addresses QP apart -> distinct banks
+   static constexpr int QP = Q | 1;
    static constexpr int T1 = NEB * Q * Q, T2 = NEB * D * Q, T3 = NEB * D * D;
    static constexpr int NT = ((T1 + 31) / 32) * 32;
-   static constexpr int XS = NX * D * Q * YQP; // [k][dx][qz][yq]
-   static constexpr int YS = NY * D * D * YQP; // [f][dx][dy][zq]
+   static constexpr int XS = NX * D * Q * NEB * QP; // [k][dx][qz][e][qy (pitch QP)]: lines over qy
+   static constexpr int YS = NY * NEB * D * D * QP; // [f][e][dy][dx][qz (pitch QP)]: lines over qz
    static constexpr size_t SMEM = sizeof(double) * (size_t)(XS + YS);
 };
 
@@ -57,9 +59,9 @@ constexpr int diag_neb(int kind, int D, int Q)
    int n = 1;
    while (n < 16)
    {
-      const int m = n + 1, yqp = (Q * m) | 1;
+      const int m = n + 1, qp = Q | 1;
       const int nx = kind == B2F_KIND_DIFFUSION ? 6 : 1, ny = kind == B2F_KIND_DIFFUSION ? 3 : 1;
-      if (m * Q * Q > 256 || 8 * (nx * D * Q * yqp + ny * D * D * yqp) > 40 * 1024) { break; }
+      if (m * Q * Q > 256 || 8 * (nx * D * Q * m * qp + ny * m * D * D * qp) > 40 * 1024) { break; }
       n = m;
    }
    return n;
@@ -88,7 +90,7 @@ pa_diag_3d_kernel(const __grid_constant__ DiagTables<D, Q> tb, const double *__r
                   double *__restrict__ out, const int *__restrict__ gmap, const int64_t ne)
 {
    using C = DiagCfg<KIND, D, Q, NEB>;
-   constexpr int Q3 = Q * Q * Q, D3 = D * D * D, YQP = C::YQP;
+   constexpr int Q3 = Q * Q * Q, D3 = D * D * D, QP = C::QP, LX = NEB * QP;
    extern __shared__ __align__(16) double dsm[];
    double *Xs = dsm, *Ys = dsm + C::XS;
    const int t = threadIdx.x;
@@ -138,7 +140,7 @@ pa_diag_3d_kernel(const __grid_constant__ DiagTables<D, Q> tb, const double *__r
 #pragma unroll
             for (int q = 0; q < Q; q++) { r[k][q] = 0.0; }
       }
-      double *X0 = Xs + qz * YQP + yq;
+      double *X0 = Xs + qz * LX + e * QP + qy;
 #pragma unroll
       for (int dx = 0; dx < D; dx++)
       {
@@ -162,7 +164,7 @@ pa_diag_3d_kernel(const __grid_constant__ DiagTables<D, Q> tb, const double *__r
             else { a[0] = fma(bb, r[0][qx], a[0]); }
          }
 #pragma unroll
-         for (int k = 0; k < C::NX; k++) { X0[(k * D + dx) * (Q * YQP)] = a[k]; }
+         for (int k = 0; k < C::NX; k++) { X0[(k * D + dx) * (Q * LX)] = a[k]; }
       }
    }
    __syncthreads();
@@ -175,8 +177,8 @@ pa_diag_3d_kernel(const __grid_constant__ DiagTables<D, Q> tb, const double *__r
 #pragma unroll
       for (int k = 0; k < C::NX; k++)
 #pragma unroll
-         for (int qy = 0; qy < Q; qy++) { r[k][qy] = Xs[((k * D + dx) * Q + qz) * YQP + Q * e + qy]; }
-      double *Y0 = Ys + dx * (D * YQP) + zq;
+         for (int qy = 0; qy < Q; qy++) { r[k][qy] = Xs[((k * D + dx) * Q + qz) * LX + e * QP + qy]; }
+      double *Y0 = Ys + (e * D * D + dx) * QP + qz; // + dy * D * QP, + f * NEB * D * D * QP
 #pragma unroll
       for (int dy = 0; dy < D; dy++)
       {
@@ -194,11 +196,11 @@ pa_diag_3d_kernel(const __grid_constant__ DiagTables<D, Q> tb, const double *__r
             }
             else { zb = fma(bb, r[0][qy], zb); }
          }
-         Y0[dy * YQP] = zb;
+         Y0[dy * (D * QP)] = zb;
          if constexpr (C::DIFF)
          {
-            Y0[(D * D + dy) * YQP] = zbg;
-            Y0[(2 * D * D + dy) * YQP] = zg;
+            Y0[NEB * D * D * QP + dy * (D * QP)] = zbg;
+            Y0[2 * NEB * D * D * QP + dy * (D * QP)] = zg;
          }
       }
    }
@@ -209,12 +211,18 @@ pa_diag_3d_kernel(const __grid_constant__ DiagTables<D, Q> tb, const double *__r
       const int dx = t % D, dy = (t / D) % D, e = t / (D * D);
       if (e < nev)
       {
+         const int64_t base = (e0 + e) * (int64_t)D3 + dx + D * dy;
+         int g[D]; // scatter targets first: their latency hides behind the shared-memory reads
+         if constexpr (FUSED)
+         {
+#pragma unroll
+            for (int dz = 0; dz < D; dz++) { g[dz] = __ldg(gmap + base + (int64_t)(D * D) * dz); }
+         }
          double r[C::NY][Q];
 #pragma unroll
          for (int f = 0; f < C::NY; f++)
 #pragma unroll
-            for (int qz = 0; qz < Q; qz++) { r[f][qz] = Ys[((f * D + dx) * D + dy) * YQP + Q * e + qz]; }
-         const int64_t base = (e0 + e) * (int64_t)D3 + dx + D * dy;
+            for (int qz = 0; qz < Q; qz++) { r[f][qz] = Ys[((f * NEB + e) * D * D + dy * D + dx) * QP + qz]; }
 #pragma unroll
          for (int dz = 0; dz < D; dz++)
          {
@@ -226,11 +234,7 @@ pa_diag_3d_kernel(const __grid_constant__ DiagTables<D, Q> tb, const double *__r
                if constexpr (C::DIFF) { s = fma(tb.BG[qz][dz], r[1][qz], fma(tb.GG[qz][dz], r[2][qz], s)); }
             }
             const int64_t i = base + (int64_t)(D * D) * dz;
-            if constexpr (FUSED)
-            {
-               const int g = __ldg(gmap + i);
-               atomicAdd(out + (g >= 0 ? g : -1 - g), s); // unsigned: AbsMultTranspose
-            }
+            if constexpr (FUSED) { atomicAdd(out + (g[dz] >= 0 ? g[dz] : -1 - g[dz]), s); } // unsigned: AbsMultTranspose
             else { out[i] += s; }
          }
       }

@@ -81,7 +81,7 @@ constexpr int smem_eo(int kind, int D, int Q, int n)
    const PipeLayout L = pipe_layout(kind, D, Q, n);
    const int sa = pad16(D * yq, L.ra), sc = pad16(Q * yq, yq);
    const int q3 = Q * Q * Q;
-   const bool tma = (nqd * q3) % 2 == 0, swz = tma && (Q == 8 || Q == 4);
+   const bool tma = (nqd * q3) % 2 == 0, swz = tma && Q == 8; // (PipeCfg::SWZ4 is off)
    const int dp = (tma && !swz) ? L.dpad : (swz && Q == 4) ? 16 : 0;
    return 16 + 8 * (n * (nqd * q3 + dp) + na * D * sa + nc * D * sc) + (swz ? 1024 : 0);
 }

@@ -72,11 +72,14 @@ struct PipeCfg
    // Q = 8: 64-byte rows, TMA tensor copies with the 64-byte swizzle (see the file header);
    // slabs are unpadded (24 576 / 4 096 B, multiples of the 512-byte swizzle period) and the
    // tile starts at a 1024-byte aligned shared-memory address found at run time.
-   // Q = 4: 32-byte rows, eight lanes = four rows of each of two elements (or of two qz planes):
-   // 2-way conflict.  32-byte swizzle (chunk ^= address bit 7, i.e. qz & 1) plus 128 B of padding
-   // per element slab (an odd number of 128-byte lines per slab flips the phase from one element
-   // to the next): the eight lanes then hit the eight bank groups.
-   static constexpr bool SWZ = TMA_OK && (Q == 8 || Q == 4);
+   // Q = 4 (32-byte rows, 2-way conflict) has the analogous cure -- 32-byte swizzle (chunk ^= address
+   // bit 7, i.e. qz & 1) plus 128 B of padding per element slab (an odd number of 128-byte lines per
+   // slab flips the phase from one element to the next) -- implemented below (SWZ4) and parity-clean,
+   // but MEASURED SLOWER (profiles/r02_opbench_q4_swizzle.txt: BP5 p=3 84.7 -> 74.3 %, BP3 p=2
+   // 83.8 -> 78.9 % of the HBM roofline): a tensor copy of 32-byte rows issues sector-sized requests,
+   // which costs more than the 2-way conflict it removes.  It stays off.
+   static constexpr bool SWZ4 = false;
+   static constexpr bool SWZ = TMA_OK && (Q == 8 || (SWZ4 && Q == 4));
    static constexpr int SWZ_PAD = (SWZ && Q == 4) ? 16 : 0; // doubles
    static constexpr int ROWS = NQD * Q2;                  // rows of Q doubles per element
    static constexpr int BOX_ROWS = ROWS <= 256 ? ROWS : ROWS / 2; // tensor-copy box (<= 256 rows)

@@ -939,6 +939,7 @@ static int do_bench(const Args &A)
 {
    const string mode = A.gets("mode", "pcg");
    const int reps = A.geti("reps", 3), iters = A.geti("iters", 32);
+   const int skip = std::min(A.geti("skip", 0), reps - 1); // pcg: leading solves left out of the average
    const int use_prec = A.geti("jacobi", 0);
    double t0 = now();
    Problem P(A);
@@ -1016,9 +1017,9 @@ static int do_bench(const Args &A)
          MFEM_DEVICE_SYNC;
          double t = now() - t1;
          best = std::min(best, t);
-         sec += t;
+         if (r >= skip) { sec += t; }
       }
-      sec /= reps; its = cg.GetNumIterations();
+      sec /= (reps - skip); its = cg.GetNumIterations();
       ynorm = X.Norml2();
       final_norm = cg.GetFinalNorm(); initial_norm = cg.GetInitialNorm();
    }
