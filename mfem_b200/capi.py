@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libb200fem.so")
+# B2F_LIB: an alternative build of the same library (kernel tuning experiments, tools/opbench.py)
+LIB_PATH = os.environ.get("B2F_LIB") or os.path.join(HERE, "lib", "libb200fem.so")
 
 c_int_p = C.POINTER(C.c_int)
 c_double_p = C.POINTER(C.c_double)
