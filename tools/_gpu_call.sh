@@ -1,8 +1,8 @@
 set -x
-for v in base v1 v4 v5; do
-  if [ $v = base ]; then unset B2F_LIB; else export B2F_LIB=$PWD/tools/_build/$v/libb200fem.so; fi
-  echo "=== $v" >> gpurun_out/r02_mass_variants.log
-  VAR=0; [ $v = v4 ] && VAR=0,persist; [ $v = v5 ] && VAR=c0
-  python tools/opbench.py --sweep 1 --variants $VAR --reps 20 >> gpurun_out/r02_mass_variants.log 2>&1
-done
-grep -v "^BP" gpurun_out/r02_mass_variants.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; tail -3 gpurun_out/r02_smoke.log
+date +%s > gpurun_out/t0
+python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_driver_ref.json 2> gpurun_out/r02_driver_ref.err; date +%s > gpurun_out/t1
+python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_driver_n1.json 2> gpurun_out/r02_driver_n1.err; date +%s > gpurun_out/t2
+echo "ref arm s: $(( $(cat gpurun_out/t1) - $(cat gpurun_out/t0) ))  b200 arm s: $(( $(cat gpurun_out/t2) - $(cat gpurun_out/t1) ))"
+cut -c1-700 gpurun_out/r02_driver_ref.json; tail -3 gpurun_out/r02_driver_ref.err
+cut -c1-300 gpurun_out/r02_driver_n1.json; tail -3 gpurun_out/r02_driver_n1.err
