@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include <climits>
+#include <new>
 #include "common.cuh"
 
 namespace b2f
@@ -108,19 +109,29 @@ int b2f_ctx_create(int device, void *stream, b2f_ctx **out)
    B2F_REQUIRE(device >= 0 && device < ndev, "b2f_ctx_create: device %d out of range [0,%d)",
                device, ndev);
    B2F_CUDA(cudaSetDevice(device));
-   b2f_ctx *ctx = new b2f_ctx;
+   b2f_ctx *ctx = new (std::nothrow) b2f_ctx;
+   B2F_REQUIRE(ctx, "b2f_ctx_create: out of host memory");
    ctx->device = device;
    ctx->stream = (cudaStream_t)stream;
-   B2F_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
-   B2F_CUDA(cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin,
-                                   device));
-   ctx->n_partials = ctx->sm_count * 8;
-   B2F_CUDA(cudaMalloc((void **)&ctx->d_partials, sizeof(double) * ctx->n_partials));
-   B2F_CUDA(cudaMalloc((void **)&ctx->d_counter, sizeof(unsigned int)));
-   B2F_CUDA(cudaMemset(ctx->d_counter, 0, sizeof(unsigned int)));
-   B2F_CUDA(cudaMalloc((void **)&ctx->d_scalars, sizeof(double) * 64));
-   B2F_CUDA(cudaMemset(ctx->d_scalars, 0, sizeof(double) * 64));
-   B2F_CUDA(cudaMallocHost((void **)&ctx->h_scalars, sizeof(double) * 64));
+   auto init = [&]() -> int
+   {
+      B2F_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+      B2F_CUDA(cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin,
+                                      device));
+      ctx->n_partials = ctx->sm_count * 8;
+      B2F_CUDA(cudaMalloc((void **)&ctx->d_partials, sizeof(double) * ctx->n_partials));
+      B2F_CUDA(cudaMalloc((void **)&ctx->d_counter, sizeof(unsigned int)));
+      B2F_CUDA(cudaMemset(ctx->d_counter, 0, sizeof(unsigned int)));
+      B2F_CUDA(cudaMalloc((void **)&ctx->d_scalars, sizeof(double) * 64));
+      B2F_CUDA(cudaMemset(ctx->d_scalars, 0, sizeof(double) * 64));
+      B2F_CUDA(cudaMallocHost((void **)&ctx->h_scalars, sizeof(double) * 64));
+      return B2F_OK;
+   };
+   if (const int rc = init())
+   {
+      b2f_ctx_destroy(ctx); // a failed creation leaks nothing
+      return rc;
+   }
    *out = ctx;
    return B2F_OK;
 }
@@ -140,6 +151,7 @@ void b2f_ctx_destroy(b2f_ctx *ctx)
 
 int b2f_ctx_sync(b2f_ctx *ctx)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(ctx, "b2f_ctx_sync: ctx is NULL");
    B2F_CUDA(cudaStreamSynchronize(ctx->stream));
    return B2F_OK;
@@ -151,6 +163,7 @@ void b2f_ctx_reset_launch_count(b2f_ctx *ctx) { if (ctx) { ctx->launches = 0; } 
 
 int b2f_ctx_kernel_timing(b2f_ctx *ctx, int enable)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(ctx, "b2f_ctx_kernel_timing: ctx is NULL");
    B2F_CUDA(cudaStreamSynchronize(ctx->stream));
    ctx->timing = enable != 0;
@@ -160,6 +173,7 @@ int b2f_ctx_kernel_timing(b2f_ctx *ctx, int enable)
 
 int b2f_ctx_kernel_time(b2f_ctx *ctx, double *ms_total_h, int *launches_h)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(ctx && ms_total_h && launches_h, "b2f_ctx_kernel_time: NULL argument");
    B2F_CUDA(cudaStreamSynchronize(ctx->stream));
    double total = 0.0;
@@ -179,12 +193,14 @@ int b2f_ctx_kernel_time(b2f_ctx *ctx, double *ms_total_h, int *launches_h)
 // ---- memory -----------------------------------------------------------------------------
 int b2f_malloc(b2f_ctx *ctx, size_t bytes, void **dptr)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(ctx && dptr, "b2f_malloc: NULL argument");
    B2F_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
    return B2F_OK;
 }
 int b2f_free(b2f_ctx *ctx, void *dptr)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(ctx, "b2f_free: ctx is NULL");
    if (dptr) { B2F_CUDA(cudaFree(dptr)); }
    return B2F_OK;
@@ -203,24 +219,28 @@ int b2f_free_host(b2f_ctx *ctx, void *hptr)
 }
 int b2f_memcpy_h2d(b2f_ctx *ctx, void *dst, const void *src_h, size_t bytes)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(ctx, "b2f_memcpy_h2d: ctx is NULL");
    if (bytes) { B2F_CUDA(cudaMemcpyAsync(dst, src_h, bytes, cudaMemcpyHostToDevice, ctx->stream)); }
    return B2F_OK;
 }
 int b2f_memcpy_d2h(b2f_ctx *ctx, void *dst_h, const void *src, size_t bytes)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(ctx, "b2f_memcpy_d2h: ctx is NULL");
    if (bytes) { B2F_CUDA(cudaMemcpyAsync(dst_h, src, bytes, cudaMemcpyDeviceToHost, ctx->stream)); }
    return B2F_OK;
 }
 int b2f_memcpy_d2d(b2f_ctx *ctx, void *dst, const void *src, size_t bytes)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(ctx, "b2f_memcpy_d2d: ctx is NULL");
    if (bytes) { B2F_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream)); }
    return B2F_OK;
 }
 int b2f_memset(b2f_ctx *ctx, void *dst, int byte, size_t bytes)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(ctx, "b2f_memset: ctx is NULL");
    if (bytes) { B2F_CUDA(cudaMemsetAsync(dst, byte, bytes, ctx->stream)); }
    return B2F_OK;
@@ -250,6 +270,7 @@ int b2f_restriction_create(b2f_ctx *ctx, int ne, int dof, int ndofs, int vdim, i
                            const int *gather_map_h, const int *offsets_h, const int *indices_h,
                            b2f_restriction **out)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(gather_map_h && offsets_h && indices_h, "b2f_restriction_create: NULL table");
    b2f_restriction *r = nullptr;
    B2F_TRY(restriction_alloc(ctx, ne, dof, ndofs, vdim, byvdim, &r));
@@ -269,6 +290,7 @@ int b2f_restriction_create_from_elem_dof(b2f_ctx *ctx, int ne, int dof, int ndof
                                          int byvdim, const int *elem_dof_h, const int *dof_map_h,
                                          b2f_restriction **out)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(elem_dof_h || ne == 0, "b2f_restriction_create_from_elem_dof: elem_dof_h is NULL");
    b2f_restriction *r = nullptr;
    B2F_TRY(restriction_alloc(ctx, ne, dof, ndofs, vdim, byvdim, &r));
@@ -295,6 +317,7 @@ void b2f_restriction_destroy(b2f_restriction *r)
 int b2f_restriction_tables(const b2f_restriction *r, const int **gather_map, const int **offsets,
                            const int **indices)
 {
+   B2F_ON(r ? r->ctx : nullptr);
    B2F_REQUIRE(r, "b2f_restriction_tables: NULL handle");
    if (gather_map) { *gather_map = r->gather_map; }
    if (offsets) { *offsets = r->offsets; }
@@ -304,22 +327,26 @@ int b2f_restriction_tables(const b2f_restriction *r, const int **gather_map, con
 
 int b2f_restriction_mult(b2f_restriction *r, const double *x_l, double *y_e)
 {
+   B2F_ON(r ? r->ctx : nullptr);
    B2F_REQUIRE(r && (x_l || !r->ndofs) && (y_e || !r->ne), "b2f_restriction_mult: NULL argument");
    return restriction_gather(r, x_l, y_e, false);
 }
 int b2f_restriction_abs_mult(b2f_restriction *r, const double *x_l, double *y_e)
 {
+   B2F_ON(r ? r->ctx : nullptr);
    B2F_REQUIRE(r && (x_l || !r->ndofs) && (y_e || !r->ne), "b2f_restriction_abs_mult: NULL argument");
    return restriction_gather(r, x_l, y_e, true);
 }
 int b2f_restriction_mult_transpose(b2f_restriction *r, const double *x_e, double *y_l, int add)
 {
+   B2F_ON(r ? r->ctx : nullptr);
    B2F_REQUIRE(r && (x_e || !r->ne) && (y_l || !r->ndofs),
                "b2f_restriction_mult_transpose: NULL argument");
    return restriction_scatter(r, x_e, y_l, add ? 1 : 0);
 }
 int b2f_restriction_abs_mult_transpose(b2f_restriction *r, const double *x_e, double *y_l)
 {
+   B2F_ON(r ? r->ctx : nullptr);
    B2F_REQUIRE(r && (x_e || !r->ne) && (y_l || !r->ndofs),
                "b2f_restriction_abs_mult_transpose: NULL argument");
    return restriction_scatter(r, x_e, y_l, 2);
@@ -370,6 +397,7 @@ int b2f_diffusion_setup(b2f_ctx *ctx, int dim, int d1d, int q1d, int64_t ne, con
                         const double *G_h, const double *W_h, const double *J,
                         const double *coeff, int coeff_dim, int64_t coeff_size, b2f_pa **out)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(G_h && W_h && (J || ne == 0) && coeff, "b2f_diffusion_setup: NULL argument");
    const int sym = dim * (dim + 1) / 2;
    B2F_REQUIRE(coeff_dim == 1 || coeff_dim == dim || coeff_dim == sym || coeff_dim == dim * dim,
@@ -397,6 +425,7 @@ int b2f_mass_setup(b2f_ctx *ctx, int dim, int d1d, int q1d, int64_t ne, const do
                    const double *W_h, const double *detJ, const double *coeff, int64_t coeff_size,
                    b2f_pa **out)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(W_h && (detJ || ne == 0) && coeff, "b2f_mass_setup: NULL argument");
    int nq = 1;
    for (int i = 0; i < dim; i++) { nq *= q1d; }
@@ -420,6 +449,7 @@ int b2f_pa_setup_from_nodes(b2f_ctx *ctx, int kind, int dim, int d1d, int q1d, i
                             const double *Bn_h, const double *Gn_h, const double *nodes_e,
                             double coeff, b2f_pa **out)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(kind == B2F_KIND_DIFFUSION || kind == B2F_KIND_MASS,
                "b2f_pa_setup_from_nodes: kind = %d", kind);
    B2F_REQUIRE(W_h && Bn_h && Gn_h && (nodes_e || ne == 0) && node_d1d >= 2,
@@ -455,6 +485,7 @@ void b2f_pa_destroy(b2f_pa *pa)
 
 int b2f_pa_data(const b2f_pa *pa, const double **data, int64_t *size)
 {
+   B2F_ON(pa ? pa->ctx : nullptr);
    B2F_REQUIRE(pa, "b2f_pa_data: NULL handle");
    if (data) { *data = pa->data; }
    if (size) { *size = pa->data_size; }
@@ -463,6 +494,7 @@ int b2f_pa_data(const b2f_pa *pa, const double **data, int64_t *size)
 
 int b2f_pa_add_mult(b2f_pa *pa, const double *x_e, double *y_e)
 {
+   B2F_ON(pa ? pa->ctx : nullptr);
    B2F_REQUIRE(pa && (pa->ne == 0 || (x_e && y_e)), "b2f_pa_add_mult: NULL argument");
    return pa_apply(pa, x_e, y_e, nullptr);
 }
@@ -501,6 +533,7 @@ extern "C" {
 
 int b2f_pa_add_abs_mult(b2f_pa *pa, const double *x_e, double *y_e)
 {
+   B2F_ON(pa ? pa->ctx : nullptr);
    B2F_REQUIRE(pa && (pa->ne == 0 || (x_e && y_e)), "b2f_pa_add_abs_mult: NULL argument");
    b2f_pa *t = nullptr;
    B2F_TRY(pa_abs_twin(pa, &t));
@@ -509,6 +542,7 @@ int b2f_pa_add_abs_mult(b2f_pa *pa, const double *x_e, double *y_e)
 
 int b2f_pa_add_mult_transpose(b2f_pa *pa, const double *x_e, double *y_e)
 {
+   B2F_ON(pa ? pa->ctx : nullptr);
    B2F_REQUIRE(pa && (pa->ne == 0 || (x_e && y_e)), "b2f_pa_add_mult_transpose: NULL argument");
    // bilininteg_diffusion_pa.cpp:95-106, bilininteg_mass_pa.cpp (AddMultTransposePA = AddMultPA)
    B2F_REQUIRE(pa->kind == B2F_KIND_MASS || pa->symmetric,
@@ -518,6 +552,7 @@ int b2f_pa_add_mult_transpose(b2f_pa *pa, const double *x_e, double *y_e)
 
 int b2f_pa_add_mult_vec(b2f_pa *pa, int vdim, const double *x_e, double *y_e)
 {
+   B2F_ON(pa ? pa->ctx : nullptr);
    B2F_REQUIRE(pa && vdim >= 1 && (pa->ne == 0 || (x_e && y_e)), "b2f_pa_add_mult_vec: bad argument");
    if (vdim == 1) { return pa_apply(pa, x_e, y_e, nullptr); }
    pa->vd = vdim;
@@ -530,6 +565,7 @@ int b2f_domain_lf_assemble(b2f_ctx *ctx, int dim, int d1d, int q1d, int vdim, in
                            const int *markers, const double *B_h, const double *W_h, const double *detJ,
                            const double *coeff, int64_t coeff_size, double *y_e)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(ctx && B_h && W_h && coeff && (ne == 0 || (detJ && y_e)), "b2f_domain_lf_assemble: NULL argument");
    B2F_REQUIRE(dim == 2 || dim == 3, "b2f_domain_lf_assemble: dim = %d", dim);
    B2F_REQUIRE(d1d >= 1 && d1d <= 16 && q1d >= 1 && q1d <= 16 && vdim >= 1,
@@ -550,6 +586,7 @@ int b2f_domain_lf_assemble(b2f_ctx *ctx, int dim, int d1d, int q1d, int vdim, in
 
 int b2f_pa_assemble_diagonal(b2f_pa *pa, double *diag_e)
 {
+   B2F_ON(pa ? pa->ctx : nullptr);
    B2F_REQUIRE(pa && (pa->ne == 0 || diag_e), "b2f_pa_assemble_diagonal: NULL argument");
    return pa_diag(pa, diag_e);
 }
@@ -730,6 +767,7 @@ static int operator_build_masks(b2f_operator *op, const int *ess_ldofs_h, int n_
 int b2f_operator_create(b2f_ctx *ctx, b2f_restriction *r, b2f_pa *const *integrators,
                         int n_integrators, const int *ess_dofs_h, int n_ess, b2f_operator **out)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(ctx && r && out && integrators && n_integrators >= 1,
                "b2f_operator_create: NULL argument");
    B2F_REQUIRE(n_ess == 0 || ess_dofs_h, "b2f_operator_create: ess_dofs_h is NULL");
@@ -997,6 +1035,7 @@ static int rap_mult(b2f_operator *op, const double *x, double *y, bool constrain
 int b2f_operator_set_markers(b2f_operator *op, int integrator, const int *elem_attributes_h,
                              const int *markers_h, int n_markers)
 {
+   B2F_ON(op ? op->ctx : nullptr);
    B2F_REQUIRE(op, "b2f_operator_set_markers: NULL handle");
    B2F_REQUIRE(integrator >= 0 && integrator < (int)op->integ.size(),
                "b2f_operator_set_markers: integrator %d of %d", integrator, (int)op->integ.size());
@@ -1039,6 +1078,7 @@ int b2f_operator_set_diag_policy(b2f_operator *op, int policy)
 
 int b2f_operator_assemble_diagonal_constrained(b2f_operator *op, double *diag)
 {
+   B2F_ON(op ? op->ctx : nullptr);
    // ConstrainedOperator::AssembleDiagonal (linalg/operator.cpp:543-572)
    B2F_TRY(b2f_operator_assemble_diagonal(op, diag));
    if (op->diag_policy == 2) { return B2F_OK; }
@@ -1047,6 +1087,7 @@ int b2f_operator_assemble_diagonal_constrained(b2f_operator *op, double *diag)
 
 int b2f_operator_set_interior(b2f_operator *op, int64_t n_interior)
 {
+   B2F_ON(op ? op->ctx : nullptr);
    B2F_REQUIRE(op, "b2f_operator_set_interior: NULL handle");
    B2F_REQUIRE(n_interior >= -1 && n_interior <= op->r->ne, "b2f_operator_set_interior: %lld of %d elements",
                (long long)n_interior, op->r->ne);
@@ -1068,6 +1109,7 @@ int b2f_operator_height(const b2f_operator *op)
 
 int b2f_operator_mult(b2f_operator *op, const double *x_l, double *y_l)
 {
+   B2F_ON(op ? op->ctx : nullptr);
    B2F_REQUIRE(op && x_l && y_l, "b2f_operator_mult: NULL argument");
    B2F_REQUIRE(x_l != y_l, "b2f_operator_mult: x and y alias");
    return rap_mult(op, x_l, y_l, false);
@@ -1075,6 +1117,7 @@ int b2f_operator_mult(b2f_operator *op, const double *x_l, double *y_l)
 
 int b2f_operator_mult_unfused(b2f_operator *op, const double *x_l, double *y_l)
 {
+   B2F_ON(op ? op->ctx : nullptr);
    B2F_REQUIRE(op && x_l && y_l, "b2f_operator_mult_unfused: NULL argument");
    B2F_REQUIRE(!op->halo, "b2f_operator_mult_unfused: local operators only");
    return local_mult_unfused(op, x_l, y_l);
@@ -1106,6 +1149,7 @@ static int rap_abs_mult(b2f_operator *op, const double *x, double *y)
 
 int b2f_operator_abs_mult(b2f_operator *op, const double *x, double *y)
 {
+   B2F_ON(op ? op->ctx : nullptr);
    B2F_REQUIRE(op && x && y, "b2f_operator_abs_mult: NULL argument");
    B2F_REQUIRE(x != y, "b2f_operator_abs_mult: x and y alias");
    return rap_abs_mult(op, x, y);
@@ -1113,6 +1157,7 @@ int b2f_operator_abs_mult(b2f_operator *op, const double *x, double *y)
 
 int b2f_operator_abs_mult_constrained(b2f_operator *op, const double *x, double *y)
 {
+   B2F_ON(op ? op->ctx : nullptr);
    B2F_REQUIRE(op && x && y, "b2f_operator_abs_mult_constrained: NULL argument");
    B2F_REQUIRE(x != y, "b2f_operator_abs_mult_constrained: x and y alias");
    if (op->n_ess == 0) { return rap_abs_mult(op, x, y); }
@@ -1156,6 +1201,7 @@ static int mult_constrained(b2f_operator *op, const double *x, double *y, bool l
 
 int b2f_operator_mult_constrained(b2f_operator *op, const double *x, double *y)
 {
+   B2F_ON(op ? op->ctx : nullptr);
    B2F_REQUIRE(op && x && y, "b2f_operator_mult_constrained: NULL argument");
    B2F_REQUIRE(x != y, "b2f_operator_mult_constrained: x and y alias");
    return mult_constrained(op, x, y, false);
@@ -1163,6 +1209,7 @@ int b2f_operator_mult_constrained(b2f_operator *op, const double *x, double *y)
 
 int b2f_operator_assemble_diagonal(b2f_operator *op, double *diag)
 {
+   B2F_ON(op ? op->ctx : nullptr);
    B2F_REQUIRE(op && diag, "b2f_operator_assemble_diagonal: NULL argument");
    b2f_ctx *ctx = op->ctx;
    b2f_restriction *r = op->r;
@@ -1227,6 +1274,7 @@ int b2f_operator_assemble_diagonal(b2f_operator *op, double *diag)
 
 int b2f_operator_eliminate_rhs(b2f_operator *op, const double *x, double *b)
 {
+   B2F_ON(op ? op->ctx : nullptr);
    B2F_REQUIRE(op && x && b, "b2f_operator_eliminate_rhs: NULL argument");
    b2f_ctx *ctx = op->ctx;
    const int n = b2f_operator_height(op);
@@ -1243,6 +1291,7 @@ int b2f_operator_eliminate_rhs(b2f_operator *op, const double *x, double *b)
 
 int b2f_operator_set_halo(b2f_operator *op, b2f_halo *halo)
 {
+   B2F_ON(op ? op->ctx : nullptr);
    B2F_REQUIRE(op, "b2f_operator_set_halo: NULL handle");
    if (halo)
    {
@@ -1267,6 +1316,7 @@ int b2f_operator_set_halo(b2f_operator *op, b2f_halo *halo)
 int b2f_jacobi_setup(b2f_ctx *ctx, int n, const double *diag, const int *ess_dofs, int n_ess,
                      double damping, double *dinv)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(ctx && (n == 0 || (diag && dinv)) && (n_ess == 0 || ess_dofs),
                "b2f_jacobi_setup: NULL argument");
    return jacobi_setup(ctx, n, diag, ess_dofs, n_ess, damping, dinv);
@@ -1274,12 +1324,14 @@ int b2f_jacobi_setup(b2f_ctx *ctx, int n, const double *diag, const int *ess_dof
 
 int b2f_jacobi_mult(b2f_ctx *ctx, int n, const double *dinv, const double *x, double *y)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(ctx && (n == 0 || (dinv && x && y)), "b2f_jacobi_mult: NULL argument");
    return vector_mul(ctx, n, dinv, x, y);
 }
 
 int b2f_vector_dot(b2f_ctx *ctx, int64_t n, const double *x, const double *y, double *result_h)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(ctx && result_h && (n == 0 || (x && y)), "b2f_vector_dot: NULL argument");
    if (n == 0) { *result_h = 0.0; return B2F_OK; }
    B2F_TRY(dot_to_device(ctx, n, x, y, ctx->d_scalars + 63));
@@ -1292,6 +1344,7 @@ int b2f_vector_dot(b2f_ctx *ctx, int64_t n, const double *x, const double *y, do
 
 int b2f_vector_add(b2f_ctx *ctx, int64_t n, const double *x, double a, const double *y, double *z)
 {
+   B2F_ON(ctx);
    B2F_REQUIRE(ctx && (n == 0 || (x && y && z)), "b2f_vector_add: NULL argument");
    return vector_add(ctx, n, x, a, y, z);
 }
@@ -1389,6 +1442,7 @@ int b2f_chebyshev_coefficients_h(int order, double max_eig_estimate, double *coe
 int b2f_power_method(b2f_operator *op, const double *dinv, double *v0, int num_steps, double tolerance,
                      double *eigenvalue_h)
 {
+   B2F_ON(op ? op->ctx : nullptr);
    B2F_REQUIRE(op && dinv && v0 && eigenvalue_h, "b2f_power_method: NULL argument");
    b2f_ctx *ctx = op->ctx;
    b2f_halo *halo = op->halo;
@@ -1427,6 +1481,7 @@ int b2f_power_method(b2f_operator *op, const double *dinv, double *v0, int num_s
 int b2f_chebyshev_create(b2f_operator *op, const double *diag, int order, double max_eig_estimate,
                          b2f_chebyshev **out)
 {
+   B2F_ON(op ? op->ctx : nullptr);
    B2F_REQUIRE(op && diag && out, "b2f_chebyshev_create: NULL argument");
    *out = nullptr;
    double coeffs[5] = {0, 0, 0, 0, 0};
@@ -1461,6 +1516,7 @@ void b2f_chebyshev_destroy(b2f_chebyshev *c)
 
 int b2f_chebyshev_mult(b2f_chebyshev *c, const double *x, double *y)
 {
+   B2F_ON((c && c->op) ? c->op->ctx : nullptr);
    B2F_REQUIRE(c && x && y, "b2f_chebyshev_mult: NULL argument");
    B2F_REQUIRE(x != y, "b2f_chebyshev_mult: x and y alias");
    return chebyshev_apply(c, x, y);
@@ -1591,6 +1647,7 @@ int b2f_pcg(b2f_operator *op, const double *dinv, const double *b, double *x,
             const b2f_pcg_options *opt, b2f_pcg_result *result_h, double *history_h,
             int history_capacity)
 {
+   B2F_ON(op ? op->ctx : nullptr);
    return pcg_impl(op, dinv, nullptr, b, x, opt, result_h, history_h, history_capacity);
 }
 
@@ -1598,6 +1655,7 @@ int b2f_pcg_chebyshev(b2f_operator *op, b2f_chebyshev *cheb, const double *b, do
                       const b2f_pcg_options *opt, b2f_pcg_result *result_h, double *history_h,
                       int history_capacity)
 {
+   B2F_ON(op ? op->ctx : nullptr);
    B2F_REQUIRE(cheb && cheb->op == op, "b2f_pcg_chebyshev: smoother was built for another operator");
    return pcg_impl(op, nullptr, cheb, b, x, opt, result_h, history_h, history_capacity);
 }

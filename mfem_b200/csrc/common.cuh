@@ -78,6 +78,26 @@ struct b2f_ctx
 
 namespace b2f
 {
+// Several contexts (devices) may live in one process: every entry point that allocates or launches
+// makes its context's device current for the duration of the call and restores the caller's.
+struct DeviceGuard
+{
+   int prev = -1;
+   explicit DeviceGuard(const b2f_ctx *ctx)
+   {
+      if (!ctx) { return; }
+      int cur = -1;
+      if (cudaGetDevice(&cur) == cudaSuccess && cur != ctx->device)
+      {
+         prev = cur;
+         cudaSetDevice(ctx->device);
+      }
+   }
+   ~DeviceGuard() { if (prev >= 0) { cudaSetDevice(prev); } }
+   DeviceGuard(const DeviceGuard &) = delete;
+};
+#define B2F_ON(ctx_expr) b2f::DeviceGuard b2f_device_guard_(ctx_expr)
+
 // record an event on the context's stream when timing is enabled (pairs: before, after)
 inline void timing_mark(b2f_ctx *ctx)
 {
