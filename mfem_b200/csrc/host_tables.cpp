@@ -6,7 +6,7 @@
 //   TensorBasisElement::GetTensorDofToQuad                fem/fe/fe_base.cpp:2697
 //   IntegrationRule(irx,iry[,irz]) tensor weights         fem/intrules.cpp:43-96
 // The same Newton iterations / barycentric formulas are used so that B, G, W agree with
-// the reference to the last bit (checked in tests/test_host_tables.py against fixtures
+// the reference to the last bit (checked in tests/test_host_cpu.py against fixtures
 // dumped from the reference).
 #include <cmath>
 #include <cstdlib>

@@ -1,6 +1,4 @@
 set -x
-for c in "5 7 66" "1 4 92" "3 4 116" "3 4 133"; do
-  set -- $c
-  timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:pa_apply_3d_eo -s 3 -c 1 --csv --log-file gpurun_out/r02_traffic_bp$1_p$2_n$3.csv python tools/opbench.py --bp $1 --p $2 --n $3 --reps 2 > gpurun_out/r02_traffic_bp$1_p$2_n$3.log 2>&1
-  tail -4 gpurun_out/r02_traffic_bp$1_p$2_n$3.csv
-done
+python -m pytest tests -m gpu -x -q > gpurun_out/r02_gputest_5.log 2>&1; tail -4 gpurun_out/r02_gputest_5.log
+python bench.py --bp 5 --steps 5 --warmup 3 --no-sweep > gpurun_out/r02_bench_bp5_c5.json 2> gpurun_out/r02_bench_bp5_c5.err; cut -c1-400 gpurun_out/r02_bench_bp5_c5.json; tail -3 gpurun_out/r02_bench_bp5_c5.err
+python bench.py --bp 1 --steps 5 --warmup 3 --no-sweep > gpurun_out/r02_bench_bp1_c2.json 2> gpurun_out/r02_bench_bp1_c2.err; cut -c1-400 gpurun_out/r02_bench_bp1_c2.json; tail -3 gpurun_out/r02_bench_bp1_c2.err
