@@ -855,7 +855,7 @@ static int local_mult_fused(b2f_operator *op, const double *x_l, double *y_l, co
 {
    b2f_ctx *ctx = op->ctx;
    const b2f_restriction *r = op->r;
-   B2F_CUDA(cudaMemsetAsync(y_l, 0, sizeof(double) * (size_t)r->ndofs * r->vdim, ctx->stream));
+   B2F_TRY(zero_vector(ctx, y_l, (int64_t)r->ndofs * r->vdim));
    for (size_t i = 0; i < op->integ.size(); i++)
    {
       b2f_pa *pa = op->integ[i];
@@ -996,7 +996,7 @@ static int rap_mult(b2f_operator *op, const double *x, double *y, bool constrain
          B2F_TRY(ensure(&op->xl, nl));
          B2F_TRY(ensure(&op->yl, nl));
          xl = op->xl; yl = op->yl;
-         B2F_CUDA(cudaMemcpyAsync(xl, x, sizeof(double) * nt, cudaMemcpyDeviceToDevice, ctx->stream));
+         B2F_TRY(copy_vector(ctx, xl, x, nt));
       }
       if (halo_is_p2p(op->halo) && operator_can_split(op))
       {
@@ -1008,7 +1008,7 @@ static int rap_mult(b2f_operator *op, const double *x, double *y, bool constrain
          const int *idx = (constrained_mask && op->fused_idx) ? op->fused_idx : op->r->gather_map;
          const int64_t ni = op->n_interior, ne = op->r->ne, half = ni / 2;
          B2F_TRY(halo_p_push(op->halo, xl));
-         B2F_CUDA(cudaMemsetAsync(yl, 0, sizeof(double) * (size_t)nl, ctx->stream));
+         B2F_TRY(zero_vector(ctx, yl, nl));
          B2F_TRY(local_mult_range(op, xl, yl, idx, 0, half, dot_acc));
          B2F_TRY(halo_p_wait(op->halo, xl));
          B2F_TRY(local_mult_range(op, xl, yl, idx, ni, ne, dot_acc));
@@ -1022,7 +1022,7 @@ static int rap_mult(b2f_operator *op, const double *x, double *y, bool constrain
          B2F_TRY(local_mult(op, xl, yl, constrained_mask, dot_acc));
          B2F_TRY(halo_mult_transpose_inplace(op->halo, yl));
       }
-      if (!lcap) { B2F_CUDA(cudaMemcpyAsync(y, yl, sizeof(double) * nt, cudaMemcpyDeviceToDevice, ctx->stream)); }
+      if (!lcap) { B2F_TRY(copy_vector(ctx, y, yl, nt)); }
       return B2F_OK;
    }
    B2F_TRY(ensure(&op->xl, nl));
@@ -1335,9 +1335,7 @@ int b2f_vector_dot(b2f_ctx *ctx, int64_t n, const double *x, const double *y, do
    B2F_REQUIRE(ctx && result_h && (n == 0 || (x && y)), "b2f_vector_dot: NULL argument");
    if (n == 0) { *result_h = 0.0; return B2F_OK; }
    B2F_TRY(dot_to_device(ctx, n, x, y, ctx->d_scalars + 63));
-   B2F_CUDA(cudaMemcpyAsync(ctx->h_scalars + 63, ctx->d_scalars + 63, sizeof(double),
-                            cudaMemcpyDeviceToHost, ctx->stream));
-   B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+   B2F_TRY(publish_scalars(ctx, ctx->d_scalars + 63, ctx->h_scalars + 63, 1));
    *result_h = ctx->h_scalars[63];
    return B2F_OK;
 }
@@ -1463,9 +1461,7 @@ int b2f_power_method(b2f_operator *op, const double *dinv, double *v0, int num_s
       B2F_TRY(vector_mul(ctx, n, dinv, q, vb));                // then the Jacobi smoother
       B2F_TRY(dot_to_device(ctx, n, va, vb, slot));
       if (halo) { B2F_TRY(halo_allreduce_sum(halo, slot, 1)); }
-      B2F_CUDA(cudaMemcpyAsync(ctx->h_scalars + 62, slot, sizeof(double), cudaMemcpyDeviceToHost,
-                               ctx->stream));
-      B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+      B2F_TRY(publish_scalars(ctx, slot, ctx->h_scalars + 62, 1));
       const double eig_new = ctx->h_scalars[62];
       const double diff = fabs((eig_new - eig) / eig);
       eig = eig_new;
@@ -1575,8 +1571,8 @@ static int pcg_impl(b2f_operator *op, const double *dinv, b2f_chebyshev *cheb, c
    };
 
    // r = b; x = 0   (iterative_mode = false, solvers.cpp:881-884)
-   B2F_CUDA(cudaMemcpyAsync(r, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
-   B2F_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * n, ctx->stream));
+   B2F_TRY(copy_vector(ctx, r, b, n));
+   B2F_TRY(zero_vector(ctx, x, n));
    const double *zz = r; // "z" of the unpreconditioned iteration is r itself
    if (cheb)
    {
@@ -1588,7 +1584,7 @@ static int pcg_impl(b2f_operator *op, const double *dinv, b2f_chebyshev *cheb, c
       B2F_TRY(vector_mul(ctx, n, dinv, r, z)); // z = B r
       zz = z;
    }
-   B2F_CUDA(cudaMemcpyAsync(d, zz, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+   B2F_TRY(copy_vector(ctx, d, zz, n));
    B2F_TRY(dot_to_device(ctx, n, d, r, pcg_dot_slot(st)));
    B2F_TRY(reduce());
    B2F_TRY(pcg_after_nom0(ctx, st, opt->rel_tol, opt->abs_tol, opt->max_iter, hist,
@@ -1602,9 +1598,8 @@ static int pcg_impl(b2f_operator *op, const double *dinv, b2f_chebyshev *cheb, c
    double nom0 = 0, betanom = 0;
    auto poll = [&]() -> int
    {
-      B2F_CUDA(cudaMemcpyAsync(ctx->h_scalars, st, pcg_state_bytes(), cudaMemcpyDeviceToHost,
-                               ctx->stream));
-      B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+      // (a store kernel into the pinned mirror, not a DMA copy: see publish_scalars)
+      B2F_TRY(publish_scalars(ctx, (const double *)st, ctx->h_scalars, (pcg_state_bytes() + 7) / 8));
       memcpy(host_state, ctx->h_scalars, pcg_state_bytes());
       pcg_read_state(host_state, &iter, &done, &converged, &final_iter, &nom0, &betanom);
       return B2F_OK;

@@ -234,6 +234,9 @@ int setup_from_nodes(b2f_ctx *ctx, int kind, int dim, int q1d, int64_t ne, const
                      double coeff, double *D);
 // vector_ops.cu
 int fill(b2f_ctx *ctx, double *x, double v, int64_t n);
+// kernel-based zero fill / copy of the solver's hot path (never a copy-engine operation)
+int zero_vector(b2f_ctx *ctx, double *x, int64_t n);
+int copy_vector(b2f_ctx *ctx, double *dst, const double *src, int64_t n);
 int set_entries(b2f_ctx *ctx, double *x, const int *idx, int n, double v);
 int copy_entries(b2f_ctx *ctx, double *dst, const double *src, const int *idx, int n);
 // dst[idx] = src[idx] and acc[0] += sum src[idx]^2
@@ -241,4 +244,6 @@ int copy_entries_sqsum(b2f_ctx *ctx, double *dst, const double *src, const int *
 // *out = sum acc[0..63]; acc[] = 0
 int collect_dot(b2f_ctx *ctx, double *acc, double *out);
 int dot_to_device(b2f_ctx *ctx, int64_t n, const double *x, const double *y, double *d_out);
+// n device doubles -> pinned host memory through a store kernel (no copy engine), then a stream sync
+int publish_scalars(b2f_ctx *ctx, const double *d_src, double *h_dst, int n);
 } // namespace b2f

@@ -700,9 +700,8 @@ int b2f_halo_dot(b2f_halo *h, int64_t n, const double *x, const double *y, doubl
    else { B2F_CUDA(cudaMemsetAsync(slot, 0, sizeof(double), ctx->stream)); }
    int rc = halo_allreduce_sum(h, slot, 1);
    if (rc) { return rc; }
-   B2F_CUDA(cudaMemcpyAsync(ctx->h_scalars + 62, slot, sizeof(double), cudaMemcpyDeviceToHost,
-                            ctx->stream));
-   B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+   rc = publish_scalars(ctx, slot, ctx->h_scalars + 62, 1);
+   if (rc) { return rc; }
    *result_h = ctx->h_scalars[62];
    return B2F_OK;
 }

@@ -365,7 +365,53 @@ __global__ void pcg_after_den0_kernel(PcgState *st)
    if (st->den == 0.0) { st->done = 1; st->converged = 0; st->final_iter = 0; }
 }
 
+// zero / copy as KERNELS (128-bit accesses).  cudaMemsetAsync / cudaMemcpyAsync may be served by a
+// copy engine, where they queue behind whatever host<->device transfers the application has in
+// flight (bench.py's double-buffered end-to-end path): the solver's per-iteration zero fill and its
+// start-up copies must not wait for a 0.8 GB download.
+__global__ void __launch_bounds__(VT) zero_kernel(double *__restrict__ x, int64_t n)
+{
+   const int64_t n2 = n / 2;
+   double2 *x2 = reinterpret_cast<double2 *>(x);
+   for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * VT)
+   {
+      x2[i] = make_double2(0.0, 0.0);
+   }
+   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) { x[n - 1] = 0.0; }
+}
+
+__global__ void __launch_bounds__(VT) copy_kernel(double *__restrict__ dst, const double *__restrict__ src, int64_t n)
+{
+   const int64_t n2 = n / 2;
+   double2 *d2 = reinterpret_cast<double2 *>(dst);
+   const double2 *s2 = reinterpret_cast<const double2 *>(src);
+   for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < n2; i += (int64_t)gridDim.x * VT) { d2[i] = s2[i]; }
+   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) { dst[n - 1] = src[n - 1]; }
+}
+
 // ---- host launchers --------------------------------------------------------------------
+int zero_vector(b2f_ctx *ctx, double *x, int64_t n)
+{
+   if (n == 0) { return B2F_OK; }
+   if (reinterpret_cast<uintptr_t>(x) & 15) { return fill(ctx, x, 0.0, n); } // (never for cudaMalloc'ed vectors)
+   zero_kernel<<<stream_grid(ctx, n / 2 + 1, 4), VT, 0, ctx->stream>>>(x, n);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
+int copy_vector(b2f_ctx *ctx, double *dst, const double *src, int64_t n)
+{
+   if (n == 0 || dst == src) { return B2F_OK; }
+   if ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15)
+   {
+      B2F_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+      return B2F_OK;
+   }
+   copy_kernel<<<stream_grid(ctx, n / 2 + 1, 4), VT, 0, ctx->stream>>>(dst, src, n);
+   B2F_LAUNCH_CHECK(ctx);
+   return B2F_OK;
+}
+
 int fill(b2f_ctx *ctx, double *x, double v, int64_t n)
 {
    if (n == 0) { return B2F_OK; }
@@ -470,6 +516,25 @@ int normalize_by(b2f_ctx *ctx, int64_t n, const double *d_normsq, double *v)
 
 // pieces of the PCG loop, called from capi.cu
 int pcg_state_bytes() { return (int)sizeof(PcgState); }
+
+// Device scalars -> the context's pinned host mirror WITHOUT a DMA copy: a one-warp kernel stores
+// straight into the (UVA-mapped) pinned buffer.  A cudaMemcpyAsync of a few bytes would queue on
+// the device-to-host copy engine behind whatever the application has in flight there -- with a
+// 0.8 GB solution download of the previous solve running, every host poll of the PCG state stalled
+// the solver for the rest of that download (the end-to-end numbers of bench.py at 4 and 8 GPUs).
+__global__ void publish_scalars_kernel(const double *__restrict__ src, volatile double *dst_host, int n)
+{
+   for (int i = threadIdx.x; i < n; i += blockDim.x) { dst_host[i] = src[i]; }
+   __threadfence_system();
+}
+
+int publish_scalars(b2f_ctx *ctx, const double *d_src, double *h_dst, int n)
+{
+   publish_scalars_kernel<<<1, 32, 0, ctx->stream>>>(d_src, h_dst, n);
+   B2F_LAUNCH_CHECK(ctx);
+   B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+   return B2F_OK;
+}
 
 int pcg_start(b2f_ctx *ctx, void *state, int64_t n, const double *d, const double *r,
               double rel_tol, double abs_tol, int max_iter, double *history, int history_cap,
