@@ -592,7 +592,6 @@ public:
       }
       // stock integrators keep their own AssemblePA only when the form stays with MFEM; when the
       // library covers the form their quadrature data is built once, by the library
-      std::vector<b2f_pa *> probe;
       if (all_b200) { mfem::PABilinearFormExtension::Assemble(); }
       if (CollectIntegrators(*form, integ, twins, symmetric))
       {
