@@ -131,6 +131,14 @@ constexpr int tuned_persist_eo(int kind, int D, int Q)
    return -1;
 }
 
+// thread-per-element mass kernel (pa_apply_tpe.cuh) by default for this D1D (Q1D = D1D + 1)?
+// Measured (profiles/r02_opbench_tpe.txt): BP1 p=1 43 -> 76.5 % of the HBM roofline; p=2 no gain
+// (229 registers, 8 warps per SM: 49.7 vs 50.5 %), so the pencil kernel stays the default there.
+constexpr bool tuned_tpe_mass(int D)
+{
+   return D == 2;
+}
+
 // the even-odd kernel (and with it the fused x.(Ax) accumulation) runs for 3D integrators with
 // a symmetric basis and a (D,Q) in the dispatch tables
 inline bool basis_is_symmetric(const b2f_pa *pa);

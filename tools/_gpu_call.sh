@@ -1,5 +1,5 @@
 set -x
-python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_final_n1.json 2> gpurun_out/r02_final_n1.err
-python -c "
-import json; l=json.loads(open('gpurun_out/r02_final_n1.json').read().strip().splitlines()[-1]); print('N=1', round(l['value'],2), round(l['e2e']['value'],2), round(l['roofline']['frac'],3), l['gpu_launches'], l['clocks'])"
-tail -3 gpurun_out/r02_final_n1.err
+B2F_TPE=1 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "mass3d_p1 or mass3d_p2 or checksum or large_properties or end_to_end" > gpurun_out/r02_gputest_tpe.log 2>&1; tail -4 gpurun_out/r02_gputest_tpe.log
+python tools/opbench.py --bp 1 --p 1 --n 270 --variants notpe,tpe --reps 20 > gpurun_out/r02_tpe.log 2>&1
+python tools/opbench.py --bp 1 --p 2 --n 135 --variants notpe,tpe --reps 20 >> gpurun_out/r02_tpe.log 2>&1
+cat gpurun_out/r02_tpe.log

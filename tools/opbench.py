@@ -5,7 +5,8 @@
     python tools/opbench.py --sweep 3,1,5 --variants c0,c1,c2     (p = 1..8)
 
 A variant is a '+'-joined list of cN (elements-per-CTA candidate B2F_NEB_CAND), pfN (L2
-prefetch distance B2F_PF, 0 = off) and vN (experimental kernel B2F_VARIANT).
+prefetch distance B2F_PF, 0 = off), persist (B2F_PERSIST=1), tpe / notpe (B2F_TPE: thread-per-element
+kernel of the lowest orders) and g (general pencil kernel).
 
 Prints one line per variant: kernel ms (CUDA events around the launches), GDOF/s and the
 achieved algorithmic GB/s (SURVEY.md section 8d bytes) against MEASURED_PEAKS.json.
@@ -74,7 +75,7 @@ def run_case(bp, p, n, variants, reps):
     ab = (k * ir.nq1d ** 3 * 8 + 4 * (p + 1) ** 3) * fes.ne + 16 * N  # D and indices once per element
     print(f"BP{bp} p={p} n={n}: NE={fes.ne} dofs={N} algorithmic bytes/apply={ab/1e9:.3f} GB", flush=True)
     for v in variants:
-        for key in ("B2F_VARIANT", "B2F_PF", "B2F_NEB_CAND", "B2F_GENERAL_KERNEL", "B2F_PERSIST"):
+        for key in ("B2F_VARIANT", "B2F_PF", "B2F_NEB_CAND", "B2F_GENERAL_KERNEL", "B2F_PERSIST", "B2F_TPE"):
             os.environ.pop(key, None)
         for kv in v.split("+"):
             if kv.startswith("c"):
@@ -83,6 +84,10 @@ def run_case(bp, p, n, variants, reps):
                 os.environ["B2F_PF"] = kv[2:]
             elif kv == "persist":
                 os.environ["B2F_PERSIST"] = "1"
+            elif kv == "tpe":
+                os.environ["B2F_TPE"] = "1"   # thread-per-element kernel (lowest orders)
+            elif kv == "notpe":
+                os.environ["B2F_TPE"] = "0"
             elif kv == "g":
                 os.environ["B2F_GENERAL_KERNEL"] = "1"
             elif kv.startswith("v"):
