@@ -132,8 +132,10 @@ constexpr int tuned_persist_eo(int kind, int D, int Q)
 }
 
 // thread-per-element mass kernel (pa_apply_tpe.cuh) by default for this D1D (Q1D = D1D + 1)?
-// Measured (profiles/r02_opbench_tpe.txt): BP1 p=1 43 -> 76.5 % of the HBM roofline; p=2 no gain
-// (229 registers, 8 warps per SM: 49.7 vs 50.5 %), so the pencil kernel stays the default there.
+// Measured (profiles/r02_opbench_tpe.txt): BP1 p=1 43 -> 76.5 % of the HBM roofline (74.9 % at 50 M
+// dofs); p=2 no gain (229 registers, 8 warps per SM: 49.7 vs 50.5 %; staging the 27-int index rows
+// through shared memory made it slower), so the pencil kernel stays the default there.  A diffusion
+// twin for (2,2) (BP5 p=1) was written, parity-clean, and dropped: 71.5 vs 72.2 %.
 constexpr bool tuned_tpe_mass(int D)
 {
    return D == 2;

@@ -24,7 +24,8 @@ DRV = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
 CASES = [(3, 4, 16, 0), (3, 4, 24, 0), (3, 4, 40, 0), (3, 1, 64, 0), (3, 2, 32, 0), (3, 8, 8, 0),
          (3, 6, 12, 0), (3, 7, 10, 0),
          (1, 4, 16, 0), (1, 4, 40, 0), (1, 6, 12, 0), (1, 8, 8, 0),
-         (5, 7, 10, 0), (5, 7, 8, 1), (5, 7, 24, 1), (5, 4, 24, 1)]
+         (5, 7, 10, 0), (5, 7, 8, 1), (5, 7, 24, 1), (5, 4, 24, 1), (5, 1, 64, 0), (5, 1, 48, 1), (1, 1, 64, 0),
+         (1, 2, 32, 0), (5, 2, 32, 0)]
 
 
 def run(mode, bp, p, n, curved):

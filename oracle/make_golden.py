@@ -43,6 +43,8 @@ CASES = {
     "mass3d_p8_n2": dict(dim=3, n=2, p=8, kind="mass"),
     "mass3d_p3_n2_curved": dict(dim=3, n=2, p=3, kind="mass", curved=1),
     # BP5-style collocated GLL diffusion (Q = p+1, B = I)
+    "bp5_3d_p1_n4": dict(dim=3, n=4, p=1, kind="diffusion", quad="gll"),
+    "bp5_3d_p1_n3_curved": dict(dim=3, n=3, p=1, kind="diffusion", quad="gll", curved=1),
     "bp5_3d_p2_n3": dict(dim=3, n=3, p=2, kind="diffusion", quad="gll"),
     "bp5_3d_p4_n2": dict(dim=3, n=2, p=4, kind="diffusion", quad="gll"),
     "bp5_3d_p7_n2": dict(dim=3, n=2, p=7, kind="diffusion", quad="gll"),

@@ -862,3 +862,19 @@ def test_diagonal_out_of_table_sizes(dev, kind, dim, D1D, Q1D):
     it.AssembleDiagonalPA(de)  # accumulates
     assert relerr(host(de), 2 * ref) < TOL
     it.close()
+
+
+@pytest.mark.parametrize("name", ["mass3d_p1_n3", "mass3d_p2_n2"])
+@pytest.mark.parametrize("tpe", ["0", "1"])
+def test_thread_per_element_kernels(dev, name, tpe, monkeypatch):
+    """The lowest orders have two fused kernels -- the five-stage pencil kernel and the
+    thread-per-element kernel (csrc/pa_apply_tpe.cuh; the default where it measured faster: BP1 p=1).
+    Both must reproduce the reference's operator, whichever the tuned table picks."""
+    monkeypatch.setenv("B2F_TPE", tpe)
+    g = load_golden(name)
+    a, it, R = make_form(dev, g)
+    x = dev.to_device(g["x"])
+    y = dev.empty(int(g["ndofs"][0]))
+    a.Mult(x, y)
+    assert relerr(host(y), g["y"]) < TOL
+    a.close(); it.close(); R.close()
