@@ -261,7 +261,8 @@ struct EOStages
          }
       }
       // quadrature data of this line: NQD rows of Q doubles from the TMA-filled slab
-      if constexpr (C::TMA_OK) { mbar_wait(bar, parity); }
+      if constexpr (C::TMA_OK) { mbar_wait(bar, C::ALIAS ? 0u : parity); }
+      if constexpr (C::ALIAS) { mbar_wait(bar + 1, parity); } // the slab's tail (pa_eo_cfg.cuh: ALIAS)
       const double *dq = qd + e * C::DS + Q * (qy + Q * qz);
       if (DIFF)
       {
@@ -518,8 +519,8 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
    // function of the shared-memory address bits); the mbarrier follows the buffers
    unsigned char *sbase = C::SWZ ? smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) : smem_raw;
    double *qd = reinterpret_cast<double *>(C::SWZ ? sbase : sbase + 16);
-   double *r1 = qd + C::QD;
-   double *r2 = r1 + C::R1;
+   double *r1 = C::ALIAS ? qd + (C::NQD * Q3 - C::QB) : qd + C::QD; // ALIAS: over the slab's tail
+   double *r2 = C::ALIAS ? qd + C::QD : r1 + C::R1;
    uint64_t *bar = reinterpret_cast<uint64_t *>(C::SWZ ? reinterpret_cast<unsigned char *>(r2 + C::R2) : sbase);
 
    const int t = threadIdx.x;
@@ -561,6 +562,15 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
             if (t == 0)
             {
                mbar_init(bar, 1);
+               if constexpr (C::ALIAS)
+               {
+                  // head of the slab now, tail after the z-stage (second barrier)
+                  mbar_init(bar + 1, 1);
+                  mbar_expect_tx(bar, (uint32_t)(C::NQD * Q3 - C::QB) * 8u);
+                  bulk_g2s(qd, qslab, (uint32_t)(C::NQD * Q3 - C::QB) * 8u, bar);
+               }
+               else
+               {
                mbar_expect_tx(bar, (uint32_t)(nev * C::NQD * Q3) * 8u);
                for (int e = 0; e < nev; e++)
                {
@@ -577,6 +587,7 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
                   {
                      bulk_g2s(qd + e * C::DS, qslab + (int64_t)e * (C::NQD * Q3), (uint32_t)(C::NQD * Q3) * 8u, bar);
                   }
+               }
                }
             }
          }
@@ -623,11 +634,22 @@ pa_apply_3d_eo_kernel(const __grid_constant__ EOBasis<D, Q> bs, const double *__
       if (t < C::T2) { S::stage2(bs, r1, r2, t); }
       if constexpr (!C::TMA_OK) { cp_async_wait_all(); }
       __syncthreads();
+      if constexpr (C::ALIAS)
+      {
+         // the y-stage buffer is dead: bring in the slab's tail over it (once per component: the
+         // z^T-stage overwrites it again)
+         if (t == 0)
+         {
+            fence_proxy_async(); // the region was just accessed through the generic proxy
+            mbar_expect_tx(bar + 1, (uint32_t)C::QB * 8u);
+            bulk_g2s(r1, qdata + e0 * (int64_t)(C::NQD * Q3) + (C::NQD * Q3 - C::QB), (uint32_t)C::QB * 8u, bar + 1);
+         }
+      }
       {
          double part = 0.0;
          if (t < C::T3)
          {
-            part = S::stage3(bs, r2, qd, t, bar, 0);
+            part = S::stage3(bs, r2, qd, t, bar, C::ALIAS ? (uint32_t)(c & 1) : 0u);
             if ((t % C::YQ) / Q >= nev) { part = 0.0; } // lines of a ragged tile: absent elements
          }
          if constexpr (DOT)
@@ -677,6 +699,7 @@ pa_apply_3d_eo_persistent_kernel(const __grid_constant__ EOBasis<D, Q> bs, const
 {
    using C = PipeCfg<KIND, D, Q, NEB>;
    using S = EOStages<KIND, D, Q, NEB, COLLOC, false>;
+   static_assert(!C::ALIAS, "the persistent form keeps the slab and the y-stage buffer apart");
    constexpr int D2 = C::D2, D3 = C::D3, Q3 = C::Q3, YQ = C::YQ;
    extern __shared__ __align__(16) unsigned char smem_raw[];
    unsigned char *sbase = C::SWZ ? smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) : smem_raw;

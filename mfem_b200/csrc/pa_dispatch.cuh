@@ -83,7 +83,8 @@ constexpr int smem_eo(int kind, int D, int Q, int n)
    const int q3 = Q * Q * Q;
    const bool tma = (nqd * q3) % 2 == 0, swz = tma && Q == 8; // (PipeCfg::SWZ4 is off)
    const int dp = (tma && !swz) ? L.dpad : (swz && Q == 4) ? 16 : 0;
-   return 16 + 8 * (n * (nqd * q3 + dp) + na * D * sa + nc * D * sc) + (swz ? 1024 : 0);
+   const bool alias = kind == B2F_KIND_DIFFUSION && tma && !swz && n == 1 && D >= 8; // PipeCfg::ALIAS
+   return 16 + 8 * (n * (nqd * q3 + dp) + (alias ? 0 : na * D * sa) + nc * D * sc) + (swz ? 1024 : 0);
 }
 
 // Elements per CTA, candidate i: 0 -> >= 4 CTAs per SM, 1 -> 3 CTAs, 2 -> 2 CTAs; <= 512 threads

@@ -87,7 +87,16 @@ struct PipeCfg
    static constexpr int DS = NQD * Q3 + ((TMA_OK && !SWZ) ? L.dpad : SWZ_PAD);
    static_assert(!SWZ || Q == 8 || ((DS * 8) % 256) == 128, "Q = 4 slabs must be an odd number of 128-byte lines");
    static constexpr int QD = NEB * DS;
-   static constexpr size_t SMEM = 16 + sizeof(double) * (size_t)(QD + R1 + R2) + (SWZ ? 1024 : 0);
+   // High orders (one element per CTA, D1D >= 8) are bound by residency: 63 / 87 KB per CTA leave 3 / 2
+   // CTAs per SM.  The y-stage buffer (R1 doubles) is dead between the z- and the z^T-stage -- exactly
+   // while the quadrature data is consumed -- so it is overlaid on the TAIL of the element's slab:
+   // the slab arrives in two bulk copies, the head at kernel entry, the last QB doubles (the region
+   // shared with the buffer) as soon as the z-stage has released it, on a second mbarrier.  52 / 73 KB
+   // per CTA: 4 / 3 CTAs per SM.
+   static constexpr bool ALIAS = DIFF && TMA_OK && !SWZ && NEB == 1 && D >= 8;
+   static constexpr int QB = ALIAS ? ((R1 + 1) / 2) * 2 : 0;   // doubles of the slab's tail, copied late
+   static_assert(!ALIAS || QB < NQD * Q3, "the aliased buffer must fit in the slab");
+   static constexpr size_t SMEM = 16 + sizeof(double) * (size_t)(QD + (ALIAS ? 0 : R1) + R2) + (SWZ ? 1024 : 0);
    static_assert(T1 <= NT && T2 <= NT, "one task per thread per stage");
 };
 
