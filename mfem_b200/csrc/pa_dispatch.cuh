@@ -83,7 +83,7 @@ constexpr int smem_eo(int kind, int D, int Q, int n)
    const int q3 = Q * Q * Q;
    const bool tma = (nqd * q3) % 2 == 0, swz = tma && Q == 8; // (PipeCfg::SWZ4 is off)
    const int dp = (tma && !swz) ? L.dpad : (swz && Q == 4) ? 16 : 0;
-   const bool alias = kind == B2F_KIND_DIFFUSION && tma && !swz && n == 1 && D >= 8; // PipeCfg::ALIAS
+   const bool alias = kind == B2F_KIND_DIFFUSION && tma && !swz && n == 1 && D >= B2F_ALIAS_MIN_D; // PipeCfg::ALIAS
    return 16 + 8 * (n * (nqd * q3 + dp) + (alias ? 0 : na * D * sa) + nc * D * sc) + (swz ? 1024 : 0);
 }
 

@@ -24,6 +24,9 @@
 //    conflict-free without touching the layout in HBM.
 #pragma once
 #include "pa_apply.cuh"
+#ifndef B2F_ALIAS_MIN_D
+#define B2F_ALIAS_MIN_D 8 // smallest D1D whose one-element tiles overlay the y-stage buffer on the slab tail
+#endif
 #include "pa_layout_table.h"
 
 namespace b2f
@@ -93,7 +96,7 @@ struct PipeCfg
    // the slab arrives in two bulk copies, the head at kernel entry, the last QB doubles (the region
    // shared with the buffer) as soon as the z-stage has released it, on a second mbarrier.  52 / 73 KB
    // per CTA: 4 / 3 CTAs per SM.
-   static constexpr bool ALIAS = DIFF && TMA_OK && !SWZ && NEB == 1 && D >= 8;
+   static constexpr bool ALIAS = DIFF && TMA_OK && !SWZ && NEB == 1 && D >= B2F_ALIAS_MIN_D;
    static constexpr int QB = ALIAS ? ((R1 + 1) / 2) * 2 : 0;   // doubles of the slab's tail, copied late
    static_assert(!ALIAS || QB < NQD * Q3, "the aliased buffer must fit in the slab");
    static constexpr size_t SMEM = 16 + sizeof(double) * (size_t)(QD + (ALIAS ? 0 : R1) + R2) + (SWZ ? 1024 : 0);

@@ -1,7 +1,7 @@
 set -x
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_vector.py -m gpu -x -q -k "p7 or p8 or checksum or large_properties" > gpurun_out/r02_gputest_alias.log 2>&1; tail -4 gpurun_out/r02_gputest_alias.log
-for c in "3 7 39" "3 8 34" "5 8 34"; do
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "p5 or p6 or p7 or checksum" > gpurun_out/r02_gputest_alias6.log 2>&1; tail -3 gpurun_out/r02_gputest_alias6.log
+for c in "3 5 54" "5 5 54" "5 6 45" "3 7 39"; do
   set -- $c
-  python tools/opbench.py --bp $1 --p $2 --n $3 --variants c0,c1 --reps 20 >> gpurun_out/r02_alias.log 2>&1
+  python tools/opbench.py --bp $1 --p $2 --n $3 --variants c0 --reps 20 >> gpurun_out/r02_alias6.log 2>&1
 done
-cat gpurun_out/r02_alias.log
+cat gpurun_out/r02_alias6.log
