@@ -128,3 +128,52 @@ def test_vector_end_to_end_own_tables(dev, name):
     assert abs(cg.GetNumIterations() - int(g["pcg_iters"][0])) <= 1
     assert relerr(host(X), g["X_sol"]) < 1e-6
     a.close(); it.close()
+
+
+@pytest.mark.parametrize("name", ["diff3d_p7_n2", "diff3d_p8_n2", "bp5_3d_p7_n2", "mass3d_p8_n2"])
+@pytest.mark.parametrize("byvdim", [1, 0])
+def test_vector_operator_is_the_scalar_one_per_component_at_high_order(dev, name, byvdim):
+    """Vector{Diffusion,Mass}Integrator acts on every component with the scalar operator
+    (fem/integ/bilininteg_vecdiffusion_pa.cpp, bilininteg_vecmass_pa.cpp).  At D1D >= 8 the fused
+    kernel keeps the element's quadrature data in shared memory across the components while the
+    y-stage buffer is overlaid on the slab's tail (PipeCfg::ALIAS: the tail is re-fetched per
+    component); the scalar fixtures of p = 7, 8 pin that path: y_c = A x_c to 1e-12."""
+    import mfem_b200 as m
+    g = load_golden(name)
+    dim, D1D, Q1D, NE, nd = (int(g[k][0]) for k in ("dim", "D1D", "Q1D", "NE", "ndofs"))
+    vdim = 3
+    it = m.MassIntegrator() if bool(g["is_mass"][0]) else m.DiffusionIntegrator()
+    it.assemble_from_factors(dev, dim, D1D, Q1D, NE, g["B"], g["G"], g["W"], J=g["J"], detJ=g["detJ"])
+    R = m.ElementRestriction.from_tables(dev, NE, D1D ** dim, nd, g["gather_map"], g["offsets"], g["indices"],
+                                         vdim=vdim, byvdim=byvdim)
+
+    class _Fes:
+        pass
+    fes = _Fes()
+    fes.ne, fes.dof, fes.ndofs = NE, D1D ** dim, nd
+    fes.GetElementRestriction = lambda d: R
+    a = m.BilinearForm(dev, fes)
+    a.AddDomainIntegrator(it)
+    a.Assemble()
+    rng = np.random.default_rng(5)
+    comps = [g["x"], rng.random(nd), rng.random(nd) - 0.5]
+    xv = np.stack(comps, axis=1).ravel() if byvdim else np.concatenate(comps)
+    yv = dev.empty(nd * vdim)
+    a.Mult(dev.to_device(xv), yv)
+    yh = host(yv)
+    # scalar reference: the fixture's y for component 0, the same (linear) operator for the others
+    Rs = m.ElementRestriction.from_tables(dev, NE, D1D ** dim, nd, g["gather_map"], g["offsets"], g["indices"])
+    fs = _Fes()
+    fs.ne, fs.dof, fs.ndofs = NE, D1D ** dim, nd
+    fs.GetElementRestriction = lambda d: Rs
+    s = m.BilinearForm(dev, fs)
+    s.AddDomainIntegrator(it)
+    s.Assemble()
+    for c in range(vdim):
+        yc = yh[c::vdim] if byvdim else yh[c * nd:(c + 1) * nd]
+        ys = dev.empty(nd)
+        s.Mult(dev.to_device(comps[c]), ys)
+        assert relerr(yc, host(ys)) < TOL
+        if c == 0:
+            assert relerr(yc, g["y"]) < TOL
+    a.close(); s.close(); it.close(); R.close(); Rs.close()

@@ -1,7 +1,5 @@
 set -x
-for v in base m6 m8; do
-  if [ $v = base ]; then unset B2F_LIB; else export B2F_LIB=$PWD/tools/_build/$v/libb200fem.so; fi
-  echo "=== $v" >> gpurun_out/r02_tpe_minb.log
-  python tools/opbench.py --bp 1 --p 1 --n 270 --variants 0 --reps 20 >> gpurun_out/r02_tpe_minb.log 2>&1
-done
-grep -v "^BP" gpurun_out/r02_tpe_minb.log
+python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_final3_n1.json 2> gpurun_out/r02_final3_n1.err
+python -c "
+import json; l=json.loads(open('gpurun_out/r02_final3_n1.json').read().strip().splitlines()[-1]); print('N=1', round(l['value'],2), round(l['e2e']['value'],2), round(l['roofline']['frac'],3), l['clocks']['sm_mhz'])"
+tail -3 gpurun_out/r02_final3_n1.err
