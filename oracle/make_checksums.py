@@ -25,7 +25,10 @@ CASES = [(3, 4, 16, 0), (3, 4, 24, 0), (3, 4, 40, 0), (3, 1, 64, 0), (3, 2, 32, 
          (3, 6, 12, 0), (3, 7, 10, 0),
          (1, 4, 16, 0), (1, 4, 40, 0), (1, 6, 12, 0), (1, 8, 8, 0),
          (5, 7, 10, 0), (5, 7, 8, 1), (5, 7, 24, 1), (5, 4, 24, 1), (5, 1, 64, 0), (5, 1, 48, 1), (1, 1, 64, 0),
-         (1, 2, 32, 0), (5, 2, 32, 0)]
+         (1, 2, 32, 0), (5, 2, 32, 0),
+         # the rest of the metric table (BP1 / BP3 / BP5 x p = 1..8): every cell has a reference checksum
+         (3, 3, 21, 0), (3, 5, 13, 0), (1, 3, 21, 0), (1, 5, 13, 0), (1, 7, 10, 0),
+         (5, 3, 21, 0), (5, 4, 16, 0), (5, 5, 13, 0), (5, 6, 12, 0), (5, 8, 8, 0)]
 
 
 def run(mode, bp, p, n, curved):
@@ -38,8 +41,14 @@ def run(mode, bp, p, n, curved):
 
 
 def main():
+    path = os.path.join(ROOT, "tests", "golden", "checksums.json")
     res = {}
+    if os.path.isfile(path) and "--all" not in sys.argv:
+        with open(path) as f:
+            res = json.load(f)["cases"]  # keep what is there, add what is missing (--all: redo everything)
     for bp, p, n, curved in CASES:
+        if f"bp{bp}_p{p}_n{n}" + ("_curved" if curved else "") in res:
+            continue
         m, c = run("mult", bp, p, n, curved), run("pcg", bp, p, n, curved)
         key = f"bp{bp}_p{p}_n{n}" + ("_curved" if curved else "")
         res[key] = dict(bp=bp, p=p, n=n, curved=curved, ndofs=m["ndofs"], ne=m["ne"], op_norm=m["norm"],
