@@ -133,13 +133,18 @@ constexpr int tuned_persist_eo(int kind, int D, int Q)
 }
 
 // thread-per-element mass kernel (pa_apply_tpe.cuh) by default for this D1D (Q1D = D1D + 1)?
-// Measured (profiles/r02_opbench_tpe.txt): BP1 p=1 43 -> 76.5 % of the HBM roofline (74.9 % at 50 M
-// dofs); p=2 no gain (229 registers, 8 warps per SM: 49.7 vs 50.5 %; staging the 27-int index rows
-// through shared memory made it slower), so the pencil kernel stays the default there.  A diffusion
-// twin for (2,2) (BP5 p=1) was written, parity-clean, and dropped: 71.5 vs 72.2 %.
+// Measured (profiles/r02_opbench_tpe.txt, r02_opbench_tpe_p2_*.txt): BP1 p=1 43 -> 76.5 % of the HBM
+// roofline, 79 % with the L2 prefetch of the next tile.  p=2: the first build (27-int index rows read
+// one int per lane, Q^3 array live: 229 registers) tied with the pencil kernel at 50 %; with the index
+// tile staged through shared memory (the strided row reads were 27 LSU wavefronts per element, as many
+// as everything else together), the z / D / z^T stages fused per column (184 registers) and the
+// prefetch it reaches 65-69 %.  Tile shapes 64x5, 96x3, 160x2, 256x1 and a variant with the index tile
+// aliased into the data region (3 CTAs per SM, two more barriers and a second index fetch) were all
+// slower than 128 threads x 2 CTAs.  A diffusion twin for (2,2) (BP5 p=1) was written, parity-clean,
+// and dropped: 71.5 vs 72.2 %.
 constexpr bool tuned_tpe_mass(int D)
 {
-   return D == 2;
+   return D == 2 || D == 3;
 }
 
 // the even-odd kernel (and with it the fused x.(Ax) accumulation) runs for 3D integrators with

@@ -149,6 +149,15 @@ __device__ __forceinline__ void cp_async8(void *dst, const void *src)
 {
    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit()
+{
+   asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N> // wait until at most N of this thread's committed groups are still in flight
+__device__ __forceinline__ void cp_async_wait_group()
+{
+   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all()
 {
    asm volatile("cp.async.wait_all;" ::: "memory");
