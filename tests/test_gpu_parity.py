@@ -878,3 +878,29 @@ def test_thread_per_element_kernels(dev, name, tpe, monkeypatch):
     a.Mult(x, y)
     assert relerr(host(y), g["y"]) < TOL
     a.close(); it.close(); R.close()
+
+
+@pytest.mark.parametrize("p,n", [(1, 11), (2, 7), (2, 5), (1, 5)])
+def test_thread_per_element_ragged_tiles(dev, p, n):
+    """The thread-per-element kernels on element counts that are not a multiple of their 128-element
+    tile (1331, 343, 125 elements): last tile partly empty, staged index and data tiles cut short.
+    Checked against the unfused path (restriction, pencil kernel, restriction^T) and the volume."""
+    import mfem_b200 as m
+    import torch
+    fes = m.FiniteElementSpace(m.Mesh.MakeCartesian3D(n, n, n), m.H1_FECollection(p, 3))
+    it = m.MassIntegrator(1.0, m.IntRules.Get(3, 2 * p + 3))
+    a = m.BilinearForm(dev, fes)
+    a.AddDomainIntegrator(it)
+    a.Assemble()
+    N = fes.GetNDofs()
+    gen = torch.Generator(device=dev.tdev).manual_seed(7)
+    x = torch.rand(N, dtype=torch.float64, device=dev.tdev, generator=gen)
+    ax, au = dev.empty(N), dev.empty(N)
+    a.Mult(x, ax)
+    a.MultUnfused(x, au)
+    dev.sync()
+    assert float(torch.linalg.norm(au - ax)) < 1e-12 * float(torch.linalg.norm(au))
+    a.Mult(torch.ones(N, dtype=torch.float64, device=dev.tdev), ax)
+    dev.sync()
+    assert abs(float(ax.sum()) - 1.0) < 1e-12
+    a.close(); it.close()
