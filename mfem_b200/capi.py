@@ -89,6 +89,13 @@ PROTOTYPES = {
     "b2f_pa_assemble_diagonal": (C.c_int, [vp, vp]),
     "b2f_domain_lf_assemble": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, i64, vp, vp, vp, vp, vp, i64,
                                          vp]),
+    "b2f_lor_vertex_coordinates": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, i64, vp, vp, vp]),
+    "b2f_lor_assemble_h1": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, i64, vp, i64, vp, C.c_int, C.c_int,
+                                      C.POINTER(vp)]),
+    "b2f_lor_csr": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "b2f_lor_sparse_ij": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
+    "b2f_lor_mult": (C.c_int, [vp, vp, vp]),
+    "b2f_lor_destroy": (None, [vp]),
     "b2f_operator_create": (C.c_int, [vp, vp, C.POINTER(vp), C.c_int, vp, C.c_int, C.POINTER(vp)]),
     "b2f_operator_destroy": (None, [vp]),
     "b2f_operator_mult": (C.c_int, [vp, vp, vp]),

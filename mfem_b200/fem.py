@@ -741,6 +741,112 @@ class OperatorChebyshevSmoother:
             pass
 
 
+class LORSparseMatrix:
+    """The assembled LOR matrix (mfem::SparseMatrix, CSR) resident on the device."""
+
+    def __init__(self, device, handle):
+        self.dev, self.h = device, handle
+        n, nnz = C.c_int(), capi.i64()
+        self._I, self._J, self._A = vp(), vp(), vp()
+        call("b2f_lor_csr", handle, C.byref(n), C.byref(nnz), C.byref(self._I), C.byref(self._J), C.byref(self._A))
+        self.n, self.nnz = n.value, nnz.value
+
+    def Height(self):
+        return self.n
+
+    def NumNonZeroElems(self):
+        return self.nnz
+
+    def device_pointers(self):
+        """(I, J, data) device addresses, e.g. for a multigrid set-up that takes CSR in place"""
+        return self._I.value, self._J.value, self._A.value
+
+    def _d2h(self, ptr, n, dtype):
+        a = np.empty(n, dtype=dtype)
+        if n:
+            call("b2f_memcpy_d2h", self.dev.ctx, _np_ptr(a), ptr, a.nbytes)
+            self.dev.sync()
+        return a
+
+    def GetI(self):
+        return self._d2h(self._I, self.n + 1, np.int32)
+
+    def GetJ(self):
+        return self._d2h(self._J, self.nnz, np.int32)
+
+    def GetData(self):
+        return self._d2h(self._A, self.nnz, np.float64)
+
+    def sparse_ij(self):
+        """BatchedLORAssembly::sparse_ij, (NE, (p+1)^3, 27); needs keep_sparse_ij at assembly"""
+        ptr, n = vp(), capi.i64()
+        call("b2f_lor_sparse_ij", self.h, C.byref(ptr), C.byref(n))
+        return self._d2h(ptr, n.value, np.float64)
+
+    def Mult(self, x, y):
+        call("b2f_lor_mult", self.h, _dp(x), _dp(y))
+
+    def close(self):
+        if self.h:
+            capi.lib().b2f_lor_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BatchedLORAssembly:
+    """BatchedLORAssembly (fem/lor/lor_batched.hpp:26-131) for H1 spaces in 3D: the low-order-refined
+    matrix of a mass + diffusion form, assembled on the device as CSR -- what LORSolver hands to an
+    algebraic multigrid.  The constructor forms the LOR vertex coordinates (FormLORVertexCoordinates)."""
+
+    def __init__(self, device, fes):
+        if fes.dim != 3 or fes.vdim != 1:
+            raise ValueError("BatchedLORAssembly: scalar H1 spaces in 3D only")
+        self.dev, self.fes = device, fes
+        p, ne = fes.p, fes.ne
+        nodes, nd = fes.mesh.nodes_e(fes.elem_vertices)
+        gp, _ = gauss_lobatto(p + 1)
+        Bn, _ = h1_dof_to_quad(nd - 1, gp)  # (q, d) column-major: B[q + nq*d]
+        Bn = np.ascontiguousarray(_f64(Bn).reshape(nd, p + 1).T)  # (p+1, nd) row-major
+        nodes_d = device.to_device(_f64(nodes))
+        self.x_vert = device.empty(3 * (p + 1) ** 3 * ne)
+        call("b2f_lor_vertex_coordinates", device.ctx, 3, p, nd, ne, _np_ptr(Bn), _dp(nodes_d), _dp(self.x_vert))
+        del nodes_d
+
+    def GetLORVertexCoordinates(self):
+        return self.x_vert
+
+    def Assemble(self, a, ess_dofs=None, mass_coeff=None, diff_coeff=None, keep_sparse_ij=False):
+        """Assemble(a, ess_dofs, A): `a` is a BilinearForm whose MassIntegrator / DiffusionIntegrator
+        constants are used, or None with mass_coeff / diff_coeff given: a number, or the coefficient at
+        the (p+1)^3 Gauss-Lobatto points of every element, (NE, (p+1)^3) -- BatchedLORKernel's c1 / c2."""
+        dev, fes = self.dev, self.fes
+        cm, cd = 0.0, 0.0
+        if a is not None:
+            for it in a.integrators:
+                if isinstance(it, MassIntegrator):
+                    cm = it.coeff
+                elif isinstance(it, DiffusionIntegrator):
+                    cd = it.coeff
+                else:
+                    raise ValueError("BatchedLORAssembly: MassIntegrator / DiffusionIntegrator only")
+        cm = cm if mass_coeff is None else mass_coeff
+        cd = cd if diff_coeff is None else diff_coeff
+        cm_d = dev.to_device(_f64(np.atleast_1d(cm)).ravel())
+        cd_d = dev.to_device(_f64(np.atleast_1d(cd)).ravel())
+        ess = _i32(ess_dofs if ess_dofs is not None else [])
+        ess_d = dev.to_device(ess) if ess.size else None
+        R = fes.GetElementRestriction(dev)
+        h = vp()
+        call("b2f_lor_assemble_h1", dev.ctx, R.h, 3, fes.p, _dp(self.x_vert), _dp(cm_d), cm_d.numel(), _dp(cd_d),
+             cd_d.numel(), _dp(ess_d), ess.size, int(bool(keep_sparse_ij)), C.byref(h))
+        return LORSparseMatrix(dev, h)
+
+
 class CGSolver:
     """linalg/solvers.cpp:869-1050 (iterative_mode = false)."""
 

@@ -102,6 +102,17 @@ CASES = {
     "lf_2d_p3_n4_curved": dict(dim=2, n=4, p=3, kind="mass", lf=1, nattr=2, curved=1),
     "lf_3d_p3_n2_vec_byvdim": dict(dim=3, n=2, p=3, kind="mass", lf=1, nattr=2, vdim=3, byvdim=1),
     "lf_3d_p2_n2_vec_bynodes": dict(dim=3, n=2, p=2, kind="mass", lf=1, nattr=2, vdim=3, byvdim=0, curved=1),
+    # LOR batched assembly, H1 (fem/lor/lor_batched.cpp, lor_h1_impl.hpp): macro-element stencil array,
+    # CSR without / with essential dofs eliminated, and the legacy refined-mesh assembly of the same form
+    "lor_3d_p1_n3": dict(dim=3, n=3, p=1, lor=1, lorkind="diffusion"),
+    "lor_3d_p2_n3": dict(dim=3, n=3, p=2, lor=1, lorkind="both", varcoef=1),
+    "lor_3d_p3_n2_curved": dict(dim=3, n=2, p=3, lor=1, lorkind="both", varcoef=1, curved=1),
+    "lor_3d_p4_n2": dict(dim=3, n=2, p=4, lor=1, lorkind="diffusion"),
+    "lor_3d_p4_n2_mass": dict(dim=3, n=2, p=4, lor=1, lorkind="mass", mass_const=2.5),
+    "lor_3d_p6_n2_curved": dict(dim=3, n=2, p=6, lor=1, lorkind="both", curved=1, mass_const=0.5, diff_const=3.0),
+    "lor_3d_p8_n1": dict(dim=3, n=1, ny=2, nz=1, p=8, lor=1, lorkind="diffusion", varcoef=1),
+    "lor_mesh_fichera_q2_p3": dict(mesh=DATA + "fichera-q2.mesh", refine=0, p=3, lor=1, lorkind="both", varcoef=1),
+    "lor_mesh_toroid_hex_p2": dict(mesh=DATA + "toroid-hex.mesh", refine=0, p=2, lor=1, lorkind="diffusion"),
 }
 
 

@@ -38,6 +38,7 @@
 #define protected public
 #include "mfem.hpp"
 #include "fem/integ/bilininteg_diffusion_kernels.hpp"
+#include "fem/lor/lor_batched.hpp"
 #undef private
 #undef protected
 
@@ -930,6 +931,107 @@ static int do_dump_cheb(const Args &A, const char *out)
    return 0;
 }
 
+// ---- LOR (low-order-refined) batched assembly, H1: fem/lor/lor_batched.cpp, lor_h1_impl.hpp ------
+// The macro-element "sparse IJ" array, its CSR form without and with essential dofs eliminated, and
+// the legacy path (full assembly on the refined mesh) of the same form as an independent check.
+static double lor_mass_coeff(const Vector &x) { return 1.0 + x(0) + 2.0 * x(1) * x(x.Size() - 1); }
+static double lor_diff_coeff(const Vector &x) { return 2.0 + std::sin(3.0 * x(0)) * std::cos(2.0 * x(1)); }
+
+static int do_dump_lor(const Args &A, const char *out)
+{
+   Problem P(A);
+   Dump D(out);
+   FiniteElementSpace &fes = *P.fes;
+   const int dim = P.dim, NE = fes.GetNE(), ndofs = fes.GetNDofs();
+   const string kind = A.gets("lorkind", "both"); // mass | diffusion | both
+   const bool var = A.geti("varcoef", 0) != 0;
+   FunctionCoefficient mc(lor_mass_coeff), dc(lor_diff_coeff);
+   ConstantCoefficient mconst(A.getd("mass_const", 1.0)), dconst(A.getd("diff_const", 1.0));
+   BilinearForm a(&fes);
+   const bool has_m = kind != "diffusion", has_d = kind != "mass";
+   if (has_m) { a.AddDomainIntegrator(var ? new MassIntegrator(mc) : new MassIntegrator(mconst)); }
+   if (has_d) { a.AddDomainIntegrator(var ? new DiffusionIntegrator(dc) : new DiffusionIntegrator(dconst)); }
+   D.scalar("dim", dim); D.scalar("n", P.n); D.scalar("p", P.p); D.scalar("NE", NE); D.scalar("ndofs", ndofs);
+   D.scalar("has_mass", (int)has_m); D.scalar("has_diffusion", (int)has_d); D.scalar("varcoef", (int)var);
+   auto R = dynamic_cast<const ElementRestriction *>(
+               fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC));
+   D.ints("gather_map", R->GatherMap());
+   D.ints("offsets", R->Offsets());
+   D.ints("indices", R->Indices());
+   {
+      // the nodes as an E-vector (input of FormLORVertexCoordinates)
+      P.mesh.EnsureNodes();
+      const GridFunction *nodes = P.mesh.GetNodes();
+      const Operator *nr = nodes->FESpace()->GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC);
+      Vector ne_(nr->Height());
+      nr->Mult(*nodes, ne_);
+      D.dbls("nodes_e", ne_);
+      D.scalar("node_order", nodes->FESpace()->GetMaxElementOrder());
+   }
+   // the projected coefficients, as BatchedLORKernel's constructor forms them (lor_batched.hpp:180-216)
+   {
+      IntegrationRule ir = GetCollocatedIntRule(fes);
+      QuadratureSpace qs(*fes.GetMesh(), ir);
+      CoefficientVector c1(qs, CoefficientStorage::COMPRESSED), c2(qs, CoefficientStorage::COMPRESSED);
+      if (!has_m) { c1.SetConstant(0.0); }
+      else if (var) { c1.Project(mc); }
+      else { c1.Project(mconst); }
+      if (!has_d) { c2.SetConstant(0.0); }
+      else if (var) { c2.Project(dc); }
+      else { c2.Project(dconst); }
+      D.dbls("c_mass", c1); D.dbls("c_diff", c2);
+   }
+   Array<int> ess;
+   {
+      Array<int> ess_bdr(P.mesh.bdr_attributes.Max()); ess_bdr = 1;
+      fes.GetEssentialTrueDofs(ess_bdr, ess);
+   }
+   D.ints("ess_tdof_list", ess);
+   BatchedLORAssembly batched(fes);
+   D.dbls("X_vert", batched.X_vert);
+   {
+      OperatorHandle A0;
+      batched.AssembleWithoutBC(a, A0);
+      D.dbls("sparse_ij", batched.sparse_ij);
+      D.ints("sparse_mapping", batched.sparse_mapping);
+      SparseMatrix *M = A0.As<SparseMatrix>();
+      D.ints("I", M->HostReadI(), ndofs + 1);
+      D.ints("J", M->HostReadJ(), M->HostReadI()[ndofs]);
+      D.dbls("data", M->HostReadData(), M->HostReadI()[ndofs]);
+   }
+   {
+      OperatorHandle A1;
+      batched.Assemble(a, ess, A1);
+      SparseMatrix *M = A1.As<SparseMatrix>();
+      D.ints("I_bc", M->HostReadI(), ndofs + 1);
+      D.ints("J_bc", M->HostReadJ(), M->HostReadI()[ndofs]);
+      D.dbls("data_bc", M->HostReadData(), M->HostReadI()[ndofs]);
+      Vector x(ndofs), y(ndofs);
+      x.Randomize(1);
+      M->Mult(x, y);
+      D.dbls("x", x); D.dbls("y_bc", y);
+   }
+   double legacy_diff = -1.0;
+   {
+      // legacy path: refined mesh, lowest-order space, full assembly (fem/lor/lor.cpp, LegacyAssembleSystem)
+      LORDiscretization lor(fes);
+      lor.LegacyAssembleSystem(a, ess);
+      SparseMatrix L = lor.GetAssembledMatrix();
+      L.SortColumnIndices();
+      D.ints("I_legacy", L.HostReadI(), ndofs + 1);
+      D.ints("J_legacy", L.HostReadJ(), L.HostReadI()[ndofs]);
+      D.dbls("data_legacy", L.HostReadData(), L.HostReadI()[ndofs]);
+      lor.AssembleSystem(a, ess);
+      SparseMatrix &B = lor.GetAssembledMatrix();
+      std::unique_ptr<SparseMatrix> diff(Add(1.0, L, -1.0, B));
+      legacy_diff = diff->MaxNorm();
+   }
+   D.scalar("legacy_minus_batched_maxnorm", legacy_diff);
+   std::printf("dump %s: LOR dim=%d NE=%d p=%d ndofs=%d kind=%s varcoef=%d legacy-batched=%.3e\n", out, dim, NE, P.p,
+               ndofs, kind.c_str(), (int)var, legacy_diff);
+   return 0;
+}
+
 // Timing of the reference CPU path.  Prints one JSON object.
 //   mode=mult : y = A x (BilinearForm::Mult, PA) repeated `reps` times
 //   mode=kernel : AddMultPA on E-vectors (bench_ceed.cpp BK style), `reps` times
@@ -1054,6 +1156,7 @@ int main(int argc, char **argv)
       Args A(argc, argv, 3);
       if (A.geti("nonsym", 0)) { return do_dump_nonsym(A, argv[2]); }
       if (A.geti("cheb", 0)) { return do_dump_cheb(A, argv[2]); }
+      if (A.geti("lor", 0)) { return do_dump_lor(A, argv[2]); }
       if (A.geti("markers", 0)) { return do_dump_markers(A, argv[2]); }
       if (A.geti("lf", 0)) { return do_dump_lf(A, argv[2]); }
       if (A.geti("lean", 0)) { return do_dump_mesh(A, argv[2]); }
