@@ -17,7 +17,7 @@ def pytest_configure(config):
 def golden_names():
     """scalar fixtures (every table of the path); vector ones are in vector_golden_names()"""
     return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
-                  if not n.startswith(("vec_", "nonsym_", "cheb_", "mark_", "lf_", "mesh_")))
+                  if not n.startswith(("vec_", "nonsym_", "cheb_", "mark_", "lf_", "mesh_", "lor_")))
 
 
 def nonsym_golden_names():
