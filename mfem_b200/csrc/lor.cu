@@ -7,10 +7,10 @@
 //   CSR matrix MFEM hands to an algebraic multigrid (LORSolver<HypreBoomerAMG>, fem/lor/lor.hpp).
 //
 // How it differs from the reference's device path:
-//   * the macro element's 27-point stencil array lives in shared memory while its p^3 sub-hexahedra
-//     are added, in 8 parity colours (sub-elements of one colour share no vertex), so there are no
+//   * the 8x8 matrices of a macro element's p^3 sub-hexahedra stay in shared memory and every dof
+//     GATHERS its 27 stencil values from the sub-hexahedra around it in a fixed order, so there are no
 //     atomics and the result is reproducible bit for bit; the reference adds with global atomics;
-//   * the CSR is filled by ROWS (one thread per dof walks the elements holding it, in element order),
+//   * the CSR is filled by ROWS (one warp per dof walks the elements holding it, in element order),
 //     not by (element, local dof) with an atomic cursor per row: the column order inside a row is then
 //     exactly the order of the reference's serial host loop, so I and J match the reference's CPU result
 //     bit for bit (its own device path returns the columns of a row in a run-dependent order);
@@ -19,6 +19,7 @@
 #include "common.cuh"
 
 #include <cub/device/device_scan.cuh>
+#include <cstdlib>
 #include <new>
 
 struct b2f_lor
@@ -138,67 +139,92 @@ __device__ __forceinline__ void lor_local_matrix(const double (&P)[3][2][2][2], 
          }
 }
 
-// CTA = `neb` macro elements; Vs[(el * nv + i) * 27 + j] in shared memory
-__global__ void __launch_bounds__(128)
+// CTA = `neb` consecutive macro elements.  Phase 1: one thread per sub-hexahedron computes its 8x8
+// matrix and leaves the lower triangle (36 values, odd pitch) in shared memory.  Phase 2: one thread per
+// dof of the macro elements GATHERS its 27 stencil values from the (up to 8) sub-hexahedra around it, in a
+// fixed order -- no atomics, no colouring, reproducible bit for bit -- and the warp writes the 32 finished
+// rows (contiguous in V) through a private staging slab, fully coalesced.
+constexpr int LOR_NT = 128, LOR_MP = 37; // threads per CTA; pitch of a sub-element's 36-entry triangle
+__device__ __forceinline__ constexpr int lor_tri(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
+
+__global__ void __launch_bounds__(LOR_NT)
 lor_h1_assemble_3d_kernel(int p, int neb, int64_t ne, const double *__restrict__ xv,
                           const double *__restrict__ cm, int cm_const, const double *__restrict__ cd,
                           int cd_const, double *__restrict__ V)
 {
-   extern __shared__ double Vs[];
-   const int n1 = p + 1, nv = n1 * n1 * n1;
+   extern __shared__ double lsm[];
+   const int n1 = p + 1, nv = n1 * n1 * n1, ns = p * p * p;
    const int64_t e0 = (int64_t)blockIdx.x * neb;
    const int nev = (int)((ne - e0) < neb ? (ne - e0) : neb);
-   for (int i = threadIdx.x; i < nev * nv * 27; i += blockDim.x) { Vs[i] = 0.0; }
-   __syncthreads();
-   for (int colour = 0; colour < 8; colour++)
+   double *Ms = lsm;                                                       // [nev * ns][LOR_MP]
+   double *stage = lsm + (size_t)neb * ns * LOR_MP + (threadIdx.x >> 5) * (32 * 27); // per warp [32][27]
+   for (int s = threadIdx.x; s < nev * ns; s += LOR_NT)
    {
-      const int cx = colour & 1, cy = (colour >> 1) & 1, cz = colour >> 2;
-      const int mx = (p - cx + 1) / 2, my = (p - cy + 1) / 2, mz = (p - cz + 1) / 2; // sub-elements per direction
-      const int per_el = mx * my * mz;
-      for (int s = threadIdx.x; s < nev * per_el; s += blockDim.x)
+      const int el = s / ns;
+      int r = s - el * ns;
+      const int kx = r % p, ky = (r / p) % p, kz = r / (p * p);
+      const int64_t e = e0 + el;
+      double P[3][2][2][2], mq[2][2][2], dq[2][2][2];
+#pragma unroll
+      for (int dz = 0; dz < 2; dz++)
+#pragma unroll
+         for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 2; dx++)
+            {
+               const int64_t v = (kx + dx) + n1 * ((ky + dy) + n1 * (kz + dz)) + (int64_t)nv * e;
+               P[0][dx][dy][dz] = xv[3 * v];
+               P[1][dx][dy][dz] = xv[3 * v + 1];
+               P[2][dx][dy][dz] = xv[3 * v + 2];
+               mq[dx][dy][dz] = cm_const ? cm[0] : cm[v];
+               dq[dx][dy][dz] = cd_const ? cd[0] : cd[v];
+            }
+      double M[8][8];
+      lor_local_matrix(P, mq, dq, M);
+      double *m = Ms + (size_t)s * LOR_MP;
+#pragma unroll
+      for (int ii = 0; ii < 8; ii++)
+#pragma unroll
+         for (int jj = 0; jj <= ii; jj++) { m[lor_tri(ii, jj)] = M[ii][jj]; }
+   }
+   __syncthreads();
+   const int total = nev * nv;
+   const int lane = threadIdx.x & 31;
+   double *Vg = V + e0 * (int64_t)nv * 27;
+   for (int d0 = (threadIdx.x >> 5) * 32; d0 < total; d0 += LOR_NT)
+   {
+      const int d = d0 + lane;
+      double acc[27];
+#pragma unroll
+      for (int j = 0; j < 27; j++) { acc[j] = 0.0; }
+      if (d < total)
       {
-         const int el = s / per_el;
-         int r = s - el * per_el;
-         const int kx = 2 * (r % mx) + cx;
-         r /= mx;
-         const int ky = 2 * (r % my) + cy, kz = 2 * (r / my) + cz;
-         const int64_t e = e0 + el;
-         double P[3][2][2][2], mq[2][2][2], dq[2][2][2];
+         const int el = d / nv, i = d - el * nv;
+         const int ix = i % n1, iy = (i / n1) % n1, iz = i / (n1 * n1);
+         // the sub-hexahedron that has this dof as its corner (cx, cy, cz) starts at (ix-cx, iy-cy, iz-cz)
 #pragma unroll
-         for (int dz = 0; dz < 2; dz++)
-#pragma unroll
-            for (int dy = 0; dy < 2; dy++)
-#pragma unroll
-               for (int dx = 0; dx < 2; dx++)
-               {
-                  const int64_t v = (kx + dx) + n1 * ((ky + dy) + n1 * (kz + dz)) + (int64_t)nv * e;
-                  P[0][dx][dy][dz] = xv[3 * v];
-                  P[1][dx][dy][dz] = xv[3 * v + 1];
-                  P[2][dx][dy][dz] = xv[3 * v + 2];
-                  mq[dx][dy][dz] = cm_const ? cm[0] : cm[v];
-                  dq[dx][dy][dz] = cd_const ? cd[0] : cd[v];
-               }
-         double M[8][8];
-         lor_local_matrix(P, mq, dq, M);
-         double *Ve = Vs + (size_t)el * nv * 27;
-#pragma unroll
-         for (int ii = 0; ii < 8; ii++)
+         for (int c = 0; c < 8; c++)
          {
-            const int ix = ii & 1, iy = (ii >> 1) & 1, iz = ii >> 2;
-            double *row = Ve + ((ix + kx) + n1 * ((iy + ky) + n1 * (iz + kz))) * 27;
+            const int cx = c & 1, cy = (c >> 1) & 1, cz = c >> 2;
+            const int kx = ix - cx, ky = iy - cy, kz = iz - cz;
+            if (kx < 0 || kx >= p || ky < 0 || ky >= p || kz < 0 || kz >= p) { continue; }
+            const double *m = Ms + (size_t)(el * ns + kx + p * (ky + p * kz)) * LOR_MP;
 #pragma unroll
             for (int jj = 0; jj < 8; jj++)
             {
                const int jx = jj & 1, jy = (jj >> 1) & 1, jz = jj >> 2;
-               const int off = (jx - ix + 1) + 3 * (jy - iy + 1) + 9 * (jz - iz + 1);
-               row[off] += (jj <= ii) ? M[ii][jj] : M[jj][ii];
+               acc[(jx - cx + 1) + 3 * (jy - cy + 1) + 9 * (jz - cz + 1)] += m[lor_tri(c, jj)];
             }
          }
       }
-      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 27; j++) { stage[lane * 27 + j] = acc[j]; }
+      __syncwarp();
+      const int rows = (total - d0) < 32 ? (total - d0) : 32;
+      double *out = Vg + (int64_t)d0 * 27;
+      for (int t = lane; t < rows * 27; t += 32) { out[t] = stage[t]; }
+      __syncwarp();
    }
-   double *Vg = V + e0 * (int64_t)nv * 27;
-   for (int i = threadIdx.x; i < nev * nv * 27; i += blockDim.x) { Vg[i] = Vs[i]; }
 }
 
 // ---- CSR ------------------------------------------------------------------------------------------
@@ -206,72 +232,214 @@ __device__ __forceinline__ int lor_decode(int s) { return s >= 0 ? s : -1 - s; }
 
 // Walk row `ii` as the reference's serial loop meets it: the elements holding the dof in ascending
 // order, the 27 stencil entries of each; an entry between two shared dofs is emitted by the lowest
-// element holding both, with the contributions of all of them.  FILL = false only counts.
+// element holding both, with the contributions of all of them (FillI / FillJAndData,
+// lor_batched.cpp:143-369).  One WARP per row, lane = stencil entry:
+//   * per incident element a, the 27 neighbour dofs nbr[a][.] and the 27 values val[a][.] of the row are
+//     loaded once (coalesced) into the warp's slab of shared memory;
+//   * element k emits column jj = nbr[k][lane] iff no earlier (lower) element of the row also holds jj,
+//     with the sum of val[a][l] over the later elements a and slots l where nbr[a][l] == jj -- the same
+//     pairs, in the same order, that the reference finds by intersecting the two dofs' element lists,
+//     without those lists, without divisions, with broadcast reads of shared memory only;
+//   * the emitted entries are compacted with a ballot (which keeps the (element, stencil entry) order)
+//     and written as one contiguous run.
+// Rows held by more than `maxe` elements (unstructured meshes can have any vertex valence) take the
+// list-intersecting path.  FILL = false only counts.
+constexpr int LOR_MAXE = 16;
+
 template <bool FILL>
-__global__ void lor_csr_rows_kernel(int p, int ndofs, const int *__restrict__ gmap, const int *__restrict__ K,
-                                    const int *__restrict__ ind, const double *__restrict__ V,
-                                    const int64_t *__restrict__ I64, int *__restrict__ count, int *__restrict__ J,
-                                    double *__restrict__ A)
+__device__ __noinline__ int lor_csr_row_by_lists(int p, int ii, int lane, const int *__restrict__ gmap,
+                                                  const int *__restrict__ K, const int *__restrict__ ind,
+                                                  const double *__restrict__ V, int64_t base, int *__restrict__ J,
+                                                  double *__restrict__ A)
 {
-   const int ii = blockIdx.x * blockDim.x + threadIdx.x;
-   if (ii >= ndofs) { return; }
+   const unsigned lt = (1u << lane) - 1u;
    const int n1 = p + 1, nv = n1 * n1 * n1;
    const int i_off = K[ii], i_ne = K[ii + 1] - i_off;
+   const int ox = lane % 3 - 1, oy = (lane / 3) % 3 - 1, oz = lane / 9 - 1;
    int n = 0;
-   const int64_t base = FILL ? I64[ii] : 0;
    for (int k = 0; k < i_ne; k++)
    {
       const int iE = lor_decode(ind[i_off + k]);
       const int e = iE / nv, i_el = iE - e * nv;
       const int ix = i_el % n1, iy = (i_el / n1) % n1, iz = i_el / (n1 * n1);
-      for (int j = 0; j < 27; j++)
+      const int jx = ix + ox, jy = iy + oy, jz = iz + oz;
+      bool emit = lane < 27 && jx >= 0 && jx <= p && jy >= 0 && jy <= p && jz >= 0 && jz <= p;
+      int jj = -1;
+      double val = 0.0;
+      if (emit)
       {
-         const int jx = ix + j % 3 - 1, jy = iy + (j / 3) % 3 - 1, jz = iz + j / 9 - 1;
-         if (jx < 0 || jx > p || jy < 0 || jy > p || jz < 0 || jz > p) { continue; }
-         const int j_el = jx + n1 * (jy + n1 * jz);
-         const int jj = lor_decode(gmap[(int64_t)e * nv + j_el]);
-         const int j_off = K[jj], j_ne = K[jj + 1] - j_off;
+         jj = lor_decode(gmap[(int64_t)e * nv + jx + n1 * (jy + n1 * jz)]);
+         int j_off = 0, j_ne = 1;
+         if (i_ne > 1) { j_off = K[jj]; j_ne = K[jj + 1] - j_off; }
          if (i_ne == 1 || j_ne == 1)
          {
-            if (FILL) { J[base + n] = jj; A[base + n] = V[((int64_t)e * nv + i_el) * 27 + j]; }
-            n++;
-            continue;
+            if (FILL) { val = V[((int64_t)e * nv + i_el) * 27 + lane]; }
          }
-         // both lists ascend with the element number: the first common element is the minimum
-         int min_e = -1;
-         for (int a = 0; a < i_ne && min_e < 0; a++)
+         else
          {
-            const int ea = lor_decode(ind[i_off + a]) / nv;
-            for (int b = 0; b < j_ne; b++)
+            // both lists ascend with the element number: the first common element is the minimum
+            int min_e = -1;
+            for (int a = 0; a < i_ne && min_e < 0; a++)
             {
-               if (lor_decode(ind[j_off + b]) / nv == ea) { min_e = ea; break; }
-            }
-         }
-         if (e != min_e) { continue; }
-         if (FILL)
-         {
-            double val = 0.0;
-            for (int a = 0; a < i_ne; a++)
-            {
-               const int iE2 = lor_decode(ind[i_off + a]);
-               const int e2 = iE2 / nv, i2 = iE2 - e2 * nv;
+               const int ea = lor_decode(ind[i_off + a]) / nv;
                for (int b = 0; b < j_ne; b++)
                {
-                  const int jE2 = lor_decode(ind[j_off + b]);
-                  if (jE2 / nv != e2) { continue; }
-                  const int j2 = jE2 - e2 * nv;
-                  const int dx = j2 % n1 - i2 % n1, dy = (j2 / n1) % n1 - (i2 / n1) % n1,
-                            dz = j2 / (n1 * n1) - i2 / (n1 * n1);
-                  val += V[((int64_t)e2 * nv + i2) * 27 + (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)];
+                  if (lor_decode(ind[j_off + b]) / nv == ea) { min_e = ea; break; }
                }
             }
-            J[base + n] = jj;
-            A[base + n] = val;
+            emit = e == min_e;
+            if (FILL && emit)
+            {
+               for (int a = 0; a < i_ne; a++)
+               {
+                  const int iE2 = lor_decode(ind[i_off + a]);
+                  const int e2 = iE2 / nv, i2 = iE2 - e2 * nv;
+                  for (int b = 0; b < j_ne; b++)
+                  {
+                     const int jE2 = lor_decode(ind[j_off + b]);
+                     if (jE2 / nv != e2) { continue; }
+                     const int j2 = jE2 - e2 * nv;
+                     const int dx = j2 % n1 - i2 % n1, dy = (j2 / n1) % n1 - (i2 / n1) % n1,
+                               dz = j2 / (n1 * n1) - i2 / (n1 * n1);
+                     val += V[((int64_t)e2 * nv + i2) * 27 + (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)];
+                  }
+               }
+            }
          }
-         n++;
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, emit);
+      if (FILL && emit)
+      {
+         const int64_t pos = base + n + __popc(mask & lt);
+         J[pos] = jj;
+         A[pos] = val;
+      }
+      n += __popc(mask);
+   }
+   return n;
+}
+
+// PT = p (compile-time index arithmetic) or 0 (run-time p)
+template <int PT, bool FILL>
+__global__ void __launch_bounds__(128)
+lor_csr_rows_kernel(int p_rt, int ndofs, int maxe, const int *__restrict__ gmap, const int *__restrict__ K,
+                    const int *__restrict__ ind, const double *__restrict__ V, const int64_t *__restrict__ I64,
+                    int *__restrict__ count, int *__restrict__ J, double *__restrict__ A)
+{
+   __shared__ __align__(16) int nbr_s[4][LOR_MAXE][28];
+   __shared__ double val_s[FILL ? 4 : 1][FILL ? LOR_MAXE : 1][27];
+   const int ii = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+   if (ii >= ndofs) { return; }
+   const int p = PT ? PT : p_rt;
+   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+   const int i_off = K[ii], i_ne = K[ii + 1] - i_off;
+   const int64_t base = FILL ? I64[ii] : 0;
+   if (i_ne > maxe)
+   {
+      const int n = lor_csr_row_by_lists<FILL>(p, ii, lane, gmap, K, ind, V, base, J, A);
+      if (!FILL && lane == 0) { count[ii] = n; }
+      return;
+   }
+   const unsigned lt = (1u << lane) - 1u;
+   const int n1 = p + 1, nv = n1 * n1 * n1;
+   const int ox = lane % 3 - 1, oy = (lane / 3) % 3 - 1, oz = lane / 9 - 1; // lane = stencil entry (< 27)
+   int (*nbr)[28] = nbr_s[w];
+   if (i_ne == 1)
+   {
+      // a dof of one element only (its interior): the row is that element's stencil, as it stands
+      const int iE = lor_decode(ind[i_off]);
+      const int e = iE / nv, i_el = iE - e * nv;
+      const int jx = i_el % n1 + ox, jy = (i_el / n1) % n1 + oy, jz = i_el / (n1 * n1) + oz;
+      const bool emit = lane < 27 && jx >= 0 && jx <= p && jy >= 0 && jy <= p && jz >= 0 && jz <= p;
+      const unsigned mask = __ballot_sync(0xffffffffu, emit);
+      if (FILL && emit)
+      {
+         const int64_t pos = base + __popc(mask & lt);
+         J[pos] = lor_decode(gmap[(int64_t)e * nv + jx + n1 * (jy + n1 * jz)]);
+         A[pos] = V[(int64_t)iE * 27 + lane];
+      }
+      if (!FILL && lane == 0) { count[ii] = __popc(mask); }
+      return;
+   }
+   for (int a = 0; a < i_ne; a++)
+   {
+      const int iE = lor_decode(ind[i_off + a]);
+      const int e = iE / nv, i_el = iE - e * nv;
+      const int jx = i_el % n1 + ox, jy = (i_el / n1) % n1 + oy, jz = i_el / (n1 * n1) + oz;
+      if (lane < 28)
+      {
+         const bool in = lane < 27 && jx >= 0 && jx <= p && jy >= 0 && jy <= p && jz >= 0 && jz <= p;
+         nbr[a][lane] = in ? lor_decode(gmap[(int64_t)e * nv + jx + n1 * (jy + n1 * jz)]) : -1;
+         if (FILL && lane < 27) { val_s[w][a][lane] = V[(int64_t)iE * 27 + lane]; }
       }
    }
-   if (!FILL) { count[ii] = n; }
+   __syncwarp();
+   int n = 0;
+   for (int k = 0; k < i_ne; k++)
+   {
+      const int jj = lane < 27 ? nbr[k][lane] : -1;
+      bool emit = jj >= 0;
+      for (int a = 0; a < k; a++) // a lower element that also holds jj has emitted the entry
+      {
+         const int4 *row = reinterpret_cast<const int4 *>(nbr[a]);
+#pragma unroll
+         for (int l = 0; l < 7; l++)
+         {
+            const int4 v = row[l];
+            emit = emit && v.x != jj && v.y != jj && v.z != jj && v.w != jj;
+         }
+      }
+      double val = 0.0;
+      if (FILL)
+      {
+         val = val_s[w][k][lane < 27 ? lane : 0];
+         for (int a = k + 1; a < i_ne; a++)
+         {
+            // the dofs of an element are distinct: at most one slot of element a holds jj
+            const int4 *row = reinterpret_cast<const int4 *>(nbr[a]);
+            int m = -1;
+#pragma unroll
+            for (int l = 0; l < 7; l++)
+            {
+               const int4 v = row[l];
+               m = v.x == jj ? 4 * l : m;
+               m = v.y == jj ? 4 * l + 1 : m;
+               m = v.z == jj ? 4 * l + 2 : m;
+               m = v.w == jj ? 4 * l + 3 : m;
+            }
+            if (m >= 0 && jj >= 0) { val += val_s[w][a][m]; }
+         }
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, emit);
+      if (FILL && emit)
+      {
+         const int64_t pos = base + n + __popc(mask & lt);
+         J[pos] = jj;
+         A[pos] = val;
+      }
+      n += __popc(mask);
+   }
+   if (!FILL && lane == 0) { count[ii] = n; }
+}
+
+template <bool FILL>
+static void lor_launch_rows(cudaStream_t st, int p, int nd, int maxe, const b2f_restriction *r, const double *V,
+                            const int64_t *I64, int *count, int *J, double *A)
+{
+   const unsigned grid = (unsigned)cdiv(32 * (int64_t)nd, 128);
+#define LOR_ROWS(P)                                                                                             \
+   case P:                                                                                                      \
+      lor_csr_rows_kernel<P, FILL><<<grid, 128, 0, st>>>(p, nd, maxe, r->gather_map, r->offsets, r->indices, V, \
+                                                          I64, count, J, A);                                     \
+      break;
+   switch (p)
+   {
+      LOR_ROWS(1) LOR_ROWS(2) LOR_ROWS(3) LOR_ROWS(4) LOR_ROWS(5) LOR_ROWS(6) LOR_ROWS(7) LOR_ROWS(8)
+      default:
+         lor_csr_rows_kernel<0, FILL><<<grid, 128, 0, st>>>(p, nd, maxe, r->gather_map, r->offsets, r->indices, V, I64,
+                                                            count, J, A);
+   }
+#undef LOR_ROWS
 }
 
 __global__ void lor_offsets_to_int_kernel(int n, const int64_t *__restrict__ in, int *__restrict__ out)
@@ -379,19 +547,20 @@ static int lor_assemble_impl(b2f_ctx *ctx, const b2f_restriction *r, int p, cons
       return B2F_OK;
    }
    B2F_CUDA(cudaMalloc(&L->V, sizeof(double) * (size_t)ne * nv * 27));
-   // macro elements per CTA: about 128 sub-elements, at most 96 KB of stencil array
-   const size_t per_el = sizeof(double) * nv * 27;
-   int neb = 128 / (p * p * p);
+   // macro elements per CTA: about one sub-hexahedron per thread
+   int neb = LOR_NT / (p * p * p);
    if (neb < 1) { neb = 1; }
-   while (neb > 1 && neb * per_el > 96 * 1024) { neb--; }
-   const size_t smem = neb * per_el;
+   const size_t smem = sizeof(double) * ((size_t)neb * p * p * p * LOR_MP + (LOR_NT / 32) * 32 * 27);
    B2F_REQUIRE((int)smem <= ctx->max_smem_optin, "b2f_lor_assemble_h1: p = %d needs %zu bytes of shared memory", p, smem);
    B2F_CUDA(cudaFuncSetAttribute(lor_h1_assemble_3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-   lor_h1_assemble_3d_kernel<<<(unsigned)cdiv(ne, neb), 128, smem, ctx->stream>>>(p, neb, ne, x_vert, c_mass,
-                                                                                  n_mass == 1, c_diff, n_diff == 1,
-                                                                                  L->V);
+   lor_h1_assemble_3d_kernel<<<(unsigned)cdiv(ne, neb), LOR_NT, smem, ctx->stream>>>(p, neb, ne, x_vert, c_mass,
+                                                                                     n_mass == 1, c_diff, n_diff == 1,
+                                                                                     L->V);
    B2F_LAUNCH_CHECK(ctx);
-   // rows: count, scan, fill
+   // rows: count, scan, fill.  B2F_LOR_MAXE (testing): rows held by more elements than this take the
+   // list-intersecting path
+   int maxe = LOR_MAXE;
+   if (const char *me = getenv("B2F_LOR_MAXE")) { maxe = atoi(me) < LOR_MAXE ? atoi(me) : LOR_MAXE; }
    int *count = nullptr;
    int64_t *I64 = nullptr;
    void *tmp = nullptr;
@@ -409,8 +578,7 @@ static int lor_assemble_impl(b2f_ctx *ctx, const b2f_restriction *r, int p, cons
    LOR_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * ((size_t)nd + 1), ctx->stream));
    if (rc == B2F_OK)
    {
-      lor_csr_rows_kernel<false><<<(unsigned)cdiv(nd, 128), 128, 0, ctx->stream>>>(
-         p, nd, r->gather_map, r->offsets, r->indices, L->V, nullptr, count, nullptr, nullptr);
+      lor_launch_rows<false>(ctx->stream, p, nd, maxe, r, L->V, nullptr, count, nullptr, nullptr);
       ctx->launches++;
       LOR_CUDA(cudaGetLastError());
    }
@@ -433,8 +601,7 @@ static int lor_assemble_impl(b2f_ctx *ctx, const b2f_restriction *r, int p, cons
    if (rc == B2F_OK)
    {
       lor_offsets_to_int_kernel<<<(unsigned)cdiv(nd + 1, 256), 256, 0, ctx->stream>>>(nd + 1, I64, L->I);
-      lor_csr_rows_kernel<true><<<(unsigned)cdiv(nd, 128), 128, 0, ctx->stream>>>(
-         p, nd, r->gather_map, r->offsets, r->indices, L->V, I64, nullptr, L->J, L->A);
+      lor_launch_rows<true>(ctx->stream, p, nd, maxe, r, L->V, I64, nullptr, L->J, L->A);
       ctx->launches += 2;
       LOR_CUDA(cudaGetLastError());
    }

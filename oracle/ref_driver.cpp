@@ -1037,9 +1037,59 @@ static int do_dump_lor(const Args &A, const char *out)
 //   mode=kernel : AddMultPA on E-vectors (bench_ceed.cpp BK style), `reps` times
 //   mode=all  : kernel, mult and pcg on one problem set-up (mult_seconds / kernel_seconds / seconds)
 //   mode=pcg  : bench_ceed.cpp BP style: CG (optionally Jacobi), fixed `iters` iterations
+// LOR batched assembly of the reference (host or its own CUDA backend): vertex coordinates once, then
+// Assemble (stencil array, CSR, boundary elimination) `reps` times; best and mean seconds.
+static int do_bench_lor(const Args &A)
+{
+   const int reps = A.geti("reps", 3);
+   Problem P(A);
+   FiniteElementSpace &fes = *P.fes;
+   const int ndofs = fes.GetVSize();
+   const string kind = A.gets("lorkind", "diffusion");
+   ConstantCoefficient one(1.0);
+   BilinearForm a(&fes);
+   if (kind != "diffusion") { a.AddDomainIntegrator(new MassIntegrator(one)); }
+   if (kind != "mass") { a.AddDomainIntegrator(new DiffusionIntegrator(one)); }
+   Array<int> ess;
+   {
+      Array<int> ess_bdr(P.mesh.bdr_attributes.Max()); ess_bdr = 1;
+      fes.GetEssentialTrueDofs(ess_bdr, ess);
+   }
+   fes.GetElementRestriction(ElementDofOrdering::LEXICOGRAPHIC); // built outside the timed region
+   MFEM_DEVICE_SYNC;
+   double t0 = now();
+   BatchedLORAssembly batched(fes);
+   MFEM_DEVICE_SYNC;
+   const double t_vert = now() - t0;
+   OperatorHandle Ah;
+   double best = 1e300, sum = 0;
+   for (int r = 0; r < reps + 1; r++)
+   {
+      MFEM_DEVICE_SYNC;
+      double t1 = now();
+      batched.Assemble(a, ess, Ah);
+      MFEM_DEVICE_SYNC;
+      const double dt = now() - t1;
+      if (r == 0) { continue; } // warm-up (allocations)
+      best = std::min(best, dt); sum += dt;
+   }
+   SparseMatrix *M = Ah.As<SparseMatrix>();
+   const long long nnz = M->NumNonZeroElems();
+   Vector x(ndofs), y(ndofs);
+   x.UseDevice(true); y.UseDevice(true);
+   x.Randomize(1);
+   M->Mult(x, y);
+   std::printf("{\"mode\": \"lor\", \"ndofs\": %d, \"ne\": %d, \"p\": %d, \"nnz\": %lld, \"assemble_seconds\": %.6e, "
+               "\"assemble_seconds_mean\": %.6e, \"vertex_seconds\": %.6e, \"ynorm\": %.17g, \"device\": \"%s\"}\n",
+               ndofs, fes.GetNE(), P.p, nnz, best, sum / reps, t_vert, (double)y.Norml2(),
+               Device::IsEnabled() ? "cuda" : "cpu");
+   return 0;
+}
+
 static int do_bench(const Args &A)
 {
    const string mode = A.gets("mode", "pcg");
+   if (mode == "lor") { return do_bench_lor(A); }
    const int reps = A.geti("reps", 3), iters = A.geti("iters", 32);
    const int skip = std::min(A.geti("skip", 0), reps - 1); // pcg: leading solves left out of the average
    const int use_prec = A.geti("jacobi", 0);

@@ -67,6 +67,19 @@ def test_lor_assembly_from_reference_tables(dev, name):
     B.close(); R.close()
 
 
+@pytest.mark.parametrize("name", ["lor_3d_p2_n3", "lor_mesh_fichera_q2_p3", "lor_3d_p6_n2_curved"])
+def test_lor_rows_held_by_many_elements(dev, name, monkeypatch):
+    """Rows held by more elements than the shared-memory slabs cover take the list-intersecting path
+    (unstructured meshes have no bound on the vertex valence); B2F_LOR_MAXE=1 sends every shared row
+    down that path."""
+    monkeypatch.setenv("B2F_LOR_MAXE", "1")
+    g = load(name)
+    B, R = assemble_from_reference_tables(dev, g, g["ess_tdof_list"])
+    assert np.array_equal(B.GetI(), g["I_bc"]) and np.array_equal(B.GetJ(), g["J_bc"])
+    assert np.abs(B.GetData() - g["data_bc"]).max() < TOL * np.abs(g["data"]).max()
+    B.close(); R.close()
+
+
 @pytest.mark.parametrize("name", NAMES)
 def test_lor_vertex_coordinates(dev, name):
     import mfem_b200 as m
