@@ -41,6 +41,7 @@
 #include <vector>
 
 #include "mfem.hpp"
+#include "fem/lor/lor_batched.hpp"
 #include "../include/b200fem.h"
 
 namespace b200
@@ -910,6 +911,105 @@ inline void PCG(const mfem::Operator &A, mfem::Solver &B, const mfem::Vector &b,
                 << (pcg.GetConverged() ? "" : " (not converged)") << '\n';
    }
 }
+
+/// LOR matrix assembly for H1 spaces in 3D: drop-in for mfem::BatchedLORAssembly::Assemble
+/// (fem/lor/lor_batched.cpp:712-734; H1 kernel fem/lor/lor_h1_impl.hpp:184-455) -- what
+/// LORDiscretization / LORSolver<T> call to obtain the SparseMatrix they hand to T (e.g. an AMG).
+/// The vertex coordinates and the projected coefficients are formed by MFEM's own routines
+/// (FormLORVertexCoordinates, ProjectLORCoefficient), exactly as BatchedLOR_H1's constructor does;
+/// the stencil array, the CSR conversion and the boundary elimination run in the library.
+/// The matrix comes back with the rows and the columns inside each row in the order of MFEM's serial
+/// host loop, on the device in device mode (no host copy), on the host otherwise.
+class BatchedLORAssembly
+{
+   mfem::FiniteElementSpace &fes_ho;
+   mfem::Vector X_vert;
+public:
+   explicit BatchedLORAssembly(mfem::FiniteElementSpace &fes) : fes_ho(fes)
+   {
+      mfem::BatchedLORAssembly::FormLORVertexCoordinates(fes_ho, X_vert);
+   }
+   const mfem::Vector &GetLORVertexCoordinates() const { return X_vert; }
+
+   /// H1, 3D, tensor elements, MassIntegrator / DiffusionIntegrator with scalar coefficients only
+   static bool FormIsSupported(mfem::BilinearForm &a)
+   {
+      using namespace mfem;
+      const FiniteElementSpace &fes = *a.FESpace();
+      if (!dynamic_cast<const H1_FECollection *>(fes.FEColl()) || fes.GetMesh()->Dimension() != 3 ||
+          fes.GetMesh()->SpaceDimension() != 3 || fes.GetVDim() != 1 || !UsesTensorBasis(fes) ||
+          fes.GetMaxElementOrder() > 8 || fes.GetConformingProlongation())
+      {
+         return false;
+      }
+      if (a.GetBBFI()->Size() || a.GetFBFI()->Size() || a.GetBFBFI()->Size()) { return false; }
+      for (BilinearFormIntegrator *bfi : *a.GetDBFI())
+      {
+         auto d = dynamic_cast<mfem::DiffusionIntegrator *>(bfi);
+         if (d)
+         {
+            Coefficient *q; VectorCoefficient *vq; MatrixCoefficient *mq;
+            b200::DiffusionIntegrator::Coefficients(*d, q, vq, mq);
+            if (vq || mq) { return false; } // the reference projects the scalar coefficient only
+         }
+         else if (!dynamic_cast<mfem::MassIntegrator *>(bfi)) { return false; }
+      }
+      return true;
+   }
+
+   void Assemble(mfem::BilinearForm &a, const mfem::Array<int> &ess_dofs, mfem::OperatorHandle &A)
+   {
+      using namespace mfem;
+      MFEM_VERIFY(FormIsSupported(a), "b200::BatchedLORAssembly: H1 mass + diffusion forms in 3D only");
+      IntegrationRule ir = GetCollocatedIntRule(fes_ho);
+      QuadratureSpace qs(*fes_ho.GetMesh(), ir);
+      CoefficientVector c1(qs, CoefficientStorage::COMPRESSED), c2(qs, CoefficientStorage::COMPRESSED);
+      ProjectLORCoefficient<mfem::MassIntegrator>(a, c1);
+      ProjectLORCoefficient<mfem::DiffusionIntegrator>(a, c2);
+      b2f_ctx *ctx = Context::Get().get();
+      RestrictionHandle R(fes_ho);
+      Bridge bx, b1, b2;
+      const int n_ess = ess_dofs.Size();
+      const int *ess = nullptr;
+      int *d_ess = nullptr;
+      if (DeviceMode()) { ess = ess_dofs.Read(); }
+      else if (n_ess)
+      {
+         B200_CHECK(b2f_malloc(ctx, sizeof(int) * n_ess, (void **)&d_ess));
+         B200_CHECK(b2f_memcpy_h2d(ctx, d_ess, ess_dofs.HostRead(), sizeof(int) * n_ess));
+         ess = d_ess;
+      }
+      b2f_lor *L = nullptr;
+      B200_CHECK(b2f_lor_assemble_h1(ctx, R.r, 3, fes_ho.GetMaxElementOrder(), bx.Read(X_vert), b1.Read(c1), c1.Size(),
+                                     b2.Read(c2), c2.Size(), ess, n_ess, 0, &L));
+      if (d_ess) { b2f_free(ctx, d_ess); }
+      int n = 0;
+      int64_t nnz = 0;
+      const int *I = nullptr, *J = nullptr;
+      const double *V = nullptr;
+      B200_CHECK(b2f_lor_csr(L, &n, &nnz, &I, &J, &V));
+      SparseMatrix *M = A.Is<SparseMatrix>();
+      if (!M) { M = new SparseMatrix; A.Reset(M); }
+      M->OverrideSize(n, n);
+      EnsureCapacity(M->GetMemoryI(), n + 1);
+      EnsureCapacity(M->GetMemoryJ(), (int)nnz);
+      EnsureCapacity(M->GetMemoryData(), (int)nnz);
+      if (DeviceMode())
+      {
+         B200_CHECK(b2f_memcpy_d2d(ctx, M->WriteI(), I, sizeof(int) * (n + 1)));
+         B200_CHECK(b2f_memcpy_d2d(ctx, M->WriteJ(), J, sizeof(int) * nnz));
+         B200_CHECK(b2f_memcpy_d2d(ctx, M->WriteData(), V, sizeof(double) * nnz));
+      }
+      else
+      {
+         B200_CHECK(b2f_memcpy_d2h(ctx, M->HostWriteI(), I, sizeof(int) * (n + 1)));
+         B200_CHECK(b2f_memcpy_d2h(ctx, M->HostWriteJ(), J, sizeof(int) * nnz));
+         B200_CHECK(b2f_memcpy_d2h(ctx, M->HostWriteData(), V, sizeof(double) * nnz));
+      }
+      B200_CHECK(b2f_ctx_sync(ctx));
+      b2f_lor_destroy(L);
+   }
+};
 
 } // namespace b200
 #endif

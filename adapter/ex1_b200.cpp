@@ -142,6 +142,7 @@ int main(int argc, char *argv[])
    cg2.SetOperator(A_b2);
    cg2.UseJacobi(ess);
    Vector X2(N);
+   X2 = 0.0; // an IterativeSolver starts from x (iterative_mode is true by default, linalg/solvers.hpp:102)
    cg2.Mult(B2, X2);
    std::printf("  PCG iterations: MFEM %d, b200 %d\n", cg.GetNumIterations(), cg2.GetNumIterations());
    check("PCG iteration count |difference|", std::abs(cg.GetNumIterations() - cg2.GetNumIterations()), 1.0);
@@ -231,6 +232,38 @@ int main(int argc, char *argv[])
       }
    }
 
+   // LOR matrix (what LORSolver hands to an AMG): mfem::BatchedLORAssembly vs b200::BatchedLORAssembly
+   if (vdim == 1 && dim == 3 && order <= 8)
+   {
+      FunctionCoefficient mcf([](const Vector &xx) { return 1.0 + xx(0) + 2.0 * xx(1) * xx(2); });
+      FunctionCoefficient dcf([](const Vector &xx) { return 2.0 + sin(3.0 * xx(0)) * cos(2.0 * xx(1)); });
+      BilinearForm al(&fes);
+      al.AddDomainIntegrator(new MassIntegrator(mcf));
+      al.AddDomainIntegrator(new DiffusionIntegrator(dcf));
+      OperatorHandle Ar, Ab;
+      BatchedLORAssembly lr(fes);
+      lr.Assemble(al, ess, Ar);
+      check("LOR: the form is supported (0 = yes)", b200::BatchedLORAssembly::FormIsSupported(al) ? 0.0 : 1.0, 0.0);
+      b200::BatchedLORAssembly lb(fes);
+      lb.Assemble(al, ess, Ab);
+      SparseMatrix &Sr = *Ar.As<SparseMatrix>(), &Sb = *Ab.As<SparseMatrix>();
+      check("LOR: number of nonzeros |difference|", std::abs(Sr.NumNonZeroElems() - Sb.NumNonZeroElems()), 0.0);
+      Sr.Mult(x, y_ref);
+      Sb.Mult(x, y);
+      check("LOR: SparseMatrix::Mult of the assembled matrix", relerr(y, y_ref), 1e-12);
+      std::unique_ptr<SparseMatrix> diff(Add(1.0, Sr, -1.0, Sb));
+      check("LOR: max |A_mfem - A_b200| / max |A_mfem|", diff->MaxNorm() / Sr.MaxNorm(), 1e-12);
+      if (!b200::DeviceMode())
+      {
+         // on the host MFEM fills rows serially: the CSR arrays themselves must coincide
+         bool same = true;
+         const int *Ir = Sr.HostReadI(), *Ib = Sb.HostReadI(), *Jr = Sr.HostReadJ(), *Jb = Sb.HostReadJ();
+         for (int i = 0; i <= N && same; i++) { same = Ir[i] == Ib[i]; }
+         for (int k = 0; k < Sr.NumNonZeroElems() && same; k++) { same = Jr[k] == Jb[k]; }
+         check("LOR: I and J identical to MFEM's (0 = yes)", same ? 0.0 : 1.0, 0.0);
+      }
+   }
+
    // right-hand side with a spatially varying coefficient, fast (device) assembly
    if (vdim == 1)
    {
@@ -264,6 +297,7 @@ int main(int argc, char *argv[])
       cg3.SetOperator(A_b2);
       cg3.SetPreconditioner(S2);
       Vector X3(N);
+      X3 = 0.0;
       cg3.Mult(B2, X3);
       std::printf("  Chebyshev-PCG iterations: MFEM %d, b200 %d\n", cg.GetNumIterations(), cg3.GetNumIterations());
       check("Chebyshev-PCG iteration count |difference|", std::abs(cg.GetNumIterations() - cg3.GetNumIterations()), 1.0);
