@@ -379,22 +379,23 @@ int b2f_halo_mult_transpose(b2f_halo *h, const double *x_l, double *y_t);
 int b2f_halo_dot(b2f_halo *h, int64_t n, const double *x, const double *y, double *result_h);
 
 
-/* ---- LOR (low-order-refined) batched assembly, H1, 3D ------------------------------------ */
+/* ---- LOR (low-order-refined) batched assembly, H1, dim = 2 or 3 --------------------------- */
 /* BatchedLORAssembly::FormLORVertexCoordinates (fem/lor/lor_batched.cpp:75-112): the mesh nodes
- * (device E-vector (nd^3, 3, NE), nd = node_nd1d) evaluated at the (p+1)^3 Gauss-Lobatto points of
- * every element: x_vert (device) is (3, (p+1)^3, NE), byVDIM.  Bn_h (host) is the 1D nodal basis of
+ * (device E-vector (nd^dim, dim, NE), nd = node_nd1d) evaluated at the (p+1)^dim Gauss-Lobatto points
+ * of every element: x_vert (device) is (dim, (p+1)^dim, NE), byVDIM.  Bn_h (host) is the 1D nodal basis of
  * the mesh at those points, (p+1, nd) row-major. */
 int b2f_lor_vertex_coordinates(b2f_ctx *ctx, int dim, int p, int node_nd1d, int64_t ne, const double *Bn_h,
                                const double *nodes_e, double *x_vert);
 /* BatchedLORAssembly::Assemble for an H1 space with a MassIntegrator and / or DiffusionIntegrator
- * (fem/lor/lor_batched.cpp:712-734): BatchedLOR_H1::Assemble3D (fem/lor/lor_h1_impl.hpp:184-455),
+ * (fem/lor/lor_batched.cpp:712-734): BatchedLOR_H1::Assemble2D / Assemble3D (fem/lor/lor_h1_impl.hpp:
+ * 19-182 / 184-455),
  * FillI / FillJAndData (lor_batched.cpp:143-369), SparseMatrix::EliminateBC(ess, DIAG_KEEP)
  * (linalg/sparsemat.cpp:2375).  r is the space's lexicographic ElementRestriction; c_mass / c_diff
  * (device) are the projected coefficients c1 / c2 of BatchedLORKernel (lor_batched.hpp:180-216): one
- * value (n == 1; 0 when the integrator is absent) or ((p+1)^3, NE); ess (device, may be NULL when
+ * value (n == 1; 0 when the integrator is absent) or ((p+1)^dim, NE); ess (device, may be NULL when
  * n_ess == 0) lists the essential dofs.  Rows and the columns inside a row come in the order of the
  * reference's serial host loop.  keep_sparse_ij != 0 keeps the macro-element stencil array
- * (BatchedLORAssembly::sparse_ij, (27, (p+1)^3, NE)) for b2f_lor_sparse_ij. */
+ * (BatchedLORAssembly::sparse_ij, (3^dim, (p+1)^dim, NE)) for b2f_lor_sparse_ij. */
 int b2f_lor_assemble_h1(b2f_ctx *ctx, const b2f_restriction *r, int dim, int p, const double *x_vert,
                         const double *c_mass, int64_t n_mass, const double *c_diff, int64_t n_diff,
                         const int *ess, int n_ess, int keep_sparse_ij, b2f_lor **out);

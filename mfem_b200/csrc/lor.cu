@@ -1,8 +1,8 @@
-// mfem_b200/csrc/lor.cu -- low-order-refined (LOR) assembly of H1 diffusion + mass forms in 3D.
+// mfem_b200/csrc/lor.cu -- low-order-refined (LOR) assembly of H1 diffusion + mass forms in 2D and 3D.
 //
 // What it replaces: BatchedLORAssembly::Assemble for H1 spaces (fem/lor/lor_batched.cpp:712-734):
-//   FormLORVertexCoordinates (lor_batched.cpp:75-112), BatchedLOR_H1::Assemble3D
-//   (fem/lor/lor_h1_impl.hpp:184-455), FillI / FillJAndData (lor_batched.cpp:143-369) and
+//   FormLORVertexCoordinates (lor_batched.cpp:75-112), BatchedLOR_H1::Assemble2D / Assemble3D
+//   (fem/lor/lor_h1_impl.hpp:19-182 / 184-455), FillI / FillJAndData (lor_batched.cpp:143-369) and
 //   SparseMatrix::EliminateBC(ess, DIAG_KEEP) (linalg/sparsemat.cpp:2375-2416).  The result is the
 //   CSR matrix MFEM hands to an algebraic multigrid (LORSolver<HypreBoomerAMG>, fem/lor/lor.hpp).
 //
@@ -25,11 +25,11 @@
 struct b2f_lor
 {
    b2f_ctx *ctx = nullptr;
-   int p = 0, ndofs = 0;
+   int dim = 3, p = 0, ndofs = 0;
    int64_t ne = 0, nnz = 0;
    int *I = nullptr, *J = nullptr;
    double *A = nullptr;
-   double *V = nullptr; // (27, nd1d^3, NE) macro-element stencil array ("sparse_ij")
+   double *V = nullptr; // (3^dim, nd1d^dim, NE) macro-element stencil array ("sparse_ij")
 };
 
 namespace b2f
@@ -66,6 +66,32 @@ __global__ void lor_vertex_coordinates_kernel(int n1, int nd, int64_t ne, const 
    }
    double *o = xv + 3 * tid;
    o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+}
+
+// 2D: X_vert(c, i, e) = sum_j Bn(ix,jx) Bn(iy,jy) nodes(j, c, e)
+__global__ void lor_vertex_coordinates_2d_kernel(int n1, int nd, int64_t ne, const double *__restrict__ Bn,
+                                                 const double *__restrict__ nodes, double *__restrict__ xv)
+{
+   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const int nv = n1 * n1, nn = nd * nd;
+   if (tid >= ne * nv) { return; }
+   const int64_t e = tid / nv;
+   const int i = (int)(tid - e * nv);
+   const int ix = i % n1, iy = i / n1;
+   double s0 = 0.0, s1 = 0.0;
+   const double *ne_ = nodes + e * 2 * (int64_t)nn;
+   for (int jy = 0; jy < nd; jy++)
+   {
+      const double by = Bn[iy * nd + jy];
+      for (int jx = 0; jx < nd; jx++)
+      {
+         const double b = by * Bn[ix * nd + jx];
+         s0 += b * ne_[jx + nd * jy];
+         s1 += b * ne_[nn + jx + nd * jy];
+      }
+   }
+   xv[2 * tid] = s0;
+   xv[2 * tid + 1] = s1;
 }
 
 // ---- macro-element stencil array ----------------------------------------------------------------
@@ -227,6 +253,119 @@ lor_h1_assemble_3d_kernel(int p, int neb, int64_t ne, const double *__restrict__
    }
 }
 
+// 2D twin (BatchedLOR_H1::Assemble2D, lor_h1_impl.hpp:19-182): sub-quadrilaterals, bilinear map, vertex
+// quadrature (weight 1/4), 4x4 matrices (lower triangle: 10 values, pitch 11), 9-point stencil.
+constexpr int LOR_MP2 = 11;
+
+__global__ void __launch_bounds__(LOR_NT)
+lor_h1_assemble_2d_kernel(int p, int neb, int64_t ne, const double *__restrict__ xv,
+                          const double *__restrict__ cm, int cm_const, const double *__restrict__ cd,
+                          int cd_const, double *__restrict__ V)
+{
+   extern __shared__ double lsm[];
+   const int n1 = p + 1, nv = n1 * n1, ns = p * p;
+   const int64_t e0 = (int64_t)blockIdx.x * neb;
+   const int nev = (int)((ne - e0) < neb ? (ne - e0) : neb);
+   double *Ms = lsm;
+   double *stage = lsm + (size_t)neb * ns * LOR_MP2 + (threadIdx.x >> 5) * (32 * 9);
+   for (int s = threadIdx.x; s < nev * ns; s += LOR_NT)
+   {
+      const int el = s / ns;
+      const int r = s - el * ns;
+      const int kx = r % p, ky = r / p;
+      const int64_t e = e0 + el;
+      double P[2][2][2], mq[2][2], dq[2][2];
+#pragma unroll
+      for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+         for (int dx = 0; dx < 2; dx++)
+         {
+            const int64_t v = (kx + dx) + n1 * (ky + dy) + (int64_t)nv * e;
+            P[0][dx][dy] = xv[2 * v];
+            P[1][dx][dy] = xv[2 * v + 1];
+            mq[dx][dy] = cm_const ? cm[0] : cm[v];
+            dq[dx][dy] = cd_const ? cd[0] : cd[v];
+         }
+      double M[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+         for (int j = 0; j < 4; j++) { M[i][j] = 0.0; }
+#pragma unroll
+      for (int qy = 0; qy < 2; qy++)
+#pragma unroll
+         for (int qx = 0; qx < 2; qx++)
+         {
+            const double J00 = P[0][1][qy] - P[0][0][qy], J10 = P[1][1][qy] - P[1][0][qy];
+            const double J01 = P[0][qx][1] - P[0][qx][0], J11 = P[1][qx][1] - P[1][qx][0];
+            const double detJ = J00 * J11 - J10 * J01;
+            const double w = 0.25;
+            const double wd = dq[qx][qy] * (w / detJ);
+            const double E = J00 * J00 + J10 * J10, F = J00 * J01 + J10 * J11, G = J01 * J01 + J11 * J11;
+            const double K[2][2] = {{wd * G, -(wd * F)}, {-(wd * F), wd * E}};
+            const int q2[2] = {qx, qy};
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+               for (int b = 0; b < 2; b++)
+#pragma unroll
+                  for (int s2 = 0; s2 < 2; s2++)
+#pragma unroll
+                     for (int t2 = 0; t2 < 2; t2++)
+                     {
+                        int i2[2] = {q2[0], q2[1]}, j2[2] = {q2[0], q2[1]};
+                        i2[a] = s2; j2[b] = t2;
+                        const int ii = i2[0] + 2 * i2[1], jj = j2[0] + 2 * j2[1];
+                        if (jj <= ii) { M[ii][jj] += ((s2 == t2) ? K[a][b] : -K[a][b]); }
+                     }
+            const int iq = qx + 2 * qy;
+            M[iq][iq] += mq[qx][qy] * (w * detJ);
+         }
+      double *m = Ms + (size_t)s * LOR_MP2;
+#pragma unroll
+      for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+         for (int jj = 0; jj <= ii; jj++) { m[lor_tri(ii, jj)] = M[ii][jj]; }
+   }
+   __syncthreads();
+   const int total = nev * nv;
+   const int lane = threadIdx.x & 31;
+   double *Vg = V + e0 * (int64_t)nv * 9;
+   for (int d0 = (threadIdx.x >> 5) * 32; d0 < total; d0 += LOR_NT)
+   {
+      const int d = d0 + lane;
+      double acc[9];
+#pragma unroll
+      for (int j = 0; j < 9; j++) { acc[j] = 0.0; }
+      if (d < total)
+      {
+         const int el = d / nv, i = d - el * nv;
+         const int ix = i % n1, iy = i / n1;
+#pragma unroll
+         for (int c = 0; c < 4; c++)
+         {
+            const int cx = c & 1, cy = c >> 1;
+            const int kx = ix - cx, ky = iy - cy;
+            if (kx < 0 || kx >= p || ky < 0 || ky >= p) { continue; }
+            const double *m = Ms + (size_t)(el * ns + kx + p * ky) * LOR_MP2;
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++)
+            {
+               const int jx = jj & 1, jy = jj >> 1;
+               acc[(jx - cx + 1) + 3 * (jy - cy + 1)] += m[lor_tri(c, jj)];
+            }
+         }
+      }
+#pragma unroll
+      for (int j = 0; j < 9; j++) { stage[lane * 9 + j] = acc[j]; }
+      __syncwarp();
+      const int rows = (total - d0) < 32 ? (total - d0) : 32;
+      double *out = Vg + (int64_t)d0 * 9;
+      for (int t = lane; t < rows * 9; t += 32) { out[t] = stage[t]; }
+      __syncwarp();
+   }
+}
+
 // ---- CSR ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int lor_decode(int s) { return s >= 0 ? s : -1 - s; }
 
@@ -246,34 +385,61 @@ __device__ __forceinline__ int lor_decode(int s) { return s >= 0 ? s : -1 - s; }
 // list-intersecting path.  FILL = false only counts.
 constexpr int LOR_MAXE = 16;
 
-template <bool FILL>
+// geometry of the stencil: S = 3^DIM entries, entry j is the offset (j%3-1, (j/3)%3-1, j/9-1)
+template <int DIM>
+struct LorStencil
+{
+   static constexpr int S = DIM == 3 ? 27 : 9;
+   static constexpr int SP = DIM == 3 ? 28 : 12; // row pitch of the neighbour slab (whole int4 words)
+   __device__ static __forceinline__ int nv(int n1) { return DIM == 3 ? n1 * n1 * n1 : n1 * n1; }
+   // local dof reached from local dof i_el by stencil entry j, or -1 outside the element
+   __device__ static __forceinline__ int neighbour(int i_el, int j, int n1)
+   {
+      const int p = n1 - 1;
+      const int jx = i_el % n1 + j % 3 - 1, jy = (i_el / n1) % n1 + (j / 3) % 3 - 1;
+      if (jx < 0 || jx > p || jy < 0 || jy > p) { return -1; }
+      if (DIM == 2) { return jx + n1 * jy; }
+      const int jz = i_el / (n1 * n1) + j / 9 - 1;
+      if (jz < 0 || jz > p) { return -1; }
+      return jx + n1 * (jy + n1 * jz);
+   }
+   // stencil entry that leads from local dof i2 to local dof j2 of the same element
+   __device__ static __forceinline__ int entry(int i2, int j2, int n1)
+   {
+      const int dx = j2 % n1 - i2 % n1, dy = (j2 / n1) % n1 - (i2 / n1) % n1;
+      const int dz = DIM == 3 ? j2 / (n1 * n1) - i2 / (n1 * n1) : -1;
+      return (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1);
+   }
+};
+
+template <int DIM, bool FILL>
 __device__ __noinline__ int lor_csr_row_by_lists(int p, int ii, int lane, const int *__restrict__ gmap,
                                                   const int *__restrict__ K, const int *__restrict__ ind,
                                                   const double *__restrict__ V, int64_t base, int *__restrict__ J,
                                                   double *__restrict__ A)
 {
+   using St = LorStencil<DIM>;
+   constexpr int S = St::S;
    const unsigned lt = (1u << lane) - 1u;
-   const int n1 = p + 1, nv = n1 * n1 * n1;
+   const int n1 = p + 1, nv = St::nv(n1);
    const int i_off = K[ii], i_ne = K[ii + 1] - i_off;
-   const int ox = lane % 3 - 1, oy = (lane / 3) % 3 - 1, oz = lane / 9 - 1;
    int n = 0;
    for (int k = 0; k < i_ne; k++)
    {
       const int iE = lor_decode(ind[i_off + k]);
       const int e = iE / nv, i_el = iE - e * nv;
-      const int ix = i_el % n1, iy = (i_el / n1) % n1, iz = i_el / (n1 * n1);
-      const int jx = ix + ox, jy = iy + oy, jz = iz + oz;
-      bool emit = lane < 27 && jx >= 0 && jx <= p && jy >= 0 && jy <= p && jz >= 0 && jz <= p;
+      const int j_el = lane < S ? St::neighbour(i_el, lane, n1) : -1;
+      bool emit = j_el >= 0;
       int jj = -1;
       double val = 0.0;
       if (emit)
       {
-         jj = lor_decode(gmap[(int64_t)e * nv + jx + n1 * (jy + n1 * jz)]);
+         jj = lor_decode(gmap[(int64_t)e * nv + j_el]);
          int j_off = 0, j_ne = 1;
          if (i_ne > 1) { j_off = K[jj]; j_ne = K[jj + 1] - j_off; }
          if (i_ne == 1 || j_ne == 1)
          {
-            if (FILL) { val = V[((int64_t)e * nv + i_el) * 27 + lane]; }
+            if (FILL) { val = V[((int64_t)e * nv + i_el) * S + lane]; }
          }
          else
          {
@@ -298,10 +464,7 @@ __device__ __noinline__ int lor_csr_row_by_lists(int p, int ii, int lane, const 
                   {
                      const int jE2 = lor_decode(ind[j_off + b]);
                      if (jE2 / nv != e2) { continue; }
-                     const int j2 = jE2 - e2 * nv;
-                     const int dx = j2 % n1 - i2 % n1, dy = (j2 / n1) % n1 - (i2 / n1) % n1,
-                               dz = j2 / (n1 * n1) - i2 / (n1 * n1);
-                     val += V[((int64_t)e2 * nv + i2) * 27 + (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)];
+                     val += V[((int64_t)e2 * nv + i2) * S + St::entry(i2, jE2 - e2 * nv, n1)];
                   }
                }
             }
@@ -320,14 +483,16 @@ __device__ __noinline__ int lor_csr_row_by_lists(int p, int ii, int lane, const 
 }
 
 // PT = p (compile-time index arithmetic) or 0 (run-time p)
-template <int PT, bool FILL>
+template <int DIM, int PT, bool FILL>
 __global__ void __launch_bounds__(128)
 lor_csr_rows_kernel(int p_rt, int ndofs, int maxe, const int *__restrict__ gmap, const int *__restrict__ K,
                     const int *__restrict__ ind, const double *__restrict__ V, const int64_t *__restrict__ I64,
                     int *__restrict__ count, int *__restrict__ J, double *__restrict__ A)
 {
-   __shared__ __align__(16) int nbr_s[4][LOR_MAXE][28];
-   __shared__ double val_s[FILL ? 4 : 1][FILL ? LOR_MAXE : 1][27];
+   using St = LorStencil<DIM>;
+   constexpr int S = St::S, SP = St::SP;
+   __shared__ __align__(16) int nbr_s[4][LOR_MAXE][SP];
+   __shared__ double val_s[FILL ? 4 : 1][FILL ? LOR_MAXE : 1][S];
    const int ii = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
    if (ii >= ndofs) { return; }
    const int p = PT ? PT : p_rt;
@@ -336,27 +501,26 @@ lor_csr_rows_kernel(int p_rt, int ndofs, int maxe, const int *__restrict__ gmap,
    const int64_t base = FILL ? I64[ii] : 0;
    if (i_ne > maxe)
    {
-      const int n = lor_csr_row_by_lists<FILL>(p, ii, lane, gmap, K, ind, V, base, J, A);
+      const int n = lor_csr_row_by_lists<DIM, FILL>(p, ii, lane, gmap, K, ind, V, base, J, A);
       if (!FILL && lane == 0) { count[ii] = n; }
       return;
    }
    const unsigned lt = (1u << lane) - 1u;
-   const int n1 = p + 1, nv = n1 * n1 * n1;
-   const int ox = lane % 3 - 1, oy = (lane / 3) % 3 - 1, oz = lane / 9 - 1; // lane = stencil entry (< 27)
-   int (*nbr)[28] = nbr_s[w];
+   const int n1 = p + 1, nv = St::nv(n1);
+   int (*nbr)[SP] = nbr_s[w];
    if (i_ne == 1)
    {
       // a dof of one element only (its interior): the row is that element's stencil, as it stands
       const int iE = lor_decode(ind[i_off]);
       const int e = iE / nv, i_el = iE - e * nv;
-      const int jx = i_el % n1 + ox, jy = (i_el / n1) % n1 + oy, jz = i_el / (n1 * n1) + oz;
-      const bool emit = lane < 27 && jx >= 0 && jx <= p && jy >= 0 && jy <= p && jz >= 0 && jz <= p;
+      const int j_el = lane < S ? St::neighbour(i_el, lane, n1) : -1;
+      const bool emit = j_el >= 0;
       const unsigned mask = __ballot_sync(0xffffffffu, emit);
       if (FILL && emit)
       {
          const int64_t pos = base + __popc(mask & lt);
-         J[pos] = lor_decode(gmap[(int64_t)e * nv + jx + n1 * (jy + n1 * jz)]);
-         A[pos] = V[(int64_t)iE * 27 + lane];
+         J[pos] = lor_decode(gmap[(int64_t)e * nv + j_el]);
+         A[pos] = V[(int64_t)iE * S + lane];
       }
       if (!FILL && lane == 0) { count[ii] = __popc(mask); }
       return;
@@ -365,25 +529,24 @@ lor_csr_rows_kernel(int p_rt, int ndofs, int maxe, const int *__restrict__ gmap,
    {
       const int iE = lor_decode(ind[i_off + a]);
       const int e = iE / nv, i_el = iE - e * nv;
-      const int jx = i_el % n1 + ox, jy = (i_el / n1) % n1 + oy, jz = i_el / (n1 * n1) + oz;
-      if (lane < 28)
+      if (lane < SP)
       {
-         const bool in = lane < 27 && jx >= 0 && jx <= p && jy >= 0 && jy <= p && jz >= 0 && jz <= p;
-         nbr[a][lane] = in ? lor_decode(gmap[(int64_t)e * nv + jx + n1 * (jy + n1 * jz)]) : -1;
-         if (FILL && lane < 27) { val_s[w][a][lane] = V[(int64_t)iE * 27 + lane]; }
+         const int j_el = lane < S ? St::neighbour(i_el, lane, n1) : -1;
+         nbr[a][lane] = j_el >= 0 ? lor_decode(gmap[(int64_t)e * nv + j_el]) : -1;
+         if (FILL && lane < S) { val_s[w][a][lane] = V[(int64_t)iE * S + lane]; }
       }
    }
    __syncwarp();
    int n = 0;
    for (int k = 0; k < i_ne; k++)
    {
-      const int jj = lane < 27 ? nbr[k][lane] : -1;
+      const int jj = lane < S ? nbr[k][lane] : -1;
       bool emit = jj >= 0;
       for (int a = 0; a < k; a++) // a lower element that also holds jj has emitted the entry
       {
          const int4 *row = reinterpret_cast<const int4 *>(nbr[a]);
 #pragma unroll
-         for (int l = 0; l < 7; l++)
+         for (int l = 0; l < SP / 4; l++)
          {
             const int4 v = row[l];
             emit = emit && v.x != jj && v.y != jj && v.z != jj && v.w != jj;
@@ -392,14 +555,14 @@ lor_csr_rows_kernel(int p_rt, int ndofs, int maxe, const int *__restrict__ gmap,
       double val = 0.0;
       if (FILL)
       {
-         val = val_s[w][k][lane < 27 ? lane : 0];
+         val = val_s[w][k][lane < S ? lane : 0];
          for (int a = k + 1; a < i_ne; a++)
          {
             // the dofs of an element are distinct: at most one slot of element a holds jj
             const int4 *row = reinterpret_cast<const int4 *>(nbr[a]);
             int m = -1;
 #pragma unroll
-            for (int l = 0; l < 7; l++)
+            for (int l = 0; l < SP / 4; l++)
             {
                const int4 v = row[l];
                m = v.x == jj ? 4 * l : m;
@@ -422,22 +585,22 @@ lor_csr_rows_kernel(int p_rt, int ndofs, int maxe, const int *__restrict__ gmap,
    if (!FILL && lane == 0) { count[ii] = n; }
 }
 
-template <bool FILL>
+template <int DIM, bool FILL>
 static void lor_launch_rows(cudaStream_t st, int p, int nd, int maxe, const b2f_restriction *r, const double *V,
                             const int64_t *I64, int *count, int *J, double *A)
 {
    const unsigned grid = (unsigned)cdiv(32 * (int64_t)nd, 128);
-#define LOR_ROWS(P)                                                                                             \
-   case P:                                                                                                      \
-      lor_csr_rows_kernel<P, FILL><<<grid, 128, 0, st>>>(p, nd, maxe, r->gather_map, r->offsets, r->indices, V, \
-                                                          I64, count, J, A);                                     \
+#define LOR_ROWS(P)                                                                                                  \
+   case P:                                                                                                           \
+      lor_csr_rows_kernel<DIM, P, FILL><<<grid, 128, 0, st>>>(p, nd, maxe, r->gather_map, r->offsets, r->indices, V, \
+                                                               I64, count, J, A);                                     \
       break;
    switch (p)
    {
       LOR_ROWS(1) LOR_ROWS(2) LOR_ROWS(3) LOR_ROWS(4) LOR_ROWS(5) LOR_ROWS(6) LOR_ROWS(7) LOR_ROWS(8)
       default:
-         lor_csr_rows_kernel<0, FILL><<<grid, 128, 0, st>>>(p, nd, maxe, r->gather_map, r->offsets, r->indices, V, I64,
-                                                            count, J, A);
+         lor_csr_rows_kernel<DIM, 0, FILL><<<grid, 128, 0, st>>>(p, nd, maxe, r->gather_map, r->offsets, r->indices, V,
+                                                                 I64, count, J, A);
    }
 #undef LOR_ROWS
 }
@@ -502,7 +665,7 @@ int b2f_lor_vertex_coordinates(b2f_ctx *ctx, int dim, int p, int node_nd1d, int6
 {
    B2F_ON(ctx);
    B2F_REQUIRE(ctx && Bn_h && (ne == 0 || (nodes_e && x_vert)), "b2f_lor_vertex_coordinates: NULL argument");
-   B2F_REQUIRE(dim == 3, "b2f_lor_vertex_coordinates: dim = %d (3D only)", dim);
+   B2F_REQUIRE(dim == 2 || dim == 3, "b2f_lor_vertex_coordinates: dim = %d", dim);
    B2F_REQUIRE(p >= 1 && p <= 16 && node_nd1d >= 2 && node_nd1d <= 17, "b2f_lor_vertex_coordinates: p = %d, nd = %d",
                p, node_nd1d);
    if (ne == 0) { return B2F_OK; }
@@ -517,9 +680,17 @@ int b2f_lor_vertex_coordinates(b2f_ctx *ctx, int dim, int p, int node_nd1d, int6
    }
    if (rc == B2F_OK)
    {
-      const int64_t n = ne * n1 * n1 * n1;
-      lor_vertex_coordinates_kernel<<<(unsigned)cdiv(n, 128), 128, 0, ctx->stream>>>(n1, node_nd1d, ne, Bn, nodes_e,
-                                                                                     x_vert);
+      const int64_t n = ne * n1 * n1 * (dim == 3 ? n1 : 1);
+      if (dim == 3)
+      {
+         lor_vertex_coordinates_kernel<<<(unsigned)cdiv(n, 128), 128, 0, ctx->stream>>>(n1, node_nd1d, ne, Bn, nodes_e,
+                                                                                        x_vert);
+      }
+      else
+      {
+         lor_vertex_coordinates_2d_kernel<<<(unsigned)cdiv(n, 128), 128, 0, ctx->stream>>>(n1, node_nd1d, ne, Bn,
+                                                                                           nodes_e, x_vert);
+      }
       ctx->launches++;
       if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
       {
@@ -531,13 +702,13 @@ int b2f_lor_vertex_coordinates(b2f_ctx *ctx, int dim, int p, int node_nd1d, int6
    return rc;
 }
 
-static int lor_assemble_impl(b2f_ctx *ctx, const b2f_restriction *r, int p, const double *x_vert, const double *c_mass,
+static int lor_assemble_impl(b2f_ctx *ctx, const b2f_restriction *r, int dim, int p, const double *x_vert, const double *c_mass,
                              int64_t n_mass, const double *c_diff, int64_t n_diff, const int *ess, int n_ess,
                              int keep_sparse_ij, b2f_lor *L)
 {
-   const int n1 = p + 1, nv = n1 * n1 * n1;
+   const int n1 = p + 1, nv = n1 * n1 * (dim == 3 ? n1 : 1), ns = p * p * (dim == 3 ? p : 1), S = dim == 3 ? 27 : 9;
    const int64_t ne = r->ne;
-   L->ctx = ctx; L->p = p; L->ne = ne; L->ndofs = r->ndofs;
+   L->ctx = ctx; L->dim = dim; L->p = p; L->ne = ne; L->ndofs = r->ndofs;
    const int nd = r->ndofs;
    B2F_CUDA(cudaMalloc(&L->I, sizeof(int) * ((size_t)nd + 1)));
    if (ne == 0 || nd == 0)
@@ -546,16 +717,24 @@ static int lor_assemble_impl(b2f_ctx *ctx, const b2f_restriction *r, int p, cons
       B2F_CUDA(cudaStreamSynchronize(ctx->stream));
       return B2F_OK;
    }
-   B2F_CUDA(cudaMalloc(&L->V, sizeof(double) * (size_t)ne * nv * 27));
-   // macro elements per CTA: about one sub-hexahedron per thread
-   int neb = LOR_NT / (p * p * p);
+   B2F_CUDA(cudaMalloc(&L->V, sizeof(double) * (size_t)ne * nv * S));
+   // macro elements per CTA: about one sub-element per thread
+   int neb = LOR_NT / ns;
    if (neb < 1) { neb = 1; }
-   const size_t smem = sizeof(double) * ((size_t)neb * p * p * p * LOR_MP + (LOR_NT / 32) * 32 * 27);
+   const size_t smem = sizeof(double) * ((size_t)neb * ns * (dim == 3 ? LOR_MP : LOR_MP2) + (LOR_NT / 32) * 32 * S);
    B2F_REQUIRE((int)smem <= ctx->max_smem_optin, "b2f_lor_assemble_h1: p = %d needs %zu bytes of shared memory", p, smem);
-   B2F_CUDA(cudaFuncSetAttribute(lor_h1_assemble_3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-   lor_h1_assemble_3d_kernel<<<(unsigned)cdiv(ne, neb), LOR_NT, smem, ctx->stream>>>(p, neb, ne, x_vert, c_mass,
-                                                                                     n_mass == 1, c_diff, n_diff == 1,
-                                                                                     L->V);
+   if (dim == 3)
+   {
+      B2F_CUDA(cudaFuncSetAttribute(lor_h1_assemble_3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      lor_h1_assemble_3d_kernel<<<(unsigned)cdiv(ne, neb), LOR_NT, smem, ctx->stream>>>(
+         p, neb, ne, x_vert, c_mass, n_mass == 1, c_diff, n_diff == 1, L->V);
+   }
+   else
+   {
+      B2F_CUDA(cudaFuncSetAttribute(lor_h1_assemble_2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      lor_h1_assemble_2d_kernel<<<(unsigned)cdiv(ne, neb), LOR_NT, smem, ctx->stream>>>(
+         p, neb, ne, x_vert, c_mass, n_mass == 1, c_diff, n_diff == 1, L->V);
+   }
    B2F_LAUNCH_CHECK(ctx);
    // rows: count, scan, fill.  B2F_LOR_MAXE (testing): rows held by more elements than this take the
    // list-intersecting path
@@ -578,7 +757,8 @@ static int lor_assemble_impl(b2f_ctx *ctx, const b2f_restriction *r, int p, cons
    LOR_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * ((size_t)nd + 1), ctx->stream));
    if (rc == B2F_OK)
    {
-      lor_launch_rows<false>(ctx->stream, p, nd, maxe, r, L->V, nullptr, count, nullptr, nullptr);
+      if (dim == 3) { lor_launch_rows<3, false>(ctx->stream, p, nd, maxe, r, L->V, nullptr, count, nullptr, nullptr); }
+      else { lor_launch_rows<2, false>(ctx->stream, p, nd, maxe, r, L->V, nullptr, count, nullptr, nullptr); }
       ctx->launches++;
       LOR_CUDA(cudaGetLastError());
    }
@@ -601,7 +781,8 @@ static int lor_assemble_impl(b2f_ctx *ctx, const b2f_restriction *r, int p, cons
    if (rc == B2F_OK)
    {
       lor_offsets_to_int_kernel<<<(unsigned)cdiv(nd + 1, 256), 256, 0, ctx->stream>>>(nd + 1, I64, L->I);
-      lor_launch_rows<true>(ctx->stream, p, nd, maxe, r, L->V, I64, nullptr, L->J, L->A);
+      if (dim == 3) { lor_launch_rows<3, true>(ctx->stream, p, nd, maxe, r, L->V, I64, nullptr, L->J, L->A); }
+      else { lor_launch_rows<2, true>(ctx->stream, p, nd, maxe, r, L->V, I64, nullptr, L->J, L->A); }
       ctx->launches += 2;
       LOR_CUDA(cudaGetLastError());
    }
@@ -630,10 +811,10 @@ int b2f_lor_assemble_h1(b2f_ctx *ctx, const b2f_restriction *r, int dim, int p, 
 {
    B2F_ON(ctx);
    B2F_REQUIRE(ctx && r && out && c_mass && c_diff, "b2f_lor_assemble_h1: NULL argument");
-   B2F_REQUIRE(dim == 3, "b2f_lor_assemble_h1: dim = %d (3D only)", dim);
+   B2F_REQUIRE(dim == 2 || dim == 3, "b2f_lor_assemble_h1: dim = %d", dim);
    B2F_REQUIRE(p >= 1 && p <= 8, "b2f_lor_assemble_h1: order %d (the reference has kernels for 1..8)", p);
    B2F_REQUIRE(r->vdim == 1, "b2f_lor_assemble_h1: vdim = %d", r->vdim);
-   const int64_t nv = (int64_t)(p + 1) * (p + 1) * (p + 1);
+   const int64_t nv = (int64_t)(p + 1) * (p + 1) * (dim == 3 ? p + 1 : 1);
    B2F_REQUIRE(r->dof == nv, "b2f_lor_assemble_h1: the restriction has %d dofs per element, order %d has %lld", r->dof,
                p, (long long)nv);
    B2F_REQUIRE(r->ne == 0 || x_vert, "b2f_lor_assemble_h1: NULL vertex coordinates");
@@ -644,7 +825,7 @@ int b2f_lor_assemble_h1(b2f_ctx *ctx, const b2f_restriction *r, int dim, int p, 
    B2F_REQUIRE((int64_t)r->ne * nv < 2147483647LL, "b2f_lor_assemble_h1: E-vector too long for 32-bit indices");
    b2f_lor *L = new (std::nothrow) b2f_lor;
    B2F_REQUIRE(L, "b2f_lor_assemble_h1: out of memory");
-   const int rc = lor_assemble_impl(ctx, r, p, x_vert, c_mass, n_mass, c_diff, n_diff, ess, n_ess, keep_sparse_ij, L);
+   const int rc = lor_assemble_impl(ctx, r, dim, p, x_vert, c_mass, n_mass, c_diff, n_diff, ess, n_ess, keep_sparse_ij, L);
    if (rc != B2F_OK)
    {
       lor_free(L);
@@ -670,7 +851,7 @@ int b2f_lor_sparse_ij(const b2f_lor *L, const double **V, int64_t *size)
    B2F_REQUIRE(L && V, "b2f_lor_sparse_ij: NULL argument");
    B2F_REQUIRE(L->V || L->ne == 0, "b2f_lor_sparse_ij: the stencil array was not kept (keep_sparse_ij = 0)");
    *V = L->V;
-   if (size) { *size = L->ne * 27 * (int64_t)(L->p + 1) * (L->p + 1) * (L->p + 1); }
+   if (size) { *size = L->ne * (L->dim == 3 ? 27 : 9) * (int64_t)(L->p + 1) * (L->p + 1) * (L->dim == 3 ? L->p + 1 : 1); }
    return B2F_OK;
 }
 

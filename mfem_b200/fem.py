@@ -778,7 +778,7 @@ class LORSparseMatrix:
         return self._d2h(self._A, self.nnz, np.float64)
 
     def sparse_ij(self):
-        """BatchedLORAssembly::sparse_ij, (NE, (p+1)^3, 27); needs keep_sparse_ij at assembly"""
+        """BatchedLORAssembly::sparse_ij, (NE, (p+1)^dim, 3^dim); needs keep_sparse_ij at assembly"""
         ptr, n = vp(), capi.i64()
         call("b2f_lor_sparse_ij", self.h, C.byref(ptr), C.byref(n))
         return self._d2h(ptr, n.value, np.float64)
@@ -799,13 +799,13 @@ class LORSparseMatrix:
 
 
 class BatchedLORAssembly:
-    """BatchedLORAssembly (fem/lor/lor_batched.hpp:26-131) for H1 spaces in 3D: the low-order-refined
+    """BatchedLORAssembly (fem/lor/lor_batched.hpp:26-131) for H1 spaces in 2D / 3D: the low-order-refined
     matrix of a mass + diffusion form, assembled on the device as CSR -- what LORSolver hands to an
     algebraic multigrid.  The constructor forms the LOR vertex coordinates (FormLORVertexCoordinates)."""
 
     def __init__(self, device, fes):
-        if fes.dim != 3 or fes.vdim != 1:
-            raise ValueError("BatchedLORAssembly: scalar H1 spaces in 3D only")
+        if fes.dim not in (2, 3) or fes.vdim != 1:
+            raise ValueError("BatchedLORAssembly: scalar H1 spaces in 2D / 3D only")
         self.dev, self.fes = device, fes
         p, ne = fes.p, fes.ne
         nodes, nd = fes.mesh.nodes_e(fes.elem_vertices)
@@ -813,8 +813,9 @@ class BatchedLORAssembly:
         Bn, _ = h1_dof_to_quad(nd - 1, gp)  # (q, d) column-major: B[q + nq*d]
         Bn = np.ascontiguousarray(_f64(Bn).reshape(nd, p + 1).T)  # (p+1, nd) row-major
         nodes_d = device.to_device(_f64(nodes))
-        self.x_vert = device.empty(3 * (p + 1) ** 3 * ne)
-        call("b2f_lor_vertex_coordinates", device.ctx, 3, p, nd, ne, _np_ptr(Bn), _dp(nodes_d), _dp(self.x_vert))
+        self.x_vert = device.empty(fes.dim * (p + 1) ** fes.dim * ne)
+        call("b2f_lor_vertex_coordinates", device.ctx, fes.dim, p, nd, ne, _np_ptr(Bn), _dp(nodes_d),
+             _dp(self.x_vert))
         del nodes_d
 
     def GetLORVertexCoordinates(self):
@@ -823,7 +824,7 @@ class BatchedLORAssembly:
     def Assemble(self, a, ess_dofs=None, mass_coeff=None, diff_coeff=None, keep_sparse_ij=False):
         """Assemble(a, ess_dofs, A): `a` is a BilinearForm whose MassIntegrator / DiffusionIntegrator
         constants are used, or None with mass_coeff / diff_coeff given: a number, or the coefficient at
-        the (p+1)^3 Gauss-Lobatto points of every element, (NE, (p+1)^3) -- BatchedLORKernel's c1 / c2."""
+        the (p+1)^dim Gauss-Lobatto points of every element, (NE, (p+1)^dim) -- BatchedLORKernel's c1 / c2."""
         dev, fes = self.dev, self.fes
         cm, cd = 0.0, 0.0
         if a is not None:
@@ -842,7 +843,7 @@ class BatchedLORAssembly:
         ess_d = dev.to_device(ess) if ess.size else None
         R = fes.GetElementRestriction(dev)
         h = vp()
-        call("b2f_lor_assemble_h1", dev.ctx, R.h, 3, fes.p, _dp(self.x_vert), _dp(cm_d), cm_d.numel(), _dp(cd_d),
+        call("b2f_lor_assemble_h1", dev.ctx, R.h, fes.dim, fes.p, _dp(self.x_vert), _dp(cm_d), cm_d.numel(), _dp(cd_d),
              cd_d.numel(), _dp(ess_d), ess.size, int(bool(keep_sparse_ij)), C.byref(h))
         return LORSparseMatrix(dev, h)
 

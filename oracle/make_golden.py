@@ -113,6 +113,12 @@ CASES = {
     "lor_3d_p8_n1": dict(dim=3, n=1, ny=2, nz=1, p=8, lor=1, lorkind="diffusion", varcoef=1),
     "lor_mesh_fichera_q2_p3": dict(mesh=DATA + "fichera-q2.mesh", refine=0, p=3, lor=1, lorkind="both", varcoef=1),
     "lor_mesh_toroid_hex_p2": dict(mesh=DATA + "toroid-hex.mesh", refine=0, p=2, lor=1, lorkind="diffusion"),
+    # 2D (BatchedLOR_H1::Assemble2D, 9-point stencil)
+    "lor_2d_p1_n4": dict(dim=2, n=4, p=1, lor=1, lorkind="diffusion"),
+    "lor_2d_p3_n3_curved": dict(dim=2, n=3, p=3, lor=1, lorkind="both", varcoef=1, curved=1),
+    "lor_2d_p5_n2": dict(dim=2, n=2, ny=3, p=5, lor=1, lorkind="both", mass_const=0.5, diff_const=2.0),
+    "lor_2d_p8_n2_curved": dict(dim=2, n=2, p=8, lor=1, lorkind="diffusion", varcoef=1, curved=1),
+    "lor_mesh_star_q3_p4": dict(mesh=DATA + "star-q3.mesh", refine=0, p=4, lor=1, lorkind="both", varcoef=1),
 }
 
 

@@ -19,7 +19,7 @@ def load(name):
 
 
 def test_fixtures_present():
-    assert len(NAMES) >= 9
+    assert len(NAMES) >= 14
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -33,16 +33,17 @@ def test_reference_batched_equals_reference_legacy(name):
 @pytest.mark.parametrize("name", NAMES)
 def test_oracle_lor_against_reference(name):
     g = load(name)
-    p, ne, nd = int(g["p"][0]), int(g["NE"][0]), int(g["ndofs"][0])
+    p, ne, nd, dim = int(g["p"][0]), int(g["NE"][0]), int(g["ndofs"][0]), int(g["dim"][0])
     n1 = p + 1
-    X = L.lor_vertex_coordinates(int(g["node_order"][0]), g["nodes_e"], ne, p)
+    X = L.lor_vertex_coordinates(int(g["node_order"][0]), g["nodes_e"], ne, p, dim)
     assert np.abs(X - g["X_vert"]).max() < 1e-14 * max(1.0, np.abs(g["X_vert"]).max())
-    assert np.array_equal(L.sparse_mapping(p).reshape(-1), g["sparse_mapping"])
-    Vref = g["sparse_ij"].reshape(ne, n1 ** 3, 27)
-    if ne * p ** 3 <= 1000:  # python loops: the larger cases check the CSR stage only
-        V = L.assemble_sparse_ij(p, ne, g["X_vert"], g["c_mass"], g["c_diff"])
+    assert np.array_equal(L.sparse_mapping(p, dim).reshape(-1), g["sparse_mapping"])
+    Vref = g["sparse_ij"].reshape(ne, n1 ** dim, 3 ** dim)
+    if ne * p ** dim <= 1000:  # python loops: the larger cases check the CSR stage only
+        asm = L.assemble_sparse_ij if dim == 3 else L.assemble_sparse_ij_2d
+        V = asm(p, ne, g["X_vert"], g["c_mass"], g["c_diff"])
         assert np.abs(V - Vref).max() < 1e-13 * np.abs(Vref).max()
-    I, J, A = L.fill_csr(p, ne, nd, g["gather_map"], g["offsets"], g["indices"], Vref)
+    I, J, A = L.fill_csr(p, ne, nd, g["gather_map"], g["offsets"], g["indices"], Vref, dim)
     assert np.array_equal(I, g["I"]) and np.array_equal(J, g["J"])      # bit-exact index work
     assert np.abs(A - g["data"]).max() <= 1e-15 * np.abs(A).max()
     Ab = L.eliminate_bc(nd, I, J, A, g["ess_tdof_list"])
