@@ -611,10 +611,12 @@ __global__ void lor_offsets_to_int_kernel(int n, const int64_t *__restrict__ in,
    if (i < n) { out[i] = (int)in[i]; }
 }
 
-__global__ void lor_mark_kernel(int n, const int *__restrict__ ess, unsigned char *__restrict__ mark)
+__global__ void lor_mark_kernel(int n, int ndofs, const int *__restrict__ ess, unsigned char *__restrict__ mark)
 {
    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < n) { mark[ess[i]] = 1; }
+   if (i >= n) { return; }
+   const int d = ess[i];
+   if (d >= 0 && d < ndofs) { mark[d] = 1; } // an index outside the space is ignored, never written through
 }
 
 // EliminateBC(ess, DIAG_KEEP): rows and columns of the essential dofs zeroed, the diagonal kept
@@ -792,7 +794,7 @@ static int lor_assemble_impl(b2f_ctx *ctx, const b2f_restriction *r, int dim, in
       LOR_CUDA(cudaMemsetAsync(mark, 0, (size_t)nd, ctx->stream));
       if (rc == B2F_OK)
       {
-         lor_mark_kernel<<<(unsigned)cdiv(n_ess, 256), 256, 0, ctx->stream>>>(n_ess, ess, mark);
+         lor_mark_kernel<<<(unsigned)cdiv(n_ess, 256), 256, 0, ctx->stream>>>(n_ess, nd, ess, mark);
          lor_eliminate_bc_kernel<<<(unsigned)cdiv(nd, 128), 128, 0, ctx->stream>>>(nd, L->I, L->J, mark, L->A);
          ctx->launches += 2;
          LOR_CUDA(cudaGetLastError());
