@@ -56,6 +56,7 @@ def parse():
                     help="skip timing the reference's own CUDA backend (oracle/_ref_cuda) on this GPU")
     ap.add_argument("--no-sweep", action="store_true", help="skip the BP1/BP3/BP5 x p=1..8 table after the headline")
     ap.add_argument("--sweep-dofs", type=float, default=50e6, help="dofs per sweep case (BASELINE config C2: ~50 M)")
+    ap.add_argument("--no-lor", action="store_true", help="skip the LOR matrix assembly record (SURVEY 8f row 4)")
     ap.add_argument("--no-anchor", action="store_true", help="skip the 1-GPU run at the per-GPU size of --gpus N > 1")
     ap.add_argument("--cpu-n", type=int, default=None, help="elements per side of the CPU sample")
     ap.add_argument("--curved", type=int, default=None,
@@ -485,6 +486,12 @@ def main():
                                      "2 timed solves after 2 warm-up solves",
                              "rows": sweep_table(m, torch, dev, capi_call, peak, a.sweep_dofs, a.iters)}
             line["sweep"]["seconds"] = round(time.time() - t_sw, 1)
+        if not a.no_lor:
+            # last, and never required: nothing here can touch the numbers above
+            try:
+                line["lor"] = lor_record(m, torch, dev, capi_call, peak, with_ref=not a.no_gpu_baseline)
+            except Exception as ex:
+                line["lor"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if parity is not None and parity.get("ok") is False:
@@ -541,6 +548,67 @@ def run_gpu_baseline(w, iters, n=None):
                                               if p == 8 else ""),
             "config": f"BP{w['bp']} p={p} {n}^3 hexes, {nd} dofs, MFEM -pa -d cuda (sm_100), {iters} Jacobi-PCG "
                       f"iterations", "dofs": nd, "final_norm": j["final_norm"]}
+
+
+def lor_record(m, torch, dev, capi_call, peak, with_ref, p=4, n=64, reps=3):
+    """SURVEY 8f row 4, the assembled half: the low-order-refined matrix of the BP3 form (what
+    LORSolver<AMG> is built from; BatchedLORAssembly::Assemble, fem/lor/lor_batched.cpp:712) at
+    p = 4, 64^3 hexes (17 M dofs, 455 M nonzeros): seconds of one Assemble (stencil array, CSR,
+    boundary elimination; CUDA events, allocations included), the algorithmic bytes (24 B per E-dof of
+    vertex coordinates + 12 B per nonzero + 4 B per row) against the HBM peak, the checksum |A x| for
+    x = Vector::Randomize(1), and beside it the reference's own CUDA backend on the same problem."""
+    import ctypes as C
+    import numpy as np
+    fes = m.FiniteElementSpace(m.Mesh.MakeCartesian3D(n, n, n), m.H1_FECollection(p, 3))
+    N = fes.GetNDofs()
+    ess = fes.GetEssentialTrueDofs()
+    fes.GetElementRestriction(dev)
+    lor = m.BatchedLORAssembly(dev, fes)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    times, ktimes, A = [], [], None
+    for r in range(reps + 1):
+        if A is not None:
+            A.close()
+        torch.cuda.synchronize()
+        e0.record()
+        A = lor.Assemble(None, ess, mass_coeff=0.0, diff_coeff=1.0)
+        e1.record()
+        torch.cuda.synchronize()
+        if r:
+            times.append(e0.elapsed_time(e1) * 1e-3)
+            ktimes.append(A.kernel_ms() * 1e-3)
+    xs = np.empty(N)
+    capi_call("b2f_vector_randomize_h", xs.ctypes.data_as(C.c_void_p), xs.size, 1)
+    y = dev.empty(N)
+    A.Mult(dev.to_device(xs), y)
+    dev.sync()
+    best, kbest, nnz = min(times), min(ktimes), A.NumNonZeroElems()
+    alg = 24.0 * fes.ne * (p + 1) ** 3 + 12.0 * nnz + 4.0 * N
+    rec = {"what": "BatchedLORAssembly::Assemble, H1 diffusion, CSR on the device", "p": p, "dofs": N, "nnz": nnz,
+           "assemble_ms": best * 1e3, "assemble_ms_is": "one call, host clock on the device timeline: kernels + the "
+           "call's own cudaMalloc / cudaFree of the stencil array and the CSR arrays",
+           "kernel_ms": kbest * 1e3, "mdofs_per_s": N / best / 1e6, "algorithmic_gb": alg / 1e9,
+           "frac_of_hbm_roofline": alg / kbest / 1e9 / peak, "checksum_norm_Ax": float(torch.linalg.norm(y))}
+    A.close()
+    del lor, y
+    torch.cuda.empty_cache()
+    drv = ref_cuda_driver_path()
+    if with_ref and drv:
+        try:
+            r = subprocess.run([drv, "bench", "--mode", "lor", "--p", str(p), "--n", str(n), "--reps", str(reps),
+                                "--lorkind", "diffusion"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600,
+                               env=dict(os.environ, REF_DRIVER_DEVICE="cuda"))
+            j = json.loads(r.stdout.decode().strip().splitlines()[-1])
+            rec["reference_cuda"] = {"assemble_ms": j["assemble_seconds"] * 1e3,
+                                     "mdofs_per_s": j["ndofs"] / j["assemble_seconds"] / 1e6,
+                                     "checksum_norm_Ax": j["ynorm"],
+                                     "config": "the unmodified reference, MFEM_USE_CUDA (sm_100), same mesh, form and x"}
+            rec["b200_over_reference"] = j["assemble_seconds"] / best
+            rec["b200_kernels_over_reference"] = j["assemble_seconds"] / kbest
+            rec["checksum_rel_diff"] = abs(j["ynorm"] - rec["checksum_norm_Ax"]) / abs(j["ynorm"])
+        except Exception as ex:
+            rec["reference_cuda"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
+    return rec
 
 
 def sweep_table(m, torch, dev, capi_call, peak, dofs, iters):

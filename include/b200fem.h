@@ -402,6 +402,9 @@ int b2f_lor_assemble_h1(b2f_ctx *ctx, const b2f_restriction *r, int dim, int p, 
 /* the assembled SparseMatrix: device pointers I (n_rows + 1), J (nnz), A (nnz); any may be NULL */
 int b2f_lor_csr(const b2f_lor *lor, int *n_rows, int64_t *nnz, const int **I, const int **J, const double **A);
 int b2f_lor_sparse_ij(const b2f_lor *lor, const double **V, int64_t *size);
+/* device time of the kernels of the assembly that produced `lor` (CUDA events on the context's stream
+ * around stencil array + count + scan and around fill + elimination; allocations excluded) */
+int b2f_lor_kernel_ms(const b2f_lor *lor, double *ms);
 /* SparseMatrix::Mult: y = A x (device vectors) */
 int b2f_lor_mult(b2f_lor *lor, const double *x, double *y);
 void b2f_lor_destroy(b2f_lor *lor);

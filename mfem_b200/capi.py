@@ -94,6 +94,7 @@ PROTOTYPES = {
                                       C.POINTER(vp)]),
     "b2f_lor_csr": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
     "b2f_lor_sparse_ij": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
+    "b2f_lor_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_double)]),
     "b2f_lor_mult": (C.c_int, [vp, vp, vp]),
     "b2f_lor_destroy": (None, [vp]),
     "b2f_operator_create": (C.c_int, [vp, vp, C.POINTER(vp), C.c_int, vp, C.c_int, C.POINTER(vp)]),

@@ -30,6 +30,7 @@ struct b2f_lor
    int *I = nullptr, *J = nullptr;
    double *A = nullptr;
    double *V = nullptr; // (3^dim, nd1d^dim, NE) macro-element stencil array ("sparse_ij")
+   float kernel_ms = 0.f; // device time of the assembly's kernels (events on the stream; allocations excluded)
 };
 
 namespace b2f
@@ -725,6 +726,10 @@ static int lor_assemble_impl(b2f_ctx *ctx, const b2f_restriction *r, int dim, in
    if (neb < 1) { neb = 1; }
    const size_t smem = sizeof(double) * ((size_t)neb * ns * (dim == 3 ? LOR_MP : LOR_MP2) + (LOR_NT / 32) * 32 * S);
    B2F_REQUIRE((int)smem <= ctx->max_smem_optin, "b2f_lor_assemble_h1: p = %d needs %zu bytes of shared memory", p, smem);
+   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+   for (int i = 0; i < 4; i++) { cudaEventCreate(&ev[i]); }
+   struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int i = 0; i < 4; i++) { if (e[i]) { cudaEventDestroy(e[i]); } } } } evg{ev};
+   if (ev[0]) { cudaEventRecord(ev[0], ctx->stream); }
    if (dim == 3)
    {
       B2F_CUDA(cudaFuncSetAttribute(lor_h1_assemble_3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -768,6 +773,7 @@ static int lor_assemble_impl(b2f_ctx *ctx, const b2f_restriction *r, int dim, in
    LOR_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, count, I64, nd + 1, ctx->stream));
    LOR_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
    LOR_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, count, I64, nd + 1, ctx->stream));
+   if (ev[1]) { cudaEventRecord(ev[1], ctx->stream); }
    int64_t nnz = 0;
    LOR_CUDA(cudaMemcpyAsync(&nnz, I64 + nd, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
    LOR_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -780,6 +786,7 @@ static int lor_assemble_impl(b2f_ctx *ctx, const b2f_restriction *r, int dim, in
    L->nnz = nnz;
    LOR_CUDA(cudaMalloc(&L->J, sizeof(int) * (size_t)(nnz ? nnz : 1)));
    LOR_CUDA(cudaMalloc(&L->A, sizeof(double) * (size_t)(nnz ? nnz : 1)));
+   if (ev[2]) { cudaEventRecord(ev[2], ctx->stream); }
    if (rc == B2F_OK)
    {
       lor_offsets_to_int_kernel<<<(unsigned)cdiv(nd + 1, 256), 256, 0, ctx->stream>>>(nd + 1, I64, L->I);
@@ -800,8 +807,17 @@ static int lor_assemble_impl(b2f_ctx *ctx, const b2f_restriction *r, int dim, in
          LOR_CUDA(cudaGetLastError());
       }
    }
+   if (ev[3]) { cudaEventRecord(ev[3], ctx->stream); }
    LOR_CUDA(cudaStreamSynchronize(ctx->stream));
 #undef LOR_CUDA
+   if (rc == B2F_OK && ev[0] && ev[1] && ev[2] && ev[3])
+   {
+      float a = 0.f, b = 0.f;
+      if (cudaEventElapsedTime(&a, ev[0], ev[1]) == cudaSuccess && cudaEventElapsedTime(&b, ev[2], ev[3]) == cudaSuccess)
+      {
+         L->kernel_ms = a + b;
+      }
+   }
    cleanup();
    if (rc == B2F_OK && !keep_sparse_ij) { cudaFree(L->V); L->V = nullptr; }
    return rc;
@@ -845,6 +861,13 @@ int b2f_lor_csr(const b2f_lor *L, int *n_rows, int64_t *nnz, const int **I, cons
    if (I) { *I = L->I; }
    if (J) { *J = L->J; }
    if (A) { *A = L->A; }
+   return B2F_OK;
+}
+
+int b2f_lor_kernel_ms(const b2f_lor *L, double *ms)
+{
+   B2F_REQUIRE(L && ms, "b2f_lor_kernel_ms: NULL argument");
+   *ms = L->kernel_ms;
    return B2F_OK;
 }
 

@@ -757,6 +757,12 @@ class LORSparseMatrix:
     def NumNonZeroElems(self):
         return self.nnz
 
+    def kernel_ms(self):
+        """device time of the kernels of the assembly (allocations excluded)"""
+        ms = C.c_double()
+        call("b2f_lor_kernel_ms", self.h, C.byref(ms))
+        return ms.value
+
     def device_pointers(self):
         """(I, J, data) device addresses, e.g. for a multigrid set-up that takes CSR in place"""
         return self._I.value, self._J.value, self._A.value
